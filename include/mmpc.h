@@ -1,0 +1,164 @@
+/*
+ * mmpc.h -- C ABI of the B200-native batched whole-body MPC solver.
+ *
+ * This is the drop-in boundary for the ONE hot path of HsinyuG/mobile-manipulator-mpc:
+ *     MPCWholeBody.solve(x_init, traj_ref, u_ref)      controllers/mpc_wholebody_qref.py:287-331
+ * whose NLP is defined in MPCWholeBody.reset()          controllers/mpc_wholebody_qref.py:142-285
+ * (all file:line citations in this header are relative to the reference checkout).
+ *
+ * The reference has no FFI of its own (it is pure Python over the casadi wheel), so the entry
+ * points below are what a ctypes binding of that class binds -- see INTEGRATION.md for the
+ * stub a maintainer would add.  Plain pointers and sizes only; no torch types; no exceptions
+ * across the ABI.  Return value: 0 = MMPC_OK, anything else = API misuse / CUDA failure
+ * (mmpc_error_string()).  Numerical failure of an instance is NOT an error code: it is
+ * reported per instance in `status`.
+ *
+ * Batch layout ("instance-major"): every per-instance array is the reference's own NumPy
+ * array with one leading batch axis, C-contiguous, float64:
+ *     x_init [B][9]        solve() arg 1            (:287)   x y psi dx dy dpsi q1 q2 q3
+ *     x_ref  [B][N+1][9]   solve() arg 2 traj_ref   (:306)
+ *     u_ref  [B][N][5]     solve() arg 3            (:307)   dV dw dq1 dq2 dq3
+ *     u_last [B][N][5]     self.u_latest            (:295-310)  previous U*, zeros on first call
+ *     u_guess[B][N][5]     initial guess of U (NULL -> u_last, the reference behaviour :303)
+ *     circles[B][n_obs][3] or [B][N+1][n_obs][3]   Obstacles(x, y, radius)  robot_models/obstacles.py:6-10
+ *     planes [B][n_pl][6]  obstacle_manipulation_list entries (point xyz, normal xyz)  demo_wholebody_qref.py:21-33
+ *     n_pl_inst[B] int32   planes actually used by instance b (NULL -> cfg.n_pl for all)
+ *     flags  [B] uint8     bit0: terminal xy equality  interface_wholebody_qref.py:167
+ * Outputs:
+ *     U [B][N][5]  X [B][N+1][9]  s [B][N+1]   sol.value(U/X/s)   (:329-330)
+ *     cost[B]  sol.value(cost) (:317)     kkt[B]  final scaled NLP error (IPOPT E_0)
+ *     iters[B] int32   status[B] int32 (MMPC_STATUS_*)
+ */
+#ifndef MMPC_H_
+#define MMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMPC_NX 9
+#define MMPC_NU 5
+#define MMPC_MAX_PLANES 4
+
+/* return codes */
+enum {
+  MMPC_OK = 0,
+  MMPC_ERR_ARG = 1,       /* NULL pointer / bad size / B > B_max            */
+  MMPC_ERR_CUDA = 2,      /* CUDA runtime error (see mmpc_error_string)     */
+  MMPC_ERR_NO_DEVICE = 3, /* no sm_100-class CUDA device: there is NO CPU fallback */
+  MMPC_ERR_UNSUPPORTED = 4
+};
+
+/* per-instance status */
+enum {
+  MMPC_STATUS_CONVERGED = 0,   /* scaled KKT error E_0 <= tol  (IPOPT Solve_Succeeded)               */
+  MMPC_STATUS_MAX_ITER = 1,    /* iteration cap reached        (IPOPT Maximum_Iterations_Exceeded)   */
+  MMPC_STATUS_LINESEARCH = 2,  /* step size underflow          (IPOPT Restoration_Failed analogue)   */
+  MMPC_STATUS_FACTOR = 3,      /* regularisation cap reached in the Riccati factorisation            */
+  MMPC_STATUS_NAN = 4,         /* non-finite iterate                                                  */
+  MMPC_STATUS_ACCEPTABLE = 5   /* E_0 <= acceptable_tol for acceptable_iter iterations (:283-284)    */
+};
+
+/* NLP variants: SURVEY.md section 8(a) rows 7-9 */
+enum {
+  MMPC_MODE_REFERENCE = 0, /* bug-for-bug: stale plane columns, terminal self-collision on s[N-1] */
+  MMPC_MODE_CLEAN = 1      /* stage-separable: -max_j c_k[i,j] <= s_k only, terminal rows on s[N]  */
+};
+
+typedef struct MmpcConfig {
+  int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */
+  int32_t n_obs;         /* ground circles per instance                                          */
+  int32_t n_pl;          /* max planes per instance (<= MMPC_MAX_PLANES), 0 = none (:224)        */
+  int32_t mode;          /* MMPC_MODE_*                                                          */
+  int32_t obs_per_stage; /* 0: circles[B][n_obs][3]; 1: circles[B][N+1][n_obs][3] (moving)       */
+  int32_t max_iter;      /* 'ipopt.max_iter': 2000 (:280)                                        */
+  int32_t reserved0, reserved1;
+  double dt;             /* robot.dt, demo_wholebody_qref.py:10                                  */
+  double Qd[9], Pd[9], Rd[5], Wd[5], S; /* diagonals of Q,P,R,W and S (:12-16); setWeight :119   */
+  double ulim[2][5];     /* (:17)  rows: lower, upper                                            */
+  double xlim[2][9];     /* (:18-21) +-inf allowed                                               */
+  double dulim[2][5];    /* (:22)                                                                */
+  double base_radius;    /* robot_models/base.py:15                                              */
+  double self_collision_radius; /* :43 */
+  double obstacle_expand_dist;  /* :44 */
+  double tol;            /* IPOPT tol default 1e-8                                               */
+  double mu_init;        /* IPOPT mu_init default 0.1                                            */
+  double acceptable_tol; /* 'ipopt.acceptable_tol': 1e-8 (:283)                                  */
+} MmpcConfig;
+
+typedef struct MmpcBatchIn {
+  const double* x_init;
+  const double* x_ref;
+  const double* u_ref;
+  const double* u_last;
+  const double* u_guess;    /* may be NULL */
+  const double* circles;    /* may be NULL iff n_obs == 0 */
+  const double* planes;     /* may be NULL iff n_pl == 0 */
+  const int32_t* n_pl_inst; /* may be NULL */
+  const uint8_t* flags;     /* may be NULL */
+} MmpcBatchIn;
+
+typedef struct MmpcBatchOut {
+  double* U;
+  double* X;      /* may be NULL */
+  double* s;      /* may be NULL */
+  double* cost;   /* may be NULL */
+  double* kkt;    /* may be NULL */
+  int32_t* iters; /* may be NULL */
+  int32_t* status;
+} MmpcBatchOut;
+
+typedef struct MmpcHandle MmpcHandle;
+
+int mmpc_version(void);
+const char* mmpc_error_string(int code);
+
+/* Fill cfg with the reference defaults: controllers/mpc_wholebody_qref.py:11-22,43-44,280-285,
+ * N = 20 and dt = 0.1 from demo_wholebody_qref.py:10-11. */
+void mmpc_default_config(MmpcConfig* cfg);
+
+/* Replaces MPCWholeBody.__init__/reset() (:7-46,142-285): fixes the NLP shape, allocates the
+ * per-instance solver workspace for up to B_max instances on CUDA device `device`. */
+int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device, MmpcHandle** out);
+int mmpc_destroy(MmpcHandle* h);
+
+/* Replaces MPCWholeBody.setWeight (:119-139); diagonals only (every use in the reference is diagonal). */
+int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* Pd, const double* Rd,
+                     const double* Wd, double S);
+
+/* Replaces MPCWholeBody.solve (:287-331) for B independent instances.  All pointers are DEVICE
+ * pointers owned by the caller; asynchronous on `stream` (a cudaStream_t).  x_init is clipped to
+ * xlim on device exactly as :290-291 does (written back in place to in->x_init's q entries is the
+ * caller's business: the host wrapper does it). */
+int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, void* stream);
+
+/* Same, with HOST pointers: stages through pinned buffers, copies host->device, solves and
+ * copies the results back; synchronous.  This is the call the reference-facing Python class uses. */
+int mmpc_solve_host(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out);
+
+/* Model evaluation for parity tests (DEVICE pointers), M independent (x,u) pairs:
+ *   f   [M][9]   MobileManipulator.f_kinematics          robot_models/mobile_manipulator.py:57-75
+ *   fk  [M][10]  forward_tranformation: endpoint x y z psi, joint2 xyz, joint3 xyz  (:17-55)
+ *   rows[M][n_obs + 4 + 6*n_pl]  circle rows (:49-54), self-collision rows (:219-222),
+ *                plane margins c[i][j], i-major (:76-80), all evaluated at x
+ * circles [M][n_obs][3], planes [M][n_pl][6]; any output may be NULL. */
+int mmpc_eval_model(MmpcHandle* h, int32_t M, const double* x, const double* u, const double* circles,
+                    const double* planes, double* f, double* fk, double* rows, void* stream);
+
+/* Warm-start shift of an initial guess on device: u_guess[b][k] = U[b][k+1], last row repeated
+ * (north_star "shift kernel"; only the GUESS may be shifted). */
+int mmpc_shift(MmpcHandle* h, int32_t B, const double* U, double* u_guess, void* stream);
+
+/* Plant step without pybullet: x_next[b] = f_kinematics(x[b], u0[b])  interface_wholebody_qref.py:143 */
+int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const double* u0, double* x_next,
+                    void* stream);
+
+/* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
+int64_t mmpc_launch_count(const MmpcHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMPC_H_ */
