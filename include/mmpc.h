@@ -158,6 +158,13 @@ int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const double* u0,
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t mmpc_launch_count(const MmpcHandle* h);
 
+/* sizeof() of the three ABI structs, for binding self-checks. */
+int mmpc_struct_sizes(int32_t* cfg_bytes, int32_t* in_bytes, int32_t* out_bytes);
+
+/* Launch geometry chosen by mmpc_create: SM count, resident warps (= instances) per SM and the
+ * dynamic shared memory one instance occupies. */
+int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* blocks_per_sm, int32_t* smem_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+"""Loader of the CUDA shared library (libmmpc_b200.so) behind include/mmpc.h.
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``build_library()``.  There is no
+CPU fallback: if the library is missing or no B200-class device is present, every compute entry
+point raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+from . import _abi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmmpc_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_solver.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+_lib = None
+
+
+class MmpcError(RuntimeError):
+    pass
+
+
+def build_library(force=False, verbose=False):
+    """nvcc-compile csrc/ into libmmpc_b200.so for sm_100a (cross-compiles without a GPU)."""
+    src_time = max(os.path.getmtime(s) for s in SOURCES + [os.path.join(_PKG, "..", "include", "mmpc.h")])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= src_time:
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    subprocess.check_call(cmd, cwd=os.path.join(_PKG, "csrc"))
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MmpcError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dp = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    L.mmpc_version.restype = C.c_int
+    L.mmpc_error_string.restype = C.c_char_p
+    L.mmpc_error_string.argtypes = [C.c_int]
+    L.mmpc_default_config.argtypes = [C.POINTER(_abi.MmpcConfig)]
+    L.mmpc_default_config.restype = None
+    L.mmpc_struct_sizes.argtypes = [C.POINTER(i32)] * 3
+    L.mmpc_create.argtypes = [C.POINTER(_abi.MmpcConfig), i32, i32, C.POINTER(vp)]
+    L.mmpc_destroy.argtypes = [vp]
+    L.mmpc_set_weights.argtypes = [vp, dp, dp, dp, dp, C.c_double]
+    L.mmpc_solve.argtypes = [vp, i32, C.POINTER(_abi.MmpcBatchIn), C.POINTER(_abi.MmpcBatchOut), vp]
+    L.mmpc_solve_host.argtypes = [vp, i32, C.POINTER(_abi.MmpcBatchIn), C.POINTER(_abi.MmpcBatchOut)]
+    L.mmpc_eval_model.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, vp]
+    L.mmpc_shift.argtypes = [vp, i32, dp, dp, vp]
+    L.mmpc_plant_step.argtypes = [vp, i32, dp, dp, dp, vp]
+    L.mmpc_launch_count.argtypes = [vp]
+    L.mmpc_launch_count.restype = i64
+    L.mmpc_occupancy.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    a, b, c = i32(), i32(), i32()
+    L.mmpc_struct_sizes(C.byref(a), C.byref(b), C.byref(c))
+    if (a.value, b.value, c.value) != (C.sizeof(_abi.MmpcConfig), C.sizeof(_abi.MmpcBatchIn), C.sizeof(_abi.MmpcBatchOut)):
+        raise MmpcError("ABI mismatch between _abi.py and libmmpc_b200.so")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != _abi.OK:
+        raise MmpcError(f"mmpc error {rc}: {lib().mmpc_error_string(rc).decode()}")
+
+
+EXPORTS = ("mmpc_version", "mmpc_error_string", "mmpc_default_config", "mmpc_create", "mmpc_destroy",
+           "mmpc_set_weights", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
+           "mmpc_plant_step", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy")

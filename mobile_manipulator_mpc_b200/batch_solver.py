@@ -1,0 +1,207 @@
+"""BatchSolver: thin Python host over the C ABI (include/mmpc.h) for B independent instances of
+the whole-body MPC NLP of MPCWholeBody (controllers/mpc_wholebody_qref.py:142-331 in the reference).
+
+Two call paths, both into the same CUDA kernel:
+  * ``solve_host(batch)``    NumPy in / NumPy out (mmpc_solve_host: pinned staging, H2D, solve, D2H)
+  * ``solve_device(batch)``  torch CUDA tensors in / out, asynchronous on torch's current stream
+torch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._lib import MmpcError, check, lib
+
+_IN_KEYS = ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")
+_OUT_KEYS = ("U", "X", "s", "cost", "kkt", "iters", "status")
+
+
+def _diag(M, n, name):
+    M = np.asarray(M, dtype=np.float64)
+    if M.ndim == 2:
+        if M.shape != (n, n):
+            raise ValueError(f"{name} must be {n}x{n}")
+        if np.any(M - np.diag(np.diag(M)) != 0):
+            raise NotImplementedError(f"{name}: only diagonal weight matrices are supported "
+                                      "(every use in the reference is diagonal)")
+        M = np.diag(M)
+    M = np.ascontiguousarray(M.reshape(-1))
+    if M.size != n:
+        raise ValueError(f"{name} must have {n} diagonal entries")
+    return M
+
+
+class BatchSolver:
+    def __init__(self, N=20, dt=0.1, n_obs=3, n_pl=3, B_max=1, mode=_abi.MODE_CLEAN, device=0,
+                 obs_per_stage=False, cfg=None, **overrides):
+        if cfg is None:
+            cfg = _abi.default_config(N=N, dt=dt, n_obs=n_obs, n_pl=n_pl, mode=mode)
+            cfg.obs_per_stage = int(bool(obs_per_stage))
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.B_max = int(B_max)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        check(lib().mmpc_create(C.byref(cfg), self.B_max, self.device, C.byref(self._h)))
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().mmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def N(self):
+        return self.cfg.N
+
+    def occupancy(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().mmpc_occupancy(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(sm_count=a.value, instances_per_sm=b.value, smem_bytes=c.value)
+
+    def launch_count(self):
+        return int(lib().mmpc_launch_count(self._h))
+
+    # -- weights: MPCWholeBody.setWeight (:119-139) ----------------------------------------------
+    def set_weights(self, Q=None, R=None, P=None, S=None, W=None):
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        Qd = None if Q is None else _diag(Q, 9, "Q")
+        Pd = None if P is None else _diag(P, 9, "P")
+        Rd = None if R is None else _diag(R, 5, "R")
+        Wd = None if W is None else _diag(W, 5, "W")
+        Sv = float("nan") if S is None else float(np.asarray(S).reshape(-1)[0])
+        check(lib().mmpc_set_weights(self._h, ptr(Qd), ptr(Pd), ptr(Rd), ptr(Wd), Sv))
+        for name, v in (("Qd", Qd), ("Pd", Pd), ("Rd", Rd), ("Wd", Wd)):
+            if v is not None:
+                getattr(self.cfg, name)[:] = list(v)
+        if S is not None:
+            self.cfg.S = Sv
+
+    # -- host path --------------------------------------------------------------------------------
+    def _shapes(self, B):
+        N, c = self.cfg.N, self.cfg
+        circ = (B, N + 1, c.n_obs, 3) if c.obs_per_stage else (B, c.n_obs, 3)
+        return dict(x_init=(B, 9), x_ref=(B, N + 1, 9), u_ref=(B, N, 5), u_last=(B, N, 5), u_guess=(B, N, 5),
+                    circles=circ, planes=(B, c.n_pl, 6))
+
+    def solve_host(self, batch, want=("X", "s", "cost", "kkt", "iters")):
+        B = int(np.asarray(batch["x_init"]).shape[0])
+        if B > self.B_max:
+            raise ValueError(f"B={B} exceeds B_max={self.B_max}")
+        shp = self._shapes(B)
+        keep = []
+        ptrs = []
+        for k in _IN_KEYS:
+            a = batch.get(k)
+            if a is None or (k == "circles" and self.cfg.n_obs == 0) or (k == "planes" and self.cfg.n_pl == 0):
+                ptrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != shp[k]:
+                raise ValueError(f"{k}: expected shape {shp[k]}, got {a.shape}")
+            keep.append(a)
+            ptrs.append(a.ctypes.data_as(C.c_void_p))
+        npl = batch.get("n_pl_inst")
+        if npl is not None:
+            npl = np.ascontiguousarray(npl, dtype=np.int32); keep.append(npl)
+        flags = batch.get("flags")
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8); keep.append(flags)
+        bi = _abi.MmpcBatchIn(*ptrs, _abi.ptr(npl), _abi.ptr(flags))
+        N = self.cfg.N
+        out = dict(U=np.empty((B, N, 5)), status=np.empty(B, np.int32))
+        full = dict(X=(B, N + 1, 9), s=(B, N + 1), cost=(B,), kkt=(B,))
+        for k in want:
+            out[k] = np.empty(B, np.int32) if k == "iters" else np.empty(full[k])
+        bo = _abi.MmpcBatchOut(*[_abi.ptr(out.get(k)) for k in _OUT_KEYS])
+        check(lib().mmpc_solve_host(self._h, B, C.byref(bi), C.byref(bo)))
+        return out
+
+    # -- device path --------------------------------------------------------------------------------
+    def solve_device(self, batch, out=None, want=("X", "s", "cost", "kkt", "iters")):
+        """torch CUDA float64 tensors in ``batch``; returns dict of torch tensors (async)."""
+        import torch
+        x0 = batch["x_init"]
+        B = int(x0.shape[0])
+        if B > self.B_max:
+            raise ValueError(f"B={B} exceeds B_max={self.B_max}")
+        dev = x0.device
+        if dev.type != "cuda" or dev.index != self.device:
+            raise MmpcError(f"solve_device needs CUDA tensors on device {self.device}")
+        shp = self._shapes(B)
+        ptrs = []
+        for k in _IN_KEYS:
+            a = batch.get(k)
+            if a is None or (k == "circles" and self.cfg.n_obs == 0) or (k == "planes" and self.cfg.n_pl == 0):
+                ptrs.append(None)
+                continue
+            if a.dtype != torch.float64 or not a.is_contiguous() or tuple(a.shape) != shp[k]:
+                raise ValueError(f"{k}: need contiguous float64 tensor of shape {shp[k]}")
+            ptrs.append(C.c_void_p(a.data_ptr()))
+        npl, flags = batch.get("n_pl_inst"), batch.get("flags")
+        bi = _abi.MmpcBatchIn(*ptrs, None if npl is None else C.c_void_p(npl.data_ptr()),
+                              None if flags is None else C.c_void_p(flags.data_ptr()))
+        N = self.cfg.N
+        if out is None:
+            out = dict(U=torch.empty((B, N, 5), dtype=torch.float64, device=dev),
+                       status=torch.empty(B, dtype=torch.int32, device=dev))
+            full = dict(X=(B, N + 1, 9), s=(B, N + 1), cost=(B,), kkt=(B,))
+            for k in want:
+                out[k] = (torch.empty(B, dtype=torch.int32, device=dev) if k == "iters"
+                          else torch.empty(full[k], dtype=torch.float64, device=dev))
+        bo = _abi.MmpcBatchOut(*[None if out.get(k) is None else C.c_void_p(out[k].data_ptr()) for k in _OUT_KEYS])
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(lib().mmpc_solve(self._h, B, C.byref(bi), C.byref(bo), stream))
+        return out
+
+    def to_device(self, batch):
+        import torch
+        dev = torch.device("cuda", self.device)
+        out = {}
+        for k, v in batch.items():
+            if isinstance(v, np.ndarray) and k in _IN_KEYS:
+                out[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
+            elif k == "n_pl_inst" and v is not None:
+                out[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.int32)).to(dev)
+            elif k == "flags" and v is not None:
+                out[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.uint8)).to(dev)
+        return out
+
+    # -- model evaluation, shift, plant (device tensors) ------------------------------------------------
+    def eval_model(self, x, u=None, circles=None, planes=None):
+        import torch
+        M = int(x.shape[0])
+        dev = x.device
+        c = self.cfg
+        f = torch.empty((M, 9), dtype=torch.float64, device=dev)
+        fk = torch.empty((M, 10), dtype=torch.float64, device=dev)
+        rows = None
+        if (c.n_obs == 0 or circles is not None) and (c.n_pl == 0 or planes is not None):
+            rows = torch.empty((M, c.n_obs + 4 + 6 * c.n_pl), dtype=torch.float64, device=dev)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(lib().mmpc_eval_model(self._h, M, p(x), p(u), p(circles), p(planes), p(f), p(fk), p(rows), stream))
+        return f, fk, rows
+
+    def shift(self, U):
+        import torch
+        ug = torch.empty_like(U)
+        stream = C.c_void_p(torch.cuda.current_stream(U.device).cuda_stream)
+        check(lib().mmpc_shift(self._h, int(U.shape[0]), C.c_void_p(U.data_ptr()), C.c_void_p(ug.data_ptr()), stream))
+        return ug
+
+    def plant_step(self, x, u0):
+        import torch
+        xn = torch.empty_like(x)
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        check(lib().mmpc_plant_step(self._h, int(x.shape[0]), C.c_void_p(x.data_ptr()), C.c_void_p(u0.data_ptr()),
+                                    C.c_void_p(xn.data_ptr()), stream))
+        return xn

@@ -1,0 +1,334 @@
+// mmpc_api.cu -- host side of the C ABI declared in include/mmpc.h (sm_100a only).
+// No torch types, no exceptions across the boundary, no CPU fallback: every entry point that
+// computes needs a CUDA device and fails with MMPC_ERR_NO_DEVICE / MMPC_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/mmpc.h"
+#include "mmpc_solver.cuh"
+
+using namespace mmpc;
+
+struct MmpcHandle {
+  MmpcConfig cfg;
+  int device, B_max, sm_count, blocks_per_sm, slots;
+  int SP, KP, R;
+  size_t smem_bytes;
+  long long ws_stride;
+  double* ws;
+  unsigned* counter;
+  long long launches;
+  // staging for mmpc_solve_host
+  struct { double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes, *U, *X, *s, *cost, *kkt;
+           int32_t *n_pl_inst, *iters, *status; uint8_t* flags; } d, h;
+  cudaStream_t stream;
+  char err[256];
+};
+
+static thread_local char g_err[256] = "";
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      snprintf(g_err, sizeof g_err, "%s failed: %s", #call, cudaGetErrorString(e_));               \
+      return MMPC_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+extern "C" int mmpc_version(void) { return 100; }
+
+extern "C" const char* mmpc_error_string(int code) {
+  switch (code) {
+    case MMPC_OK: return "ok";
+    case MMPC_ERR_ARG: return "invalid argument";
+    case MMPC_ERR_CUDA: return g_err[0] ? g_err : "CUDA error";
+    case MMPC_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case MMPC_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+extern "C" void mmpc_default_config(MmpcConfig* c) {
+  memset(c, 0, sizeof *c);
+  c->N = 20; c->n_obs = 3; c->n_pl = 3; c->mode = MMPC_MODE_REFERENCE; c->obs_per_stage = 0; c->max_iter = 2000;
+  c->dt = 0.1;
+  const double q[9] = {25, 25, 0, 0, 0, 5, 5, 5, 5};
+  const double r[5] = {0.1, 0.1, 0, 0, 0}, w[5] = {0, 0, 0.1, 0.1, 0.1};
+  for (int i = 0; i < 9; ++i) c->Qd[i] = c->Pd[i] = q[i];
+  for (int j = 0; j < 5; ++j) { c->Rd[j] = r[j]; c->Wd[j] = w[j]; }
+  c->S = 1e5;
+  const double pi = 3.14159265358979323846, inf = INFINITY;
+  const double ul[5] = {2, pi, 1, 1, 1};
+  for (int j = 0; j < 5; ++j) { c->ulim[0][j] = -ul[j]; c->ulim[1][j] = ul[j]; }
+  const double xl[9] = {-100, -100, -inf, -2, -2, -pi, -pi / 2, -pi, 0}, xh[9] = {100, 100, inf, 2, 2, pi, pi / 2, 0, 3 * pi / 2};
+  for (int i = 0; i < 9; ++i) { c->xlim[0][i] = xl[i]; c->xlim[1][i] = xh[i]; }
+  const double dl[5] = {inf, inf, 0.5, 0.5, 0.5};
+  for (int j = 0; j < 5; ++j) { c->dulim[0][j] = -dl[j]; c->dulim[1][j] = dl[j]; }
+  c->base_radius = 0.4; c->self_collision_radius = 0.05; c->obstacle_expand_dist = 0.03;
+  c->tol = 1e-8; c->mu_init = 0.1; c->acceptable_tol = 1e-8;
+}
+
+extern "C" int mmpc_struct_sizes(int32_t* cfg_bytes, int32_t* in_bytes, int32_t* out_bytes) {
+  *cfg_bytes = (int32_t)sizeof(MmpcConfig); *in_bytes = (int32_t)sizeof(MmpcBatchIn); *out_bytes = (int32_t)sizeof(MmpcBatchOut);
+  return MMPC_OK;
+}
+
+static size_t circles_per_instance(const MmpcConfig& c) { return (size_t)c.n_obs * 3 * (c.obs_per_stage ? c.N + 1 : 1); }
+
+extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device, MmpcHandle** out) {
+  if (!cfg || !out || B_max < 1) return MMPC_ERR_ARG;
+  if (cfg->N < 1 || cfg->N > 63 || cfg->n_obs < 0 || cfg->n_pl < 0 || cfg->n_pl > MMPC_MAX_PLANES) return MMPC_ERR_ARG;
+  if (cfg->mode != MMPC_MODE_CLEAN && cfg->mode != MMPC_MODE_REFERENCE) return MMPC_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MMPC_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) return MMPC_ERR_ARG;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return MMPC_ERR_CUDA;
+  }
+  MmpcHandle* h = new (std::nothrow) MmpcHandle();
+  if (!h) return MMPC_ERR_ARG;
+  memset(h, 0, sizeof *h);
+  h->cfg = *cfg; h->device = device; h->B_max = B_max; h->sm_count = prop.multiProcessorCount;
+  int N = cfg->N;
+  h->SP = N + 1; h->KP = ((N + 1 + 3) / 4) * 4; h->R = cfg->n_obs + 4 + (cfg->n_pl > 0 ? 6 : 0);
+  h->smem_bytes = (size_t)smem_doubles(N) * sizeof(double);
+  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, solve_kernel, 32, h->smem_bytes));
+  if (h->blocks_per_sm < 1) { snprintf(g_err, sizeof g_err, "solve_kernel does not fit on an SM (smem %zu B)", h->smem_bytes); return MMPC_ERR_CUDA; }
+  h->slots = h->sm_count * h->blocks_per_sm;
+  h->ws_stride = ws_doubles(N, h->KP, h->R);
+  CK(cudaMalloc(&h->ws, (size_t)h->slots * h->ws_stride * sizeof(double)));
+  CK(cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * sizeof(double)));
+  CK(cudaMalloc(&h->counter, sizeof(unsigned)));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  *out = h;
+  return MMPC_OK;
+}
+
+static void free_staging(MmpcHandle* h) {
+  void** dp = (void**)&h->d; void** hp = (void**)&h->h;
+  for (size_t i = 0; i < sizeof(h->d) / sizeof(void*); ++i) {
+    if (dp[i]) cudaFree(dp[i]);
+    if (hp[i]) cudaFreeHost(hp[i]);
+    dp[i] = hp[i] = nullptr;
+  }
+}
+
+extern "C" int mmpc_destroy(MmpcHandle* h) {
+  if (!h) return MMPC_ERR_ARG;
+  cudaSetDevice(h->device);
+  free_staging(h);
+  if (h->ws) cudaFree(h->ws);
+  if (h->counter) cudaFree(h->counter);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* Pd, const double* Rd, const double* Wd, double S) {
+  if (!h) return MMPC_ERR_ARG;
+  if (Qd) memcpy(h->cfg.Qd, Qd, sizeof h->cfg.Qd);
+  if (Pd) memcpy(h->cfg.Pd, Pd, sizeof h->cfg.Pd);
+  if (Rd) memcpy(h->cfg.Rd, Rd, sizeof h->cfg.Rd);
+  if (Wd) memcpy(h->cfg.Wd, Wd, sizeof h->cfg.Wd);
+  if (S == S && S > 0) h->cfg.S = S;
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, void* stream) {
+  if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
+  if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
+  if ((h->cfg.n_obs > 0 && !in->circles) || (h->cfg.n_pl > 0 && !in->planes)) return MMPC_ERR_ARG;
+  if (h->cfg.mode != MMPC_MODE_CLEAN) return MMPC_ERR_UNSUPPORTED;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  KParams P; memset(&P, 0, sizeof P);
+  P.cfg = h->cfg; P.B = B;
+  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
+  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
+  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  P.ws = h->ws; P.ws_stride = h->ws_stride; P.counter = h->counter;
+  P.SP = h->SP; P.KP = h->KP; P.R = h->R;
+  CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
+  int grid = B < h->slots ? B : h->slots;
+  solve_kernel<<<grid, 32, h->smem_bytes, st>>>(P);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
+template <class T>
+static int stage_alloc(T** d, T** hp, size_t n) {
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void**)d, n * sizeof(T)));
+  CK(cudaMallocHost((void**)hp, n * sizeof(T)));
+  return MMPC_OK;
+}
+
+static int ensure_staging(MmpcHandle* h) {
+  if (h->d.x_init) return MMPC_OK;
+  size_t B = h->B_max, N = h->cfg.N;
+  int rc;
+#define SA(name, n) if ((rc = stage_alloc(&h->d.name, &h->h.name, (n))) != MMPC_OK) return rc
+  SA(x_init, B * 9); SA(x_ref, B * (N + 1) * 9); SA(u_ref, B * N * 5); SA(u_last, B * N * 5); SA(u_guess, B * N * 5);
+  SA(circles, B * circles_per_instance(h->cfg)); SA(planes, B * (size_t)h->cfg.n_pl * 6);
+  SA(U, B * N * 5); SA(X, B * (N + 1) * 9); SA(s, B * (N + 1)); SA(cost, B); SA(kkt, B);
+  SA(n_pl_inst, B); SA(iters, B); SA(status, B); SA(flags, B);
+#undef SA
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_solve_host(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out) {
+  if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
+  if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc != MMPC_OK) return rc;
+  size_t N = h->cfg.N, b = B;
+  cudaStream_t st = h->stream;
+  MmpcBatchIn din; memset(&din, 0, sizeof din);
+  MmpcBatchOut dout; memset(&dout, 0, sizeof dout);
+#define UP(name, n, T)                                                                       \
+  if (in->name) {                                                                            \
+    memcpy(h->h.name, in->name, (n) * sizeof(T));                                            \
+    CK(cudaMemcpyAsync(h->d.name, h->h.name, (n) * sizeof(T), cudaMemcpyHostToDevice, st));  \
+    din.name = h->d.name;                                                                    \
+  }
+  UP(x_init, b * 9, double); UP(x_ref, b * (N + 1) * 9, double); UP(u_ref, b * N * 5, double);
+  UP(u_last, b * N * 5, double); UP(u_guess, b * N * 5, double);
+  UP(circles, b * circles_per_instance(h->cfg), double); UP(planes, b * (size_t)h->cfg.n_pl * 6, double);
+  UP(n_pl_inst, b, int32_t); UP(flags, b, uint8_t);
+#undef UP
+  dout.U = h->d.U; dout.status = h->d.status;
+  if (out->X) dout.X = h->d.X;
+  if (out->s) dout.s = h->d.s;
+  if (out->cost) dout.cost = h->d.cost;
+  if (out->kkt) dout.kkt = h->d.kkt;
+  if (out->iters) dout.iters = h->d.iters;
+  rc = mmpc_solve(h, B, &din, &dout, st);
+  if (rc != MMPC_OK) return rc;
+#define DOWN(name, n, T) if (out->name) CK(cudaMemcpyAsync(h->h.name, h->d.name, (n) * sizeof(T), cudaMemcpyDeviceToHost, st))
+  DOWN(U, b * N * 5, double); DOWN(X, b * (N + 1) * 9, double); DOWN(s, b * (N + 1), double);
+  DOWN(cost, b, double); DOWN(kkt, b, double); DOWN(iters, b, int32_t); DOWN(status, b, int32_t);
+#undef DOWN
+  CK(cudaStreamSynchronize(st));
+#define OUTC(name, n, T) if (out->name) memcpy(out->name, h->h.name, (n) * sizeof(T))
+  OUTC(U, b * N * 5, double); OUTC(X, b * (N + 1) * 9, double); OUTC(s, b * (N + 1), double);
+  OUTC(cost, b, double); OUTC(kkt, b, double); OUTC(iters, b, int32_t); OUTC(status, b, int32_t);
+#undef OUTC
+  return MMPC_OK;
+}
+
+// ---- model evaluation / shift / plant step: one thread per instance ----------------------------
+__global__ void eval_model_kernel(MmpcConfig cfg, int M, const double* x, const double* u, const double* circles,
+                                  const double* planes, double* fo, double* fko, double* rows) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double xs[NX], us[NU] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < NX; ++i) xs[i] = x[(size_t)m * NX + i];
+  if (u) for (int j = 0; j < NU; ++j) us[j] = u[(size_t)m * NU + j];
+  FK f; fk_eval(xs[2], xs[6], xs[7], xs[8], f);
+  if (fo) { double xn[NX]; dyn_f(xs, us, cfg.dt, f.cp, f.sp, xn); for (int i = 0; i < NX; ++i) fo[(size_t)m * NX + i] = xn[i]; }
+  if (fko) {
+    Point e, j2, j3;
+    point_eval(xs[0], xs[1], f, BODY[5], e); point_eval(xs[0], xs[1], f, BODY[1], j2); point_eval(xs[0], xs[1], f, BODY[3], j3);
+    double* o = fko + (size_t)m * 10;
+    o[0] = e.P[0]; o[1] = e.P[1]; o[2] = e.P[2]; o[3] = xs[2];
+    o[4] = j2.P[0]; o[5] = j2.P[1]; o[6] = j2.P[2]; o[7] = j3.P[0]; o[8] = j3.P[1]; o[9] = j3.P[2];
+  }
+  if (rows) {
+    int nr = cfg.n_obs + 4 + 6 * cfg.n_pl;
+    double* o = rows + (size_t)m * nr;
+    for (int i = 0; i < cfg.n_obs; ++i) {
+      const double* c = circles + ((size_t)m * cfg.n_obs + i) * 3;
+      double dx = xs[0] - c[0], dy = xs[1] - c[1];
+      o[i] = (c[2] + cfg.base_radius) - sqrt(dx * dx + dy * dy);
+    }
+    for (int q = 0; q < 4; ++q) {
+      Point p; point_eval(xs[0], xs[1], f, SELFD[q], p);
+      o[cfg.n_obs + q] = cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]);
+    }
+    for (int i = 0; i < 6; ++i) {
+      Point p; point_eval(xs[0], xs[1], f, BODY[i], p);
+      for (int j = 0; j < cfg.n_pl; ++j) {
+        const double* pl = planes + ((size_t)m * cfg.n_pl + j) * 6;
+        double c = 0;
+        for (int a = 0; a < 3; ++a) c += pl[3 + a] * ((pl[a] - cfg.obstacle_expand_dist * pl[3 + a]) - p.P[a]);
+        o[cfg.n_obs + 4 + i * cfg.n_pl + j] = c;
+      }
+    }
+  }
+}
+
+extern "C" int mmpc_eval_model(MmpcHandle* h, int32_t M, const double* x, const double* u, const double* circles,
+                               const double* planes, double* f, double* fk, double* rows, void* stream) {
+  if (!h || !x || M < 0) return MMPC_ERR_ARG;
+  if (rows && ((h->cfg.n_obs > 0 && !circles) || (h->cfg.n_pl > 0 && !planes))) return MMPC_ERR_ARG;
+  if (M == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  eval_model_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cfg, M, x, u, circles, planes, f, fk, rows);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
+__global__ void shift_kernel(int B, int N, const double* U, double* ug) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)B * N * NU;
+  if (i >= tot) return;
+  int j = (int)(i % NU); long long r = i / NU; int k = (int)(r % N); long long b = r / N;
+  int ks = k + 1 < N ? k + 1 : N - 1;
+  ug[i] = U[(b * N + ks) * NU + j];
+}
+
+extern "C" int mmpc_shift(MmpcHandle* h, int32_t B, const double* U, double* u_guess, void* stream) {
+  if (!h || !U || !u_guess || B < 0) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  long long tot = (long long)B * h->cfg.N * NU;
+  shift_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, h->cfg.N, U, u_guess);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
+__global__ void plant_kernel(int B, double dt, const double* x, const double* u0, double* xn) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double xs[NX], us[NU], o[NX];
+  for (int i = 0; i < NX; ++i) xs[i] = x[(size_t)b * NX + i];
+  for (int j = 0; j < NU; ++j) us[j] = u0[(size_t)b * NU + j];
+  double sp, cp; sincos(xs[2], &sp, &cp);
+  dyn_f(xs, us, dt, cp, sp, o);
+  for (int i = 0; i < NX; ++i) xn[(size_t)b * NX + i] = o[i];
+}
+
+extern "C" int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const double* u0, double* x_next, void* stream) {
+  if (!h || !x || !u0 || !x_next || B < 0) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  plant_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, h->cfg.dt, x, u0, x_next);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
+extern "C" int64_t mmpc_launch_count(const MmpcHandle* h) { return h ? h->launches : 0; }
+
+extern "C" int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* blocks_per_sm, int32_t* smem_bytes) {
+  if (!h) return MMPC_ERR_ARG;
+  if (sm_count) *sm_count = h->sm_count;
+  if (blocks_per_sm) *blocks_per_sm = h->blocks_per_sm;
+  if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
+  return MMPC_OK;
+}

@@ -497,7 +497,8 @@ static int riccati(Work* w, double reg) {
   const double* HN = w->H + (size_t)N * NY * NY;
   for (int a = 0; a < NXA; ++a) {
     for (int b = 0; b < NXA; ++b) PN[a * NXA + b] = HN[a * NY + b];
-    PN[a * NXA + a] += reg; pN[a] = w->g[N * NY + a];
+    if (a != IS) PN[a * NXA + a] += reg; /* s_k is never regularised: its pivot 2S + sum(sigma) is always positive */
+    pN[a] = w->g[N * NY + a];
   }
   for (int k = N - 1; k >= 0; --k) {
     double A[NX][NX], B[NX][NU];
@@ -517,7 +518,7 @@ static int riccati(Work* w, double reg) {
     const double* H = w->H + (size_t)k * NY * NY;
     for (int a = 0; a < NY; ++a) {
       for (int b = 0; b < NY; ++b) { double s = H[a * NY + b]; for (int r = 0; r < NXA; ++r) s += G[r][a] * PG[r][b]; M[a][b] = s; }
-      if (a != IV) M[a][a] += reg;
+      if (a != IV && a != IS) M[a][a] += reg;
       double s = w->g[k * NY + a]; for (int r = 0; r < NXA; ++r) s += G[r][a] * pd[r]; mv[a] = s;
     }
     double Muu[NUA][NUA], L[NUA][NUA];

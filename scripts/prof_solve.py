@@ -1,0 +1,16 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from mobile_manipulator_mpc_b200 import scenarios
+from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+cid = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+b = scenarios.make_batch(cid, B)
+S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B, obs_per_stage=b["obs_per_stage"])
+d = S.to_device(b)
+out = None
+for r in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out = S.solve_device(d, out=out); e1.record(); torch.cuda.synchronize()
+    print("rep", r, "ms", e0.elapsed_time(e1), "converged", int((out["status"] == 0).sum()), "iters sum", int(out["iters"].sum()))

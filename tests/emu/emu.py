@@ -1,0 +1,37 @@
+"""TEST INFRASTRUCTURE: ctypes front-end of the CPU lane emulator of the solver kernel."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mobile_manipulator_mpc_b200 import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+        _LIB = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu.so"))
+        _LIB.mmpc_emu_solve.argtypes = [C.POINTER(_abi.MmpcConfig), C.c_int32, C.POINTER(_abi.MmpcBatchIn),
+                                        C.POINTER(_abi.MmpcBatchOut)]
+    return _LIB
+
+
+def solve(batch, cfg):
+    B = batch["x_init"].shape[0]
+    N = cfg.N
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    arrs = {k: f(batch.get(k)) for k in ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")}
+    npl = batch.get("n_pl_inst")
+    npl = None if npl is None else np.ascontiguousarray(npl, dtype=np.int32)
+    bi = _abi.MmpcBatchIn(*[_abi.ptr(arrs[k]) for k in ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")],
+                          _abi.ptr(npl), None)
+    out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
+               kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
+    bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])
+    assert lib().mmpc_emu_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo)) == 0
+    return out
