@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched whole-body MPC solver (BASELINE.json metric:
+"converged MPC solves/sec (batch 65,536)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" = one batched MPCWholeBody.solve over B independent instances of BASELINE config 3's
+shape (mixed scenarios 1/2, 16 random circles, horizon 20), cold start.  Weak scaling: every rank
+solves its own B instances (no data-path collective; NCCL only reduces the statistics).
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every definition used here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "converged_mpc_solves_per_sec"
+UNIT = "solves/s"
+
+
+def flops_per_iteration(N, n_obs, n_pl):
+    """Algorithmic FP64 flops of ONE interior-point iteration of one instance:
+    N dense Riccati stages (nx=9, nu=5: 4,871 flop, Frison-Jorgensen count) + (N+1) stage
+    evaluations (1,290 + 40 per circle + 122 per plane row, 6 plane rows in the clean NLP)."""
+    c_ric = 4871
+    c_eval = 1290 + 40 * n_obs + 122 * 6 * (n_pl > 0)
+    return N * c_ric + (N + 1) * c_eval
+
+
+def bytes_per_solve(N, n_obs, n_pl):
+    """Algorithmic HBM bytes of one solve (inputs read once, outputs written once)."""
+    din = 9 + (N + 1) * 9 + N * 5 + N * 5 + n_obs * 3 + n_pl * 6
+    dout = N * 5 + (N + 1) * 9 + (N + 1) + 3
+    return 8 * (din + dout)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_workload(B, seed):
+    from mobile_manipulator_mpc_b200 import scenarios
+    return scenarios.make_batch(3, B, seed=seed)
+
+
+def cpu_baseline(batch, sample, threads):
+    """Oracle port (oracle/mmpc_oracle.c) on the host cores, bounded sample of the same workload."""
+    from oracle import solver as osolver
+    from mobile_manipulator_mpc_b200 import _abi
+    sub = {k: (v[:sample] if isinstance(v, np.ndarray) else v) for k, v in batch.items()}
+    osolver.lib()
+    t = time.perf_counter()
+    o = osolver.solve(sub, mode=_abi.MODE_CLEAN, threads=threads)
+    dt = time.perf_counter() - t
+    conv = int((o["status"] == 0).sum())
+    return conv / dt, conv, dt, o
+
+
+def run_reference(args):
+    """--impl reference: the reference path on the host cores.  CasADi/IPOPT cannot be installed in
+    this image (no wheel, no network), so this arm times the oracle port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.ref_sample
+    batch = make_workload(max(sample, 64), seed=3)
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, conv, dt, _ = cpu_baseline(batch, sample, cores)
+        if i >= args.warmup:
+            vals.append(v); times.append(dt)
+    value = float(np.mean(vals))
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=float(np.mean(times) * 1e3), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload="BASELINE config 3 shape: mixed scenarios 1/2, 16 circles, N=20, cold start",
+                            batch_per_step=sample, horizon=20, n_obs=16, nlp="clean"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{sample} instances per step, oracle/mmpc_oracle.c over {cores} threads; "
+                                         "CasADi/IPOPT not installable in this image"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=65536, help="instances per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--ref-sample", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from mobile_manipulator_mpc_b200 import _abi
+    from mobile_manipulator_mpc_b200._lib import lib, check
+    from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    batch = make_workload(B, seed=3 + 1000 * rank)
+    N, n_obs, n_pl = batch["N"], batch["n_obs"], batch["n_pl"]
+    S = BatchSolver(N=N, dt=batch["dt"], n_obs=n_obs, n_pl=n_pl, B_max=B, device=local)
+    dev_in = S.to_device(batch)
+    out = S.solve_device(dev_in)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ----
+    l0 = S.launch_count()
+    for _ in range(args.warmup):
+        out = S.solve_device(dev_in, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l1 = S.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_all0.record()
+    for a, b in ev:
+        a.record(); out = S.solve_device(dev_in, out=out); b.record()
+    e_all1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = S.launch_count() - l1
+    total_ms = e_all0.elapsed_time(e_all1)
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    conv = int((out["status"] == 0).sum().item())
+    iters_sum = int(out["iters"].sum().item())
+    npl_inst = batch["n_pl_inst"]
+    work_flops = float(sum(flops_per_iteration(N, n_obs, int(p)) * int(i)
+                           for p, i in zip(npl_inst, out["iters"].cpu().numpy())))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    c = torch.tensor([conv, iters_sum, B], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    total_ms_max = float(t.item())
+    conv_all, iters_all, B_all = (float(v) for v in c.tolist())
+    value = conv_all * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    out_h = S.solve_host(batch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_h = S.solve_host(batch)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ce = torch.tensor([float((out_h["status"] == 0).sum())], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    e2e_value = float(ce.item()) * args.steps / float(te.item())
+    h2d = sum(np.asarray(batch[k]).nbytes for k in ("x_init", "x_ref", "u_ref", "u_last", "circles", "planes", "n_pl_inst"))
+    d2h = sum(v.nbytes for v in out_h.values())
+
+    # ---- NCCL gather of the per-instance result (u0, status): statistics only, outside the solve ----
+    gathered = None
+    if dist is not None:
+        u0 = out["U"][:, 0, :].contiguous()
+        allu0 = torch.empty((world * B, 5), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allu0, u0)
+        gathered = int(allu0.shape[0])
+
+    if rank == 0:
+        fp64 = C.c_double()
+        check(lib().mmpc_bench_fp64(local, C.byref(fp64)))
+        kms = float(np.mean(kern_ms))
+        achieved_tf = work_flops / (kms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_ach = bytes_per_solve(N, n_obs, n_pl) * B / (kms * 1e-3) / 1e9
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload="BASELINE config 3 shape: batch %d per GPU, mixed scenarios 1/2 (n_pl 3/2), "
+                                         "16 random circles, N=20, dt=0.1, cold start (u_last=0)" % B,
+                                batch_per_gpu=B, horizon=N, n_obs=n_obs, n_pl_max=n_pl, nlp="clean",
+                                l2_policy="inputs+outputs %.0f MB per step exceed the 126 MB L2" % ((h2d + d2h) / 1e6),
+                                converged_fraction=conv_all / B_all, mean_iterations=iters_all / B_all,
+                                instances_per_sm=S.occupancy()["instances_per_sm"]),
+                    clocks=clocks, gpu_launches=int(launches),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
+                    roofline=dict(bound="fp64", achieved=achieved_tf, peak=float(fp64.value), unit="TFLOP/s",
+                                  frac=achieved_tf / float(fp64.value), traffic=None,
+                                  peak_source="same-run DFMA micro-benchmark (mmpc_bench_fp64); nominal 37.2",
+                                  kernel="mmpc::solve_kernel", kernel_ms=kms,
+                                  hbm=dict(achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=hbm_ach / hbm_peak,
+                                           note="algorithmic bytes only: shows the path is not HBM-bound")))
+        if gathered is not None:
+            line["config"]["nccl_gathered_rows"] = gathered
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, cconv, cdt, _ = cpu_baseline(batch, args.cpu_sample, cores)
+            line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
+                                        sample="first %d instances of rank 0's batch, oracle/mmpc_oracle.c on %d threads, %.1f s"
+                                               % (args.cpu_sample, cores, cdt))
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

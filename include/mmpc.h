@@ -165,6 +165,10 @@ int mmpc_struct_sizes(int32_t* cfg_bytes, int32_t* in_bytes, int32_t* out_bytes)
  * dynamic shared memory one instance occupies. */
 int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* blocks_per_sm, int32_t* smem_bytes);
 
+/* FP64 FMA peak of `device` in TFLOP/s, measured by a register-resident DFMA micro-benchmark
+ * (the roofline denominator of bench.py; MEASURED_PEAKS.json carries no FP64 figure). */
+int mmpc_bench_fp64(int32_t device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

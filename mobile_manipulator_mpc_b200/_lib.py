@@ -60,6 +60,7 @@ def lib():
     L.mmpc_launch_count.argtypes = [vp]
     L.mmpc_launch_count.restype = i64
     L.mmpc_occupancy.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.mmpc_bench_fp64.argtypes = [i32, C.POINTER(C.c_double)]
     a, b, c = i32(), i32(), i32()
     L.mmpc_struct_sizes(C.byref(a), C.byref(b), C.byref(c))
     if (a.value, b.value, c.value) != (C.sizeof(_abi.MmpcConfig), C.sizeof(_abi.MmpcBatchIn), C.sizeof(_abi.MmpcBatchOut)):
@@ -75,4 +76,4 @@ def check(rc):
 
 EXPORTS = ("mmpc_version", "mmpc_error_string", "mmpc_default_config", "mmpc_create", "mmpc_destroy",
            "mmpc_set_weights", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
-           "mmpc_plant_step", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy")
+           "mmpc_plant_step", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")

@@ -332,3 +332,37 @@ extern "C" int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* b
   if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
   return MMPC_OK;
 }
+
+// ---- FP64 FMA peak micro-benchmark: the denominator of the roofline (MEASURED_PEAKS.json has no
+// FP64 entry).  8 independent DFMA chains per thread. -----------------------------------------
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+    v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+extern "C" int mmpc_bench_fp64(int32_t device, double* tflops) {
+  if (!tflops) return MMPC_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MMPC_ERR_NO_DEVICE; }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double* out; CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = (double)blocks * threads * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return MMPC_OK;
+}

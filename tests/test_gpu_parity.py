@@ -1,0 +1,213 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs, against the committed SciPy goldens, and -- at BASELINE's full batch sizes --
+through size-independent properties (feasibility of the restated NLP, KKT error, determinism)."""
+import os
+
+import numpy as np
+import pytest
+
+from mobile_manipulator_mpc_b200 import _abi, scenarios
+from oracle import model as M
+from oracle import nlp, solver
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _solver(batch, B=None, **kw):
+    from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    return BatchSolver(N=batch["N"], dt=batch["dt"], n_obs=batch["n_obs"], n_pl=batch["n_pl"],
+                       B_max=B or batch["x_init"].shape[0], obs_per_stage=batch["obs_per_stage"], **kw)
+
+
+def _gold(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=True)
+    batch = {k[3:]: (g[k].item() if g[k].ndim == 0 else g[k]) for k in g.files if k.startswith("in_")}
+    return g, batch
+
+
+# ---- function values: FK, dynamics, constraint rows at 1e-12 relative (north_star) -------------------
+def test_model_values_match_oracle_1e12():
+    import torch
+    rng = np.random.default_rng(7)
+    Mn = 20000
+    x = np.column_stack([rng.uniform(-6, 6, Mn), rng.uniform(-6, 6, Mn), rng.uniform(-7, 7, Mn),
+                         rng.uniform(-2, 2, (Mn, 3)), rng.uniform(-np.pi / 2, np.pi / 2, Mn),
+                         rng.uniform(-np.pi, 0, Mn), rng.uniform(0, 1.5 * np.pi, Mn)])
+    u = rng.uniform(-2, 2, (Mn, 5))
+    circ = np.tile(scenarios.DEMO_CIRCLES, (Mn, 1, 1)) + rng.uniform(-0.2, 0.2, (Mn, 3, 3))
+    _, _, planes1 = scenarios.demo_scenario(1)
+    planes = np.tile(planes1, (Mn, 1, 1))
+    b = dict(N=20, dt=0.1, n_obs=3, n_pl=3, obs_per_stage=0, x_init=x)
+    S = _solver(b, B=1)
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    f, fk, rows = S.eval_model(t(x), t(u), t(circ), t(planes))
+    f, fk, rows = f.cpu().numpy(), fk.cpu().numpy(), rows.cpu().numpy()
+    rel = lambda a, r: np.abs(a - r).max() / max(1.0, np.abs(r).max())
+    assert rel(f, M.f_kinematics(x, u, 0.1)) < 1e-12
+    pe, j2, j3 = M.forward_transformation(x)
+    ref_fk = np.column_stack([pe[0], pe[1], pe[2], pe[3], j2[0], j2[1], j2[2], j3[0], j3[1], j3[2]])
+    assert np.abs(fk - ref_fk).max() < 1e-12 * max(1.0, np.abs(ref_fk).max())
+    # rows: circles, self-collision, plane margins c[i][j] (i-major)
+    ref_rows = np.empty_like(rows)
+    for m in range(0, Mn, 1):
+        if m >= 400:
+            break
+        rr = (M.circle_rows(x[m], circ[m]) + M.self_collision_rows(x[m])
+              + [c for row in M.plane_margins(x[m], [(p[:3], p[3:]) for p in planes[m]]) for c in row])
+        ref_rows[m] = rr
+    assert np.abs(rows[:400] - ref_rows[:400]).max() < 1e-12 * max(1.0, np.abs(ref_rows[:400]).max())
+
+
+# ---- golden instances ---------------------------------------------------------------------------------
+def test_config1_golden_and_known_answers():
+    g, batch = _gold("cfg1_N20_reference")
+    S = _solver(batch)
+    o = S.solve_host(batch)
+    assert o["status"][0] == 0
+    assert abs(o["cost"][0] - float(g["cost"])) <= 1e-5 * float(g["cost"])       # 167.5914832...
+    assert np.abs(o["U"][0, 0] - g["U"][0]).max() < 5e-4                          # see tests/test_oracle_solver.py
+    assert np.allclose(o["U"][0, 0], [2, np.pi, 0, 0, 0], atol=3e-4)
+    assert abs(o["s"][0, 16] - 1.962e-4) < 1e-6                                   # circle #2 active at k=16
+    P = nlp.from_batch(batch, 0, "clean")
+    w = P.pack(o["X"][0], o["U"][0], o["s"][0])
+    assert P.violation(w) <= 1e-6
+
+
+def test_config1_tight_tolerance_u0_1e4():
+    g, batch = _gold("cfg1_N20_reference")
+    S = _solver(batch, tol=1e-10)
+    o = S.solve_host(batch)
+    assert o["status"][0] == 0 and np.abs(o["U"][0, 0] - g["U"][0]).max() < 1e-4
+
+
+# ---- batched parity against the oracle ------------------------------------------------------------------
+@pytest.mark.parametrize("cid,B,N", [(1, 1, 20), (1, 1, 10), (2, 512, 20), (3, 512, 20), (5, 96, 40)])
+def test_batched_solve_matches_oracle(cid, B, N):
+    batch = scenarios.make_batch(cid, B, N=N)
+    S = _solver(batch)
+    o = S.solve_host(batch)
+    ref = solver.solve(batch, mode=_abi.MODE_CLEAN, threads=os.cpu_count() or 4)
+    both = (o["status"] == 0) & (ref["status"] == 0)
+    assert (o["status"] == 0).mean() >= 0.97 and both.mean() >= 0.96
+    rel = np.abs(o["cost"] - ref["cost"])[both] / np.abs(ref["cost"][both])
+    du0 = np.abs(o["U"][:, 0] - ref["U"][:, 0]).max(axis=1)[both]
+    # north_star: 1e-5 relative on the optimal cost, 1e-4 absolute on u0.  A handful of non-convex
+    # instances may bifurcate to another local minimum through round-off; bound their share.
+    assert (rel <= 1e-5).mean() >= 0.99, rel.max()
+    assert (du0 <= 1e-4).mean() >= 0.99, du0.max()
+    assert (o["kkt"][o["status"] == 0] <= 1e-8).all()
+    # same active obstacle rows (g - s >= -1e-6) on a sample
+    for b in np.nonzero(both)[0][:16]:
+        P = nlp.from_batch(batch, int(b), "clean")
+        wa = P.pack(o["X"][b], o["U"][b], o["s"][b]); wb = P.pack(ref["X"][b], ref["U"][b], ref["s"][b])
+        assert P.violation(wa) <= 1e-6
+        if rel[np.nonzero(both)[0].tolist().index(b)] <= 1e-5:
+            ga, gb = P.ineq(wa, with_boxes=False), P.ineq(wb, with_boxes=False)
+            strong = gb >= -1e-9
+            assert (ga[strong] >= -1e-6).all()
+
+
+def test_edge_cases_no_obstacles_and_warm_start():
+    # no planes, no circles (the reference's debug scenario 0: empty obstacle_manipulation_list)
+    b = scenarios.make_batch(2, 32)
+    b0 = dict(b); b0.update(n_obs=0, n_pl=0, circles=None, planes=None, n_pl_inst=None)
+    S0 = _solver(b0)
+    o0 = S0.solve_host(b0)
+    r0 = solver.solve(b0, mode=_abi.MODE_CLEAN, threads=4)
+    ok = (o0["status"] == 0) & (r0["status"] == 0)
+    assert ok.mean() >= 0.95
+    assert (np.abs(o0["cost"] - r0["cost"])[ok] <= 1e-5 * np.abs(r0["cost"][ok])).all()
+    # second MPC step semantics: U_last := previous U* (cost W term + dulim box), guess = previous U*
+    S = _solver(b)
+    o1 = S.solve_host(b)
+    b2 = dict(b); b2["u_last"] = o1["U"].copy()
+    o2 = S.solve_host(b2)
+    r2 = solver.solve(b2, mode=_abi.MODE_CLEAN, threads=4)
+    ok = (o2["status"] == 0) & (r2["status"] == 0)
+    assert ok.mean() >= 0.9
+    rel = np.abs(o2["cost"] - r2["cost"])[ok] / np.abs(r2["cost"][ok])
+    assert (rel <= 1e-5).mean() >= 0.95
+    assert (np.abs(o2["U"] - b2["u_last"])[ok][:, :, 2:] <= 0.5 + 1e-6).all()     # dulim :22,:205
+
+
+def test_determinism_and_device_path_equals_host_path():
+    import torch
+    batch = scenarios.make_batch(3, 256)
+    S = _solver(batch)
+    a = S.solve_host(batch)
+    b = S.solve_host(batch)
+    for k in ("U", "X", "s", "cost", "iters", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    d = S.solve_device(S.to_device(batch))
+    torch.cuda.synchronize()
+    for k in ("U", "cost", "iters", "status"):
+        assert np.array_equal(a[k], d[k].cpu().numpy()), k
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 shape at 65,536 instances: size-independent properties."""
+    batch = scenarios.make_batch(3, 65536)
+    S = _solver(batch)
+    o = S.solve_host(batch)
+    ok = o["status"] == 0
+    assert ok.mean() >= 0.98
+    assert (o["kkt"][ok] <= 1e-8).all()
+    X, U, s = o["X"][ok], o["U"][ok], o["s"][ok]
+    # dynamics equalities :180
+    d = M.f_kinematics(X[:, :-1], U, batch["dt"]) - X[:, 1:]
+    assert np.abs(d).max() <= 1e-6
+    # boxes :203-205
+    cfg = S.cfg
+    ulim = np.array([list(cfg.ulim[0]), list(cfg.ulim[1])]); xlim = np.array([list(cfg.xlim[0]), list(cfg.xlim[1])])
+    assert (U >= ulim[0] - 1e-6).all() and (U <= ulim[1] + 1e-6).all()
+    assert (X[:, 1:] >= xlim[0] - 1e-6).all() and (X[:, 1:] <= xlim[1] + 1e-6).all()
+    assert (np.abs(U[:, :, 2:]) <= 0.5 + 1e-6).all()
+    # circle rows g - s <= 1e-6 :208-209
+    c = batch["circles"][ok]
+    dist = np.sqrt((X[:, :, None, 0] - c[:, None, :, 0]) ** 2 + (X[:, :, None, 1] - c[:, None, :, 1]) ** 2)
+    g = (c[:, None, :, 2] + 0.4) - dist - s[:, :, None]
+    assert g.max() <= 1e-6
+    # cost reported == cost recomputed
+    ex = X - batch["x_ref"][ok]
+    Qd = np.array(list(cfg.Qd))
+    J = (Qd * ex ** 2).sum(axis=(1, 2)) + (np.array(list(cfg.Rd)) * (U - batch["u_ref"][ok]) ** 2).sum(axis=(1, 2)) \
+        + (np.array(list(cfg.Wd)) * (U - batch["u_last"][ok]) ** 2).sum(axis=(1, 2)) + cfg.S * (s ** 2).sum(axis=1)
+    assert np.allclose(J, o["cost"][ok], rtol=1e-10)
+
+
+def test_shift_and_plant_kernels():
+    import torch
+    batch = scenarios.make_batch(2, 64)
+    S = _solver(batch)
+    rng = np.random.default_rng(0)
+    U = rng.normal(size=(64, 20, 5)); x = batch["x_init"]; u0 = U[:, 0].copy()
+    Ud = torch.from_numpy(U).cuda()
+    ug = S.shift(Ud).cpu().numpy()
+    assert np.array_equal(ug[:, :-1], U[:, 1:]) and np.array_equal(ug[:, -1], U[:, -1])
+    xn = S.plant_step(torch.from_numpy(x).cuda(), torch.from_numpy(u0).cuda()).cpu().numpy()
+    assert np.abs(xn - M.f_kinematics(x, u0, 0.1)).max() < 1e-13
+
+
+def test_dropin_class_solve_semantics(capsys):
+    from mobile_manipulator_mpc_b200.controllers.mpc_wholebody_qref import MPCWholeBody
+    from mobile_manipulator_mpc_b200.robot_models import MobileManipulator, Obstacles
+    robot = MobileManipulator(0.1)
+    x_start, tgt, planes = scenarios.demo_scenario(1)
+    ctrl = MPCWholeBody(robot, [Obstacles(*c) for c in scenarios.DEMO_CIRCLES],
+                        [(p[:3], p[3:].reshape(1, 3)) for p in planes], N=20)
+    ref, uref = scenarios.global_plan_2d(x_start, scenarios.base_target(x_start, tgt), 5, 0.1)
+    state = x_start.copy(); state[7] = -np.pi - 0.2          # outside xlim: clipped in place (:290)
+    xr, ur = scenarios.local_window(ref, uref, state, [0, 1], 20)
+    u = ctrl.solve(state, xr, ur)
+    assert state[7] == -np.pi
+    assert u.shape == (5,) and u.dtype == np.float64
+    assert "cost: " in capsys.readouterr().out
+    assert abs(ctrl.cost - 167.5914832) < 2e-3 and ctrl.u_latest.shape == (20, 5) and ctrl.x_guess.shape == (21, 9)
+    # closed loop for a few steps, plant = the model (interface_wholebody_qref.py:143)
+    for _ in range(3):
+        state = np.asarray(ctrl.f_dynamics(state, u)).squeeze()
+        xr, ur = scenarios.local_window(ref, uref, state, [0, 1], 20)
+        u = ctrl.solve(state, xr, ur)
+    assert np.isfinite(u).all()
