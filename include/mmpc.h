@@ -67,6 +67,11 @@ enum {
   MMPC_MODE_CLEAN = 1      /* stage-separable: -max_j c_k[i,j] <= s_k only, terminal rows on s[N]  */
 };
 
+/* execution strategy of mmpc_solve (same algorithm, same results to rounding):
+ *   LANE  one thread per instance, 32 instances per warp in lock-step (throughput kernel)
+ *   WARP  one warp per instance, lanes cooperate on the stages of one horizon */
+enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2 };
+
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */
   int32_t n_obs;         /* ground circles per instance                                          */
@@ -127,6 +132,9 @@ int mmpc_destroy(MmpcHandle* h);
 /* Replaces MPCWholeBody.setWeight (:119-139); diagonals only (every use in the reference is diagonal). */
 int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* Pd, const double* Rd,
                      const double* Wd, double S);
+
+/* Selects the execution strategy of the following mmpc_solve calls (MMPC_KERNEL_*; default AUTO). */
+int mmpc_set_kernel(MmpcHandle* h, int32_t kernel);
 
 /* Replaces MPCWholeBody.solve (:287-331) for B independent instances.  All pointers are DEVICE
  * pointers owned by the caller; asynchronous on `stream` (a cudaStream_t).  x_init is clipped to

@@ -34,7 +34,7 @@ def _diag(M, n, name):
 
 class BatchSolver:
     def __init__(self, N=20, dt=0.1, n_obs=3, n_pl=3, B_max=1, mode=_abi.MODE_CLEAN, device=0,
-                 obs_per_stage=False, cfg=None, **overrides):
+                 obs_per_stage=False, cfg=None, kernel=None, **overrides):
         if cfg is None:
             cfg = _abi.default_config(N=N, dt=dt, n_obs=n_obs, n_pl=n_pl, mode=mode)
             cfg.obs_per_stage = int(bool(obs_per_stage))
@@ -45,6 +45,13 @@ class BatchSolver:
         self.device = int(device)
         self._h = C.c_void_p()
         check(lib().mmpc_create(C.byref(cfg), self.B_max, self.device, C.byref(self._h)))
+        if kernel is not None:
+            self.set_kernel(kernel)
+
+    def set_kernel(self, kernel):
+        """'auto' | 'lane' (thread per instance, throughput) | 'warp' (warp per instance, latency)."""
+        k = {"auto": _abi.KERNEL_AUTO, "lane": _abi.KERNEL_LANE, "warp": _abi.KERNEL_WARP}.get(kernel, kernel)
+        check(lib().mmpc_set_kernel(self._h, int(k)))
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):

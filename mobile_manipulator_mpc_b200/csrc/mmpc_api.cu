@@ -9,6 +9,7 @@
 
 #include "../../include/mmpc.h"
 #include "mmpc_solver.cuh"
+#include "mmpc_lane.cuh"
 
 using namespace mmpc;
 
@@ -21,6 +22,10 @@ struct MmpcHandle {
   double* ws;
   unsigned* counter;
   long long launches;
+  // lane-per-instance kernel: resident warps, interleaved workspace (allocated on first use)
+  int kernel, lane_warps_per_sm, lane_warps;
+  long long lane_warp_stride;
+  double* lane_ws;
   // staging for mmpc_solve_host
   struct { double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes, *U, *X, *s, *cost, *kkt;
            int32_t *n_pl_inst, *iters, *status; uint8_t* flags; } d, h;
@@ -109,6 +114,13 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   CK(cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * sizeof(double)));
   CK(cudaMalloc(&h->counter, sizeof(unsigned)));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->kernel = MMPC_KERNEL_AUTO;
+  h->lane_warps_per_sm = 8;
+  h->lane_warp_stride = lane_instance_doubles(*cfg) * 32;
+  {
+    int want = (B_max + 31) / 32, cap = h->sm_count * h->lane_warps_per_sm;
+    h->lane_warps = want < cap ? want : cap;
+  }
   *out = h;
   return MMPC_OK;
 }
@@ -127,6 +139,7 @@ extern "C" int mmpc_destroy(MmpcHandle* h) {
   cudaSetDevice(h->device);
   free_staging(h);
   if (h->ws) cudaFree(h->ws);
+  if (h->lane_ws) cudaFree(h->lane_ws);
   if (h->counter) cudaFree(h->counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -143,6 +156,49 @@ extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* P
   return MMPC_OK;
 }
 
+extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
+  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_WARP) return MMPC_ERR_ARG;
+  h->kernel = kernel;
+  return MMPC_OK;
+}
+
+static int launch_warp(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
+  KParams P; memset(&P, 0, sizeof P);
+  P.cfg = h->cfg; P.B = B;
+  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
+  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
+  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  P.ws = h->ws; P.ws_stride = h->ws_stride; P.counter = h->counter;
+  P.SP = h->SP; P.KP = h->KP; P.R = h->R;
+  int grid = B < h->slots ? B : h->slots;
+  solve_kernel<<<grid, 32, h->smem_bytes, st>>>(P);
+  CK(cudaGetLastError());
+  return MMPC_OK;
+}
+
+static int launch_lane(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
+  if (!h->lane_ws) {
+    size_t bytes = (size_t)h->lane_warps * (size_t)h->lane_warp_stride * sizeof(double);
+    CK(cudaMalloc(&h->lane_ws, bytes));
+    CK(cudaMemset(h->lane_ws, 0, bytes));
+  }
+  LParams P; memset(&P, 0, sizeof P);
+  P.cfg = h->cfg; P.B = B;
+  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
+  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
+  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  P.ws = h->lane_ws; P.warp_stride = h->lane_warp_stride; P.counter = h->counter;
+  P.R = lane_rows(h->cfg); P.STG = lane_stage_doubles(h->cfg); P.OG = (h->cfg.N + 1) * P.STG;
+  int warps = (B + 31) / 32;
+  if (warps > h->lane_warps) warps = h->lane_warps;
+  // few warps: one per block so they spread over the SMs; otherwise 8 warps per block, one block per SM
+  int tpb = warps <= h->sm_count ? 32 : 32 * h->lane_warps_per_sm;
+  int grid = (warps * 32 + tpb - 1) / tpb;
+  lane_kernel<<<grid, tpb, 0, st>>>(P);
+  CK(cudaGetLastError());
+  return MMPC_OK;
+}
+
 extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, void* stream) {
   if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
   if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
@@ -151,17 +207,10 @@ extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const
   if (B == 0) return MMPC_OK;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  KParams P; memset(&P, 0, sizeof P);
-  P.cfg = h->cfg; P.B = B;
-  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
-  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
-  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
-  P.ws = h->ws; P.ws_stride = h->ws_stride; P.counter = h->counter;
-  P.SP = h->SP; P.KP = h->KP; P.R = h->R;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
-  int grid = B < h->slots ? B : h->slots;
-  solve_kernel<<<grid, 32, h->smem_bytes, st>>>(P);
-  CK(cudaGetLastError());
+  int kernel = h->kernel == MMPC_KERNEL_AUTO ? MMPC_KERNEL_LANE : h->kernel;
+  int rc = kernel == MMPC_KERNEL_LANE ? launch_lane(h, B, in, out, st) : launch_warp(h, B, in, out, st);
+  if (rc != MMPC_OK) return rc;
   h->launches += 1;
   return MMPC_OK;
 }

@@ -20,6 +20,7 @@
 #include "../../include/mmpc.h"
 #include "mmpc_model.cuh"
 #include "mmpc_warp.cuh"
+#include "mmpc_ipm.cuh"
 
 namespace mmpc {
 
@@ -47,7 +48,6 @@ __host__ __device__ inline long long ws_doubles(int N, int KP, int R) {
   return (long long)(3 * R + 28) * KP + (long long)N * 50 + (long long)(N + 1) * 54;
 }
 
-__device__ constexpr int POSE2X[6] = {0, 1, 2, 6, 7, 8};
 // (i,j) state pair -> slot in the sparse Hessian, -1 if structurally zero
 __device__ __forceinline__ int qidx(int i, int j) {
   if (i > j) { int t = i; i = j; j = t; }
@@ -65,40 +65,6 @@ __device__ __forceinline__ void tri9(int e, int& i, int& j) {
   while (e >= base + (9 - r)) { base += 9 - r; ++r; }
   i = r; j = r + (e - base);
 }
-
-struct KktParts {
-  double e_stat, e_prim, c_hi, c_lo, sum_lam, sum_z;
-  int n_z, n_eq;
-};
-__device__ __forceinline__ double kkt_error(const KktParts& k, double mu) {
-  const double smax = 100.0;
-  double sd = fmax(smax, (k.sum_lam + k.sum_z) / fmax(1.0, (double)(k.n_eq + k.n_z))) / smax;
-  double sc = fmax(smax, k.sum_z / fmax(1.0, (double)k.n_z)) / smax;
-  double ec = k.n_z ? fmax(fabs(k.c_hi - mu), fabs(k.c_lo - mu)) : 0.0;
-  return fmax(fmax(k.e_stat / sd, k.e_prim), ec / sc);
-}
-
-__device__ __forceinline__ double push_in(double v, double lo, double hi) {
-  const double k1 = 1e-2, k2 = 1e-2;
-  bool fl = is_fin(lo), fh = is_fin(hi);
-  if (fl && fh) {
-    double pl = fmin(k1 * fmax(1.0, fabs(lo)), k2 * (hi - lo)), pu = fmin(k1 * fmax(1.0, fabs(hi)), k2 * (hi - lo));
-    v = fmax(v, lo + pl); v = fmin(v, hi - pu);
-  } else if (fl) v = fmax(v, lo + k1 * fmax(1.0, fabs(lo)));
-  else if (fh) v = fmin(v, hi - k1 * fmax(1.0, fabs(hi)));
-  return v;
-}
-
-// log of a running product without one log() per factor
-struct LogProd {
-  double prod, acc;
-  __device__ __forceinline__ void init() { prod = 1.0; acc = 0.0; }
-  __device__ __forceinline__ void mul(double v) {
-    prod *= v;
-    if (prod < 1e-120 || prod > 1e120) { acc += log(prod); prod = 1.0; }
-  }
-  __device__ __forceinline__ double value() const { return acc + log(prod); }
-};
 
 struct Solver {
   const KParams& P;

@@ -6,7 +6,9 @@
 // part of the shipped library (the product path has no CPU fallback).
 #pragma once
 
-#ifdef MMPC_EMULATE
+#if defined(MMPC_EMULATE_LANE)
+#include "emu_lane_runtime.h"  // tests/emu/emu_lane_runtime.h (one lane at a time, votes are the identity)
+#elif defined(MMPC_EMULATE)
 #include "emu_runtime.h"  // tests/emu/emu_runtime.h
 #else
 #include <cuda_runtime.h>
@@ -25,6 +27,7 @@ __device__ __forceinline__ unsigned next_instance(unsigned* counter) {
   if (lane_id() == 0) v = atomicAdd(counter, 1u);
   return __shfl_sync(FULL, v, 0);
 }
+__device__ __forceinline__ unsigned lane_next_instance(unsigned* counter) { return atomicAdd(counter, 1u); }
 __device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
 __device__ __forceinline__ int ldg(const int* p) { return __ldg(p); }
 }  // namespace mmpc

@@ -17,11 +17,11 @@ def fl(d, k):
 tot_i = sum(fl(d, 'Instructions Executed') for _, _, _, d in recs)
 tot_s = sum(fl(d, '# Samples') for _, _, _, d in recs)
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = open(os.path.join(root, 'mobile_manipulator_mpc_b200/csrc/mmpc_solver.cuh')).read().split('\n')
+src = open(os.path.join(root, 'mobile_manipulator_mpc_b200/csrc/mmpc_lane.cuh')).read().split('\n')
 marks = [(i + 1, re.sub(r'\(.*', '', l.strip().replace('__device__ ', '').replace('__forceinline__ ', '')))
          for i, l in enumerate(src) if re.match(r'\s*__device__ .*\(', l) and not l.strip().startswith('//')]
 def phase(f, line):
-    if not f.endswith('mmpc_solver.cuh'): return os.path.basename(f)
+    if not f.endswith('mmpc_lane.cuh'): return os.path.basename(f)
     name = '?'
     for ln, l in marks:
         if ln <= line: name = l

@@ -6,8 +6,9 @@ from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
 cid = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+kern = sys.argv[4] if len(sys.argv) > 4 else "auto"
 b = scenarios.make_batch(cid, B)
-S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B, obs_per_stage=b["obs_per_stage"])
+S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B, obs_per_stage=b["obs_per_stage"], kernel=kern)
 d = S.to_device(b)
 out = None
 for r in range(reps):

@@ -18,10 +18,12 @@ def lib():
         _LIB = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu.so"))
         _LIB.mmpc_emu_solve.argtypes = [C.POINTER(_abi.MmpcConfig), C.c_int32, C.POINTER(_abi.MmpcBatchIn),
                                         C.POINTER(_abi.MmpcBatchOut)]
+        _LIB.lane = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_lane.so"))
+        _LIB.lane.mmpc_emu_lane_solve.argtypes = _LIB.mmpc_emu_solve.argtypes
     return _LIB
 
 
-def solve(batch, cfg):
+def solve(batch, cfg, kernel="warp"):
     B = batch["x_init"].shape[0]
     N = cfg.N
     f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
@@ -33,5 +35,6 @@ def solve(batch, cfg):
     out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
                kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])
-    assert lib().mmpc_emu_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo)) == 0
+    fn = lib().mmpc_emu_solve if kernel == "warp" else lib().lane.mmpc_emu_lane_solve
+    assert fn(C.byref(cfg), B, C.byref(bi), C.byref(bo)) == 0
     return out
