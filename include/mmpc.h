@@ -68,9 +68,11 @@ enum {
 };
 
 /* execution strategy of mmpc_solve (same algorithm, same results to rounding):
- *   LANE  one thread per instance, 32 instances per warp in lock-step (throughput kernel)
- *   WARP  one warp per instance, lanes cooperate on the stages of one horizon */
-enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2 };
+ *   STAGED batch-synchronous rounds of phase kernels over compacted lists of active instances
+ *          (stage-parallel evaluation / step / trial, thread-per-instance Riccati); the default
+ *   LANE   one persistent thread per instance, 32 instances per warp in lock-step
+ *   WARP   one warp per instance, lanes cooperate on the stages of one horizon */
+enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2, MMPC_KERNEL_STAGED = 3 };
 
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */

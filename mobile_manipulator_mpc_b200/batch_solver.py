@@ -49,8 +49,9 @@ class BatchSolver:
             self.set_kernel(kernel)
 
     def set_kernel(self, kernel):
-        """'auto' | 'lane' (thread per instance, throughput) | 'warp' (warp per instance, latency)."""
-        k = {"auto": _abi.KERNEL_AUTO, "lane": _abi.KERNEL_LANE, "warp": _abi.KERNEL_WARP}.get(kernel, kernel)
+        """'auto' | 'staged' (phase kernels over active lists) | 'lane' (thread per instance) | 'warp'."""
+        k = {"auto": _abi.KERNEL_AUTO, "lane": _abi.KERNEL_LANE, "warp": _abi.KERNEL_WARP,
+             "staged": _abi.KERNEL_STAGED}.get(kernel, kernel)
         check(lib().mmpc_set_kernel(self._h, int(k)))
 
     # -- lifetime -----------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 #include "../../include/mmpc.h"
 #include "mmpc_solver.cuh"
 #include "mmpc_lane.cuh"
+#include "mmpc_staged.cuh"
 
 using namespace mmpc;
 
@@ -26,6 +27,9 @@ struct MmpcHandle {
   int kernel, lane_warps_per_sm, lane_warps;
   long long lane_warp_stride;
   double* lane_ws;
+  // staged (batch-synchronous) solver: field-major state, per-instance scalars, lists, counters
+  struct { double *ws, *gd; int *gi, *lists, *cnt; long long LS; int* pin; cudaEvent_t ev[8]; bool ready;
+           int rounds; } sg;
   // staging for mmpc_solve_host
   struct { double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes, *U, *X, *s, *cost, *kkt;
            int32_t *n_pl_inst, *iters, *status; uint8_t* flags; } d, h;
@@ -140,6 +144,11 @@ extern "C" int mmpc_destroy(MmpcHandle* h) {
   free_staging(h);
   if (h->ws) cudaFree(h->ws);
   if (h->lane_ws) cudaFree(h->lane_ws);
+  if (h->sg.ready) {
+    cudaFree(h->sg.ws); cudaFree(h->sg.gd); cudaFree(h->sg.gi); cudaFree(h->sg.lists); cudaFree(h->sg.cnt);
+    cudaFreeHost(h->sg.pin);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->sg.ev[i]);
+  }
   if (h->counter) cudaFree(h->counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -157,7 +166,7 @@ extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* P
 }
 
 extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
-  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_WARP) return MMPC_ERR_ARG;
+  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_STAGED) return MMPC_ERR_ARG;
   h->kernel = kernel;
   return MMPC_OK;
 }
@@ -199,6 +208,71 @@ static int launch_lane(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const Mm
   return MMPC_OK;
 }
 
+// Staged solver: one interior-point round of the whole batch = six kernels over the device-side
+// lists of active instances.  The host only sequences rounds; it learns that the lists are empty
+// from a 16-byte copy that trails the launches by STAGED_LAG rounds, so the GPU queue never drains.
+static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
+  const MmpcConfig& cfg = h->cfg;
+  const int N = cfg.N, STG = staged_stage_doubles(cfg);
+  if (!h->sg.ready) {
+    long long LS = ((long long)h->B_max + 31) / 32 * 32;
+    h->sg.LS = LS;
+    CK(cudaMalloc(&h->sg.ws, (size_t)(N + 1) * STG * LS * sizeof(double)));
+    CK(cudaMalloc(&h->sg.gd, (size_t)staged_inst_doubles(cfg) * LS * sizeof(double)));
+    CK(cudaMalloc(&h->sg.gi, (size_t)J_NFIELDS * LS * sizeof(int)));
+    CK(cudaMalloc(&h->sg.lists, (size_t)2 * LS * sizeof(int)));
+    CK(cudaMalloc(&h->sg.cnt, 2 * sizeof(int)));
+    CK(cudaMallocHost(&h->sg.pin, 8 * 2 * sizeof(int)));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming));
+    h->sg.ready = true;
+  }
+  SParams P; memset(&P, 0, sizeof P);
+  P.cfg = cfg; P.B = B;
+  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
+  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
+  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  P.ws = h->sg.ws; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
+  P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = STG;
+  staged_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(P);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  const int LAG = 2, cap = h->sm_count * 16;
+  long long ub = B;  // upper bound of the active instances (the lists only shrink)
+  int r = 0;
+  for (;; ++r) {
+    long long items = ub * (N + 1);
+    int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
+    int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
+    if (gs < 1) gs = 1; if (gi_ < 1) gi_ = 1; if (g64 < 1) g64 = 1;
+    staged_compact_kernel<<<1, 1024, 0, st>>>(P, 0, ST_ACTIVE);
+    staged_eval_kernel<<<gs, 128, 0, st>>>(P);
+    staged_solve_kernel<<<g64, 64, 0, st>>>(P);
+    staged_step_kernel<<<gs, 128, 0, st>>>(P);
+    staged_ctrl_step_kernel<<<gi_, 128, 0, st>>>(P);
+    staged_compact_kernel<<<1, 1024, 0, st>>>(P, 1, ST_TRIAL);
+    staged_trial_kernel<<<gs, 128, 0, st>>>(P);
+    staged_ctrl_trial_kernel<<<gi_, 128, 0, st>>>(P);
+    CK(cudaGetLastError());
+    h->launches += 8;
+    // the list lengths of this round trail the launches by LAG rounds
+    int slot = r & 7;
+    CK(cudaMemcpyAsync(h->sg.pin + 2 * slot, h->sg.cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->sg.ev[slot], st));
+    if (r >= LAG) {
+      int qs = (r - LAG) & 7;
+      CK(cudaEventSynchronize(h->sg.ev[qs]));
+      // every instance still active after a round is in that round's trial list, and the
+      // active set only shrinks: its length bounds every later list
+      long long nT = h->sg.pin[2 * qs + 1];
+      if (nT == 0) break;
+      if (nT < ub) ub = nT;
+    }
+    if (r > 4000000) break;
+  }
+  h->sg.rounds = r + 1;
+  return MMPC_OK;
+}
+
 extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, void* stream) {
   if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
   if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
@@ -208,7 +282,8 @@ extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
-  int kernel = h->kernel == MMPC_KERNEL_AUTO ? MMPC_KERNEL_LANE : h->kernel;
+  int kernel = h->kernel == MMPC_KERNEL_AUTO ? MMPC_KERNEL_STAGED : h->kernel;
+  if (kernel == MMPC_KERNEL_STAGED) return launch_staged(h, B, in, out, st);
   int rc = kernel == MMPC_KERNEL_LANE ? launch_lane(h, B, in, out, st) : launch_warp(h, B, in, out, st);
   if (rc != MMPC_OK) return rc;
   h->launches += 1;

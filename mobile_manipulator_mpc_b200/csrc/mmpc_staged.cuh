@@ -1,0 +1,1122 @@
+// mmpc_staged.cuh -- batch-synchronous ("staged") interior-point solve of the whole-body MPC NLP
+// (controllers/mpc_wholebody_qref.py:142-285), replacing opti.solve() (:315), i.e. the
+// CasADi/IPOPT/MUMPS stack, for tens of thousands of independent instances at once.
+//
+// Mapping (B200).  One interior-point iteration of the whole batch is a short sequence of kernels
+// over compacted lists of still-active instances; all per-instance state lives in HBM in a
+// field-major / instance-minor layout  ws[(stage*STG + field) * LS + b]  so that every access of a
+// warp is a coalesced line, whichever way the threads are mapped:
+//
+//   eval        thread per (instance, stage)   dynamics, FK, every inequality row with gradient and
+//                                              Hessian, barrier condensation -> stage QP, KKT partials
+//   riccati     thread per instance            KKT reduction + convergence test + barrier update,
+//                                              register-resident Riccati recursion (inertia
+//                                              correction by delta_w), roll-out of the Newton step
+//   step        thread per (instance, stage)   slack / multiplier steps of every row and bound,
+//                                              fraction to the boundary, merit ingredients
+//   ctrl_step   thread per instance            reduction, line-search start
+//   trial       thread per (instance, stage)   candidate iterate  w + alpha d  (primal and dual) into
+//                                              the other half of a ping-pong buffer, merit values
+//   ctrl_trial  thread per instance            filter acceptance test; accepted instances flip their
+//                                              buffer and join the next round's eval list, rejected
+//                                              ones halve alpha and join the next round's trial list
+//
+// The stage-parallel kernels expose (N+1) x more threads than instances and carry no sequential
+// dependency; the sequential part (the Riccati sweep) is isolated in one kernel.  Instances leave
+// the lists when they finish, so the tail of slow instances costs launch latency, not idle lanes.
+// Algorithm = oracle/mmpc_oracle.c (IPOPT-style: monotone mu, tau = max(0.99, 1-mu), bound push,
+// gradient-based objective scaling, filter line search with slack reset).
+//
+// The phase bodies are plain __device__ functions of (params, instance, stage) so that tests/emu can
+// run the same source on the CPU (g++), one work item at a time.
+#pragma once
+#include <stdint.h>
+#include "../../include/mmpc.h"
+#include "mmpc_model.cuh"
+#include "mmpc_warp.cuh"
+#include "mmpc_ipm.cuh"
+
+namespace mmpc {
+
+struct SParams {
+  MmpcConfig cfg;
+  int B;
+  const double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes;
+  const int32_t* n_pl_inst;
+  const uint8_t* flags;
+  double *U, *X, *s, *cost, *kkt;
+  int32_t *iters, *status;
+  double* ws;      // per-stage records, field-major / instance-minor
+  double* gd;      // per-instance doubles  gd[field * LS + b]
+  int* gi;         // per-instance ints     gi[field * LS + b]
+  int* lists;      // 2 lists of LS ints: E (next phase eval), T (next phase trial)
+  int* cnt;        // their lengths
+  long long LS;    // instance stride (B_max rounded up)
+  int R, STG, ITSZ;
+};
+
+// ---- iterate buffer (two copies, ping-pong): offsets inside one copy --------------------------
+constexpr int I_X = 0, I_U = 9, I_S = 14, I_LAM = 15, I_ZXL = 24, I_ZXU = 33, I_ZUL = 42, I_ZUU = 47, I_T = 52;
+// ---- after the two iterate copies -----------------------------------------------------------------
+constexpr int S_DX = 0, S_DU = 9, S_DS = 14, S_LAMN = 15, S_FK = 24, S_DFC = 32, S_PART = 41;
+// stage QP: pose Hessian (21 packed) | velocity diagonal 3 | (dx,dpsi) (dy,dpsi) | control diagonal 5 |
+// (psi,u0) | a = H[pose][s] 6 | c = H[s][s] | bv = H[pose][v] 6 | hvv | gA 16 | gB 16   (y = x9 s u5 v)
+constexpr int Q_HP = 49, Q_HVD = 70, Q_H35 = 73, Q_H45 = 74, Q_HUU = 75, Q_HPU = 80, Q_A = 81, Q_C = 87,
+              Q_BV = 88, Q_HVV = 94, Q_GA = 95, Q_GB = 111;
+// Riccati: K 45 | kff 5 | w 14 | cv | l0 | Pxx 45 | pxx 9
+constexpr int R_K = 127, R_KFF = 172, R_W = 177, R_CV = 191, R_L0 = 192, R_P = 193, R_PV = 238;
+constexpr int IN_XREF = 247, IN_UREF = 256, IN_ULAST = 261, IN_ULO = 266, IN_UHI = 271;
+constexpr int S_DT = 276;  // dt[R], then (moving obstacles) circles[3*nobs]
+constexpr int S_FIXED = 276;
+constexpr int SGY_S = 9, SGY_U = 10, SGY_V = 15;
+// per-instance doubles
+constexpr int D_MU = 0, D_REGLAST = 1, D_THMAX = 2, D_THMIN = 3, D_E0 = 4, D_OS = 5, D_ALPHA = 6, D_AD = 7,
+              D_GPHI = 8, D_THETA = 9, D_PHI0 = 10, D_FILT = 11, D_PL = 43, D_CIRC = 43 + 6 * MMPC_MAX_PLANES;
+// per-instance ints
+constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_NFIELDS = 6;
+constexpr int ST_ACTIVE = 0, ST_DONE = 1, ST_TRIAL = 2;  // ACTIVE: next phase is eval; TRIAL: next phase is a trial
+// partial slots
+constexpr int NPART = 8;
+
+__host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + 4 + (c.n_pl > 0 ? 6 : 0); }
+__host__ __device__ inline int staged_itsz(const MmpcConfig& c) { return I_T + 2 * staged_rows(c); }
+__host__ __device__ inline int staged_stage_doubles(const MmpcConfig& c) {
+  return 2 * staged_itsz(c) + S_FIXED + staged_rows(c) + (c.obs_per_stage ? 3 * c.n_obs : 0);
+}
+__host__ __device__ inline int staged_inst_doubles(const MmpcConfig& c) { return D_CIRC + (c.obs_per_stage ? 0 : 3 * c.n_obs); }
+
+__host__ __device__ constexpr int ssidx(int i, int j) { return i <= j ? i * 9 - i * (i - 1) / 2 + (j - i) : j * 9 - j * (j - 1) / 2 + (i - j); }
+struct SACoef { double dt, a32, a42, a34, a43, a35, a45, cp, sp; };
+
+struct Inst {
+  const SParams& P;
+  const MmpcConfig& cfg;
+  double* w;   // ws + b
+  double* gd;  // P.gd + b
+  int* gi;     // P.gi + b
+  long long LS;
+  int N, R, STG, ITSZ, B2, nobs, npl, b;
+  double dt;
+
+  __device__ __forceinline__ Inst(const SParams& p, int b_) : P(p), cfg(p.cfg) {
+    b = b_; w = p.ws + b_; gd = p.gd + b_; gi = p.gi + b_; LS = p.LS;
+    N = cfg.N; R = p.R; STG = p.STG; ITSZ = p.ITSZ; B2 = 2 * p.ITSZ; nobs = cfg.n_obs; dt = cfg.dt;
+    npl = 0;
+  }
+  __device__ __forceinline__ double& W(int k, int o) const { return w[((long long)k * STG + o) * LS]; }
+  __device__ __forceinline__ double& W2(int k, int o) const { return w[((long long)k * STG + B2 + o) * LS]; }
+  __device__ __forceinline__ double& D(int o) const { return gd[(long long)o * LS]; }
+  __device__ __forceinline__ int& J(int o) const { return gi[(long long)o * LS]; }
+  __device__ __forceinline__ double circ(int k, int i, int c) const {
+    return cfg.obs_per_stage ? W2(k, S_DT + R + 3 * i + c) : D(D_CIRC + 3 * i + c);
+  }
+  __device__ __forceinline__ void load_npl() { npl = J(J_NPL); }
+
+  // -max_j c[i][j] for body point i (:76-87); returns the arg-max plane
+  __device__ __forceinline__ double plane_row(const Point& p, int& jbest) const {
+    double cb = 0; jbest = 0;
+    for (int j = 0; j < npl; ++j) {
+      double n0 = D(D_PL + 6 * j + 3), n1 = D(D_PL + 6 * j + 4), n2 = D(D_PL + 6 * j + 5);
+      double e = cfg.obstacle_expand_dist;
+      double off = n0 * (D(D_PL + 6 * j + 0) - e * n0) + n1 * (D(D_PL + 6 * j + 1) - e * n1) + n2 * (D(D_PL + 6 * j + 2) - e * n2);
+      double c = off - (n0 * p.P[0] + n1 * p.P[1] + n2 * p.P[2]);
+      bool take = (j == 0) || (npl == 2 ? !(cb > c) : (c > cb));  // if_else(c0 > c1, c0, c1) :85 ; mmax :87
+      if (take) { cb = c; jbest = j; }
+    }
+    return -cb;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // init (thread per instance): copy the instance into the field-major layout, reference initial
+  // guess (:302-304) + IPOPT bound push; s lifted so every row starts strictly feasible;
+  // objective scaling.
+  __device__ void init() {
+    const double* xref = P.x_ref + (long long)b * (N + 1) * NX;
+    const double* uref = P.u_ref + (long long)b * N * NU;
+    const double* ulast = P.u_last + (long long)b * N * NU;
+    npl = P.n_pl_inst ? ldg(P.n_pl_inst + b) : cfg.n_pl;
+    J(J_NPL) = npl;
+    for (int j = 0; j < cfg.n_pl; ++j)
+      for (int c = 0; c < 6; ++c) D(D_PL + 6 * j + c) = ldg(P.planes + ((long long)b * cfg.n_pl + j) * 6 + c);
+    if (!cfg.obs_per_stage)
+      for (int i = 0; i < 3 * nobs; ++i) D(D_CIRC + i) = ldg(P.circles + (long long)b * 3 * nobs + i);
+    double gmax = 0;
+    for (int k = 0; k <= N; ++k) {
+      double x[NX];
+      if (cfg.obs_per_stage)
+        for (int i = 0; i < 3 * nobs; ++i) W2(k, S_DT + R + i) = ldg(P.circles + ((long long)b * (N + 1) + k) * 3 * nobs + i);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = fmax(fmin(ldg(P.x_init + (long long)b * NX + i), cfg.xlim[1][i]), cfg.xlim[0][i]);  // :290-291
+        if (k >= 1) v = push_in(v, cfg.xlim[0][i], cfg.xlim[1][i]);
+        double xr = ldg(xref + k * NX + i);
+        x[i] = v; W(k, I_X + i) = v; W(k, I_LAM + i) = 0; W2(k, IN_XREF + i) = xr;
+        W(k, I_ZXL + i) = 1; W(k, I_ZXU + i) = 1;
+        double Wx = (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+        if (k >= 1) gmax = fmax(gmax, fabs(2 * Wx * (v - xr)));
+      }
+      if (k < N) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          double ul = ldg(ulast + k * NU + j), ur = ldg(uref + k * NU + j);
+          double lo = fmax(cfg.ulim[0][j], ul + cfg.dulim[0][j]);  // mpc_wholebody_qref.py:203 and :205 merged
+          double hi = fmin(cfg.ulim[1][j], ul + cfg.dulim[1][j]);
+          double v = P.u_guess ? ldg(P.u_guess + ((long long)b * N + k) * NU + j) : ul;
+          v = push_in(v, lo, hi);
+          W(k, I_U + j) = v; W2(k, IN_UREF + j) = ur; W2(k, IN_ULAST + j) = ul; W2(k, IN_ULO + j) = lo; W2(k, IN_UHI + j) = hi;
+          W(k, I_ZUL + j) = 1; W(k, I_ZUU + j) = 1;
+          gmax = fmax(gmax, fabs(2 * cfg.Rd[j] * (v - ur) + 2 * cfg.Wd[j] * (v - ul)));
+        }
+      }
+      FK f; fk_eval(x[2], x[6], x[7], x[8], f);
+      double hmax = -1e300;
+      for (int i = 0; i < nobs; ++i) {
+        double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+        double h = (circ(k, i, 2) + cfg.base_radius) - sqrt(ddx * ddx + ddy * ddy);
+        W(k, I_T + i) = h; hmax = fmax(hmax, h);
+      }
+#pragma unroll 1
+      for (int m = 0; m < 4; ++m) {
+        Point p; point_eval(x[0], x[1], f, SELFD[m], p);
+        double h = cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]);
+        W(k, I_T + nobs + m) = h; hmax = fmax(hmax, h);
+      }
+      if (npl > 0) {
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {
+          Point p; point_eval(x[0], x[1], f, BODY[i], p);
+          int jb; double h = plane_row(p, jb);
+          W(k, I_T + nobs + 4 + i) = h; hmax = fmax(hmax, h);
+        }
+      }
+      double s = fmax(0.0, hmax + 1e-2);
+      W(k, I_S) = s;
+      gmax = fmax(gmax, fabs(2 * cfg.S * s));
+      for (int r = 0; r < R; ++r) { W(k, I_T + r) = s - W(k, I_T + r); W(k, I_T + R + r) = 1.0; }
+    }
+    D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
+    D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
+    J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0;
+  }
+
+  struct RowAcc {
+    double H[21], a[NP], gA[NP], gB[NP], st[NP];
+    double csum, be0, be1, zrows, chi, clo, prim, sumz;
+    int nz;
+  };
+
+  // bookkeeping of one slack row  h - s + t = 0  with multiplier z
+  __device__ __forceinline__ void row_state(int it, int r, int k, double h, double s, double& z, double& it_, double& res, RowAcc& A) const {
+    double t = W(k, it + I_T + r);
+    z = W(k, it + I_T + R + r);
+    it_ = 1.0 / t;
+    res = h - s + t;
+    A.prim = fmax(A.prim, fabs(res));
+    double zt = z * t;
+    A.chi = fmax(A.chi, zt); A.clo = fmin(A.clo, zt);
+    A.sumz += z; A.zrows += z; A.nz++;
+    double sig = z * it_;
+    A.csum += sig; A.be0 += sig * res; A.be1 += it_;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // eval (thread per instance and stage): full evaluation of stage k at the current iterate.
+  __device__ void eval(int k) {
+    load_npl();
+    const int it = J(J_CUR) * ITSZ;
+    const double os = D(D_OS);
+    RowAcc A;
+    double x[NX], u[NU], lam[NX], lam1[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { x[i] = W(k, it + I_X + i); lam[i] = (k >= 1) ? W(k, it + I_LAM + i) : 0.0; }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) u[j] = (k < N) ? W(k, it + I_U + j) : 0.0;
+    double s = W(k, it + I_S);
+    FK f; fk_eval(x[2], x[6], x[7], x[8], f);
+    W2(k, S_FK + 0) = f.cp; W2(k, S_FK + 1) = f.sp;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { W2(k, S_FK + 2 + q) = f.vr[q]; W2(k, S_FK + 5 + q) = f.vh[q]; }
+    A.chi = -1e300; A.clo = 1e300; A.prim = 0; A.sumz = 0; A.zrows = 0; A.nz = 0; A.csum = A.be0 = A.be1 = 0;
+#pragma unroll
+    for (int e = 0; e < 21; ++e) A.H[e] = 0;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) A.a[a] = A.gA[a] = A.gB[a] = A.st[a] = 0;
+    double es = 0;  // stationarity inf-norm of this stage
+    double hpp = 0, sum_lam = 0;
+    int n_eq = 0;
+    // dynamics :180 -- defect and costate terms (A^T lam_{k+1}, B^T lam_{k+1})
+    double stx[NX], stu[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) stx[i] = 0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) stu[j] = 0;
+    if (k < N) {
+      double xn[NX];
+      dyn_f(x, u, dt, f.cp, f.sp, xn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        lam1[i] = W(k + 1, it + I_LAM + i);
+        double d = xn[i] - W(k + 1, it + I_X + i);
+        W2(k, S_DFC + i) = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
+      }
+      n_eq = NX;
+      hpp = -dt * u[0] * (lam1[3] * f.cp + lam1[4] * f.sp);
+      W2(k, Q_HPU) = dt * (-lam1[3] * f.sp + lam1[4] * f.cp);
+      W2(k, Q_H45) = -dt * lam1[3];  // (dy,dpsi)
+      W2(k, Q_H35) = dt * lam1[4];   // (dx,dpsi)
+      stx[0] = lam1[0]; stx[1] = lam1[1];
+      stx[2] = lam1[2] + dt * u[0] * (-f.sp * lam1[3] + f.cp * lam1[4]);
+      stx[3] = dt * lam1[0] + lam1[3] + dt * x[5] * lam1[4];
+      stx[4] = dt * lam1[1] - dt * x[5] * lam1[3] + lam1[4];
+      stx[5] = dt * lam1[2] - dt * x[4] * lam1[3] + dt * x[3] * lam1[4] + lam1[5];
+      stx[6] = lam1[6]; stx[7] = lam1[7]; stx[8] = lam1[8];
+      stu[0] = dt * (f.cp * lam1[3] + f.sp * lam1[4]);
+      stu[1] = dt * lam1[5];
+      stu[2] = dt * lam1[6]; stu[3] = dt * lam1[7]; stu[4] = dt * lam1[8];
+    } else {
+      W2(k, Q_HPU) = 0; W2(k, Q_H45) = 0; W2(k, Q_H35) = 0;
+    }
+    // cost and boxes -- :192-205, :240-245.  Pose components seed the row accumulators, the
+    // others are final here.
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+      double gr = 2 * Wx * (x[i] - W2(k, IN_XREF + i));
+      double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
+      if (k >= 1) {
+        double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
+        if (is_fin(lo)) {
+          double z = W(k, it + I_ZXL + i), d = x[i] - lo, id = 1.0 / d;
+          Hd += z * id; gB -= id; st -= z;
+          A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
+        }
+        if (is_fin(hi)) {
+          double z = W(k, it + I_ZXU + i), d = hi - x[i], id = 1.0 / d;
+          Hd += z * id; gB += id; st += z;
+          A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
+        }
+      }
+      if (i < 3 || i >= 6) {
+        const int a = (i < 3) ? i : i - 3;
+        A.H[pidx(a, a)] = Hd + (i == 2 ? hpp : 0.0); A.gA[a] = gA; A.gB[a] = gB; A.st[a] = st;
+      } else {
+        W2(k, Q_HVD + (i - 3)) = Hd; W2(k, Q_GA + i) = gA; W2(k, Q_GB + i) = gB;
+        if (k >= 1) es = fmax(es, fabs(st));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      double Hd = 0, gA = 0, gB = 0;
+      if (k < N) {
+        double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
+        double gr = 2 * Rj * (u[j] - W2(k, IN_UREF + j)) + 2 * Wj * (u[j] - W2(k, IN_ULAST + j));
+        Hd = 2 * Rj + 2 * Wj; gA = gr;
+        double st = gr + stu[j];
+        double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
+        if (is_fin(lo)) {
+          double z = W(k, it + I_ZUL + j), d = u[j] - lo, id = 1.0 / d;
+          Hd += z * id; gB -= id; st -= z;
+          A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
+        }
+        if (is_fin(hi)) {
+          double z = W(k, it + I_ZUU + j), d = hi - u[j], id = 1.0 / d;
+          Hd += z * id; gB += id; st += z;
+          A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
+        }
+        es = fmax(es, fabs(st));
+      }
+      W2(k, Q_HUU + j) = Hd; W2(k, Q_GA + SGY_U + j) = gA; W2(k, Q_GB + SGY_U + j) = gB;
+    }
+    // inequality rows with slack:  h(x_k) - s_k + t = 0
+    for (int i = 0; i < nobs; ++i) {  // obsAvoid :49-54
+      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+      double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+      double h = (circ(k, i, 2) + cfg.base_radius) - d;
+      double z, it_, res; row_state(it, i, k, h, s, z, it_, res, A);
+      double sig = z * it_, nx = ddx * inv, ny = ddy * inv, zd = z * inv;
+      A.H[pidx(0, 0)] += sig * nx * nx - zd * (1 - nx * nx);
+      A.H[pidx(0, 1)] += (sig + zd) * nx * ny;
+      A.H[pidx(1, 1)] += sig * ny * ny - zd * (1 - ny * ny);
+      double cb = sig * res;
+      A.a[0] += sig * nx; A.a[1] += sig * ny; A.gA[0] -= cb * nx; A.gA[1] -= cb * ny;
+      A.gB[0] -= it_ * nx; A.gB[1] -= it_ * ny; A.st[0] -= z * nx; A.st[1] -= z * ny;
+    }
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {  // self collision :219-222
+      Point p; point_eval(x[0], x[1], f, SELFD[m], p);
+      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2);
+      double h = cfg.self_collision_radius - d2 * inv;
+      double z, it_, res; row_state(it, nobs + m, k, h, s, z, it_, res, A);
+      double sig = z * it_, zd = z * inv;
+      double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
+      point_grad(f, p, n, g);  // grad h = -g
+      double cgg = sig + zd;
+#pragma unroll
+      for (int a = 0; a < NP; ++a)
+#pragma unroll
+        for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += cgg * g[a] * g[c];
+      point_jtj_acc(f, p, -zd, A.H);
+      point_hess_acc(f, p, n, -z, A.H);
+      double cb = sig * res;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { A.a[a] += sig * g[a]; A.gA[a] -= cb * g[a]; A.gB[a] -= it_ * g[a]; A.st[a] -= z * g[a]; }
+    }
+    if (npl > 0) {
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {  // obsAvoidConvex :57-89 (proper row)
+        Point p; point_eval(x[0], x[1], f, BODY[i], p);
+        int jb; double h = plane_row(p, jb);
+        double z, it_, res; row_state(it, nobs + 4 + i, k, h, s, z, it_, res, A);
+        double sig = z * it_;
+        double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)}, g[NP];
+        point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g
+#pragma unroll
+        for (int a = 0; a < NP; ++a)
+#pragma unroll
+          for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += sig * g[a] * g[c];
+        point_hess_acc(f, p, n, z, A.H);
+        double cb = sig * res;
+#pragma unroll
+        for (int a = 0; a < NP; ++a) { A.a[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
+      }
+    }
+    // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
+    double S2 = 2 * os * cfg.S;
+    W2(k, Q_C) = S2 + A.csum;
+    W2(k, Q_GA + SGY_S) = S2 * s - A.be0;
+    W2(k, Q_GB + SGY_S) = -A.be1;
+    W2(k, Q_HVV) = 0; W2(k, Q_GA + SGY_V) = 0; W2(k, Q_GB + SGY_V) = 0;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      W2(k, Q_A + a) = A.a[a]; W2(k, Q_BV + a) = 0;
+      W2(k, Q_GA + POSE2X[a]) = A.gA[a]; W2(k, Q_GB + POSE2X[a]) = A.gB[a];
+      if (k >= 1) es = fmax(es, fabs(A.st[a]));
+    }
+#pragma unroll
+    for (int e = 0; e < 21; ++e) W2(k, Q_HP + e) = A.H[e];
+    es = fmax(es, fabs(S2 * s - A.zrows));
+    W2(k, S_PART + 0) = es; W2(k, S_PART + 1) = A.prim; W2(k, S_PART + 2) = A.chi; W2(k, S_PART + 3) = A.clo;
+    W2(k, S_PART + 4) = sum_lam; W2(k, S_PART + 5) = A.sumz; W2(k, S_PART + 6) = (double)A.nz; W2(k, S_PART + 7) = (double)n_eq;
+  }
+
+  __device__ __forceinline__ SACoef acoef(int k, int it) const {
+    SACoef c; c.dt = dt; c.cp = W2(k, S_FK + 0); c.sp = W2(k, S_FK + 1);
+    double u0 = W(k, it + I_U + 0), x3 = W(k, it + I_X + 3), x4 = W(k, it + I_X + 4), x5 = W(k, it + I_X + 5);
+    c.a32 = -dt * u0 * c.sp; c.a42 = dt * u0 * c.cp; c.a34 = -dt * x5; c.a43 = dt * x5; c.a35 = -dt * x4; c.a45 = dt * x3;
+    return c;
+  }
+  // v <- A^T v  (in place on a 9-vector)
+  __device__ __forceinline__ static void at_mul(double* v, const SACoef& c) {
+    double v2 = v[2] + c.a32 * v[3] + c.a42 * v[4];
+    double v3 = v[3] + c.dt * v[0] + c.a43 * v[4];
+    double v4 = v[4] + c.dt * v[1] + c.a34 * v[3];
+    double v5 = v[5] + c.dt * v[2] + c.a35 * v[3] + c.a45 * v[4];
+    v[2] = v2; v[3] = v3; v[4] = v4; v[5] = v5;
+  }
+  // o <- B^T v
+  __device__ __forceinline__ static void bt_mul(const double* v, double* o, const SACoef& c) {
+    o[0] = c.dt * (c.cp * v[3] + c.sp * v[4]); o[1] = c.dt * v[5];
+    o[2] = c.dt * v[6]; o[3] = c.dt * v[7]; o[4] = c.dt * v[8];
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Riccati backward recursion in registers.  Stage k eliminates v_k = s_{k+1} (scalar pivot cv)
+  // and u_k (5x5 LDL^T); reg = delta_w on the x and u diagonals.  Returns 0, or 1 on a
+  // non-positive pivot (wrong inertia).
+  __device__ int riccati(double reg, double mu, int it) {
+    double Pm[45], pv[NX], an[NP], cn, gsn;  // cost-to-go of stage k+1: Pxx, pxx, slack column a, c, g_s
+    {
+#pragma unroll
+      for (int e = 0; e < 45; ++e) Pm[e] = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a)
+#pragma unroll
+        for (int c = a; c < NP; ++c) Pm[ssidx(POSE2X[a], POSE2X[c])] = W2(N, Q_HP + pidx(a, c));
+#pragma unroll
+      for (int q = 0; q < 3; ++q) Pm[ssidx(3 + q, 3 + q)] = W2(N, Q_HVD + q);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        Pm[ssidx(i, i)] += reg;
+        pv[i] = W2(N, Q_GA + i) + mu * W2(N, Q_GB + i);
+      }
+#pragma unroll
+      for (int a = 0; a < NP; ++a) an[a] = W2(N, Q_A + a);
+      cn = W2(N, Q_C); gsn = W2(N, Q_GA + SGY_S) + mu * W2(N, Q_GB + SGY_S);
+#pragma unroll
+      for (int e = 0; e < 45; ++e) W2(N, R_P + e) = Pm[e];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) W2(N, R_PV + i) = pv[i];
+    }
+    int bad = 0;
+    for (int k = N - 1; k >= 0; --k) {
+      SACoef c = acoef(k, it);
+      double d[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) d[i] = W2(k, S_DFC + i);
+      // pd = p + P d ;  l0 = a.d + g_s(k+1) + g_v(k)
+      double pd[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = pv[i];
+#pragma unroll
+        for (int q = 0; q < NX; ++q) v = fma(Pm[ssidx(i, q)], d[q], v);
+        pd[i] = v;
+      }
+      double l0 = gsn + W2(k, Q_GA + SGY_V) + mu * W2(k, Q_GB + SGY_V);
+#pragma unroll
+      for (int a = 0; a < NP; ++a) l0 = fma(an[a], d[POSE2X[a]], l0);
+      // C = (P A)[:, 2..5]
+      double C[NX][4];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double p0 = Pm[ssidx(i, 0)], p1 = Pm[ssidx(i, 1)], p2 = Pm[ssidx(i, 2)], p3 = Pm[ssidx(i, 3)], p4 = Pm[ssidx(i, 4)], p5 = Pm[ssidx(i, 5)];
+        C[i][0] = p2 + c.a32 * p3 + c.a42 * p4;
+        C[i][1] = p3 + c.dt * p0 + c.a43 * p4;
+        C[i][2] = p4 + c.dt * p1 + c.a34 * p3;
+        C[i][3] = p5 + c.dt * p2 + c.a35 * p3 + c.a45 * p4;
+      }
+#define PA_(l, j) (((j) >= 2 && (j) <= 5) ? C[l][(j) - 2] : Pm[ssidx(l, j)])
+      // Mux = B^T (P A) + H_ux ; Muu = B^T P B + H_uu + reg ; m_u
+      double Mux[NU][NX], Muu[15], mvu[NU];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        Mux[0][j] = c.dt * (c.cp * PA_(3, j) + c.sp * PA_(4, j));
+        Mux[1][j] = c.dt * PA_(5, j);
+        Mux[2][j] = c.dt * PA_(6, j); Mux[3][j] = c.dt * PA_(7, j); Mux[4][j] = c.dt * PA_(8, j);
+      }
+      Mux[0][2] += W2(k, Q_HPU);
+      {
+        const double dd = c.dt * c.dt;
+        double q33 = Pm[ssidx(3, 3)], q34 = Pm[ssidx(3, 4)], q44 = Pm[ssidx(4, 4)];
+        Muu[0] = dd * (c.cp * (c.cp * q33 + c.sp * q34) + c.sp * (c.cp * q34 + c.sp * q44));
+        Muu[1] = dd * (c.cp * Pm[ssidx(3, 5)] + c.sp * Pm[ssidx(4, 5)]);
+        Muu[2] = dd * (c.cp * Pm[ssidx(3, 6)] + c.sp * Pm[ssidx(4, 6)]);
+        Muu[3] = dd * (c.cp * Pm[ssidx(3, 7)] + c.sp * Pm[ssidx(4, 7)]);
+        Muu[4] = dd * (c.cp * Pm[ssidx(3, 8)] + c.sp * Pm[ssidx(4, 8)]);
+        // rows 1..4 <-> states 5..8
+#pragma unroll
+        for (int a = 1; a < NU; ++a)
+#pragma unroll
+          for (int b2 = a; b2 < NU; ++b2) Muu[a * 5 - a * (a - 1) / 2 + (b2 - a)] = dd * Pm[ssidx(4 + a, 4 + b2)];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) Muu[a * 5 - a * (a - 1) / 2] += W2(k, Q_HUU + a) + reg;
+      }
+      bt_mul(pd, mvu, c);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) mvu[a] += W2(k, Q_GA + SGY_U + a) + mu * W2(k, Q_GB + SGY_U + a);
+      // Mxx = A^T (P A) + H_xx + reg (upper triangle, packed)
+      double Mxx[45], mvx[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+#pragma unroll
+        for (int j = i; j < NX; ++j) {
+          double v;
+          if (i == 2) v = PA_(2, j) + c.a32 * PA_(3, j) + c.a42 * PA_(4, j);
+          else if (i == 3) v = PA_(3, j) + c.dt * PA_(0, j) + c.a43 * PA_(4, j);
+          else if (i == 4) v = PA_(4, j) + c.dt * PA_(1, j) + c.a34 * PA_(3, j);
+          else if (i == 5) v = PA_(5, j) + c.dt * PA_(2, j) + c.a35 * PA_(3, j) + c.a45 * PA_(4, j);
+          else v = PA_(i, j);
+          Mxx[ssidx(i, j)] = v;
+        }
+#undef PA_
+#pragma unroll
+      for (int a = 0; a < NP; ++a)
+#pragma unroll
+        for (int c2 = a; c2 < NP; ++c2) Mxx[ssidx(POSE2X[a], POSE2X[c2])] += W2(k, Q_HP + pidx(a, c2));
+#pragma unroll
+      for (int q = 0; q < 3; ++q) Mxx[ssidx(3 + q, 3 + q)] += W2(k, Q_HVD + q);
+      Mxx[ssidx(3, 5)] += W2(k, Q_H35); Mxx[ssidx(4, 5)] += W2(k, Q_H45);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { Mxx[ssidx(i, i)] += reg; mvx[i] = pd[i]; }
+      at_mul(mvx, c);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) mvx[i] += W2(k, Q_GA + i) + mu * W2(k, Q_GB + i);
+      // eliminate v_k = s_{k+1}:  w = [A^T a(k+1) + bv(k) ; B^T a(k+1)],  cv = hvv(k) + c(k+1)
+      double wx[NX], wu[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) wx[i] = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) wx[POSE2X[a]] = an[a];
+      bt_mul(wx, wu, c);
+      at_mul(wx, c);
+#pragma unroll
+      for (int a = 0; a < NP; ++a) wx[POSE2X[a]] += W2(k, Q_BV + a);
+      double cv = W2(k, Q_HVV) + cn, icv = 1.0 / cv;
+      bad |= !(cv > 1e-13);
+      {
+        double l0c = l0 * icv;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double wi = wx[i] * icv;
+#pragma unroll
+          for (int j = i; j < NX; ++j) Mxx[ssidx(i, j)] = fma(-wi, wx[j], Mxx[ssidx(i, j)]);
+          mvx[i] = fma(-wx[i], l0c, mvx[i]);
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          double wa = wu[a] * icv;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) Mux[a][j] = fma(-wa, wx[j], Mux[a][j]);
+#pragma unroll
+          for (int b2 = a; b2 < NU; ++b2) Muu[a * 5 - a * (a - 1) / 2 + (b2 - a)] = fma(-wa, wu[b2], Muu[a * 5 - a * (a - 1) / 2 + (b2 - a)]);
+          mvu[a] = fma(-wu[a], l0c, mvu[a]);
+        }
+      }
+      // LDL^T of Muu
+      double L[NU][NU], Dg[NU], iD[NU];
+#define MUU_(i, j) Muu[(j) * 5 - (j) * ((j) - 1) / 2 + ((i) - (j))]  // i >= j
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        double dj = MUU_(j, j);
+#pragma unroll
+        for (int q = 0; q < j; ++q) dj -= L[j][q] * L[j][q] * Dg[q];
+        bad |= !(dj > 1e-13);
+        Dg[j] = dj; iD[j] = 1.0 / dj;
+#pragma unroll
+        for (int i = j + 1; i < NU; ++i) {
+          double v = MUU_(i, j);
+#pragma unroll
+          for (int q = 0; q < j; ++q) v -= L[i][q] * L[j][q] * Dg[q];
+          L[i][j] = v * iD[j];
+        }
+      }
+#undef MUU_
+      if (bad) return 1;
+      // gains: K = -Muu^{-1} Mux (column by column), kff = -Muu^{-1} m_u
+      double Kc[NU][NX], kff[NU];
+#pragma unroll
+      for (int j = 0; j <= NX; ++j) {
+        double y[NU];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) y[a] = (j < NX) ? Mux[a][j < NX ? j : 0] : mvu[a];
+#pragma unroll
+        for (int i = 1; i < NU; ++i)
+#pragma unroll
+          for (int q = 0; q < i; ++q) y[i] -= L[i][q] * y[q];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) y[i] *= iD[i];
+#pragma unroll
+        for (int i = NU - 2; i >= 0; --i)
+#pragma unroll
+          for (int q = i + 1; q < NU; ++q) y[i] -= L[q][i] * y[q];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          if (j < NX) { Kc[a][j < NX ? j : 0] = -y[a]; W2(k, R_K + a * NX + (j < NX ? j : 0)) = -y[a]; }
+          else { kff[a] = -y[a]; W2(k, R_KFF + a) = -y[a]; }
+        }
+      }
+      // P_k = Mxx + Mux^T K ; p_k = m_x + Mux^T kff
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = i; j < NX; ++j) {
+          double v = Mxx[ssidx(i, j)];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) v = fma(Mux[a][i], Kc[a][j], v);
+          Pm[ssidx(i, j)] = v; W2(k, R_P + ssidx(i, j)) = v;
+        }
+        double v = mvx[i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) v = fma(Mux[a][i], kff[a], v);
+        pv[i] = v; W2(k, R_PV + i) = v;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) W2(k, R_W + i) = wx[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) W2(k, R_W + NX + a) = wu[a];
+      W2(k, R_CV) = cv; W2(k, R_L0) = l0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) an[a] = W2(k, Q_A + a);
+      cn = W2(k, Q_C); gsn = W2(k, Q_GA + SGY_S) + mu * W2(k, Q_GB + SGY_S);
+    }
+    if (!(cn > 1e-13)) return 1;
+    return 0;
+  }
+
+  // roll-out of the Newton step (thread per instance): dx, du, ds and the new costates
+  // lam+ = P [dx; ds] + p
+  __device__ void rollout(double mu, int it) {
+    double dxv[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { dxv[i] = 0; W2(0, S_DX + i) = 0; }
+    double dsv = -(W2(0, Q_GA + SGY_S) + mu * W2(0, Q_GB + SGY_S)) / W2(0, Q_C);
+    W2(0, S_DS) = dsv;
+    for (int k = 0; k < N; ++k) {
+      double duv[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        double v = W2(k, R_KFF + a);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v = fma(W2(k, R_K + a * NX + j), dxv[j], v);
+        duv[a] = v; W2(k, S_DU + a) = v;
+      }
+      double l = W2(k, R_L0);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) l = fma(W2(k, R_W + i), dxv[i], l);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) l = fma(W2(k, R_W + NX + a), duv[a], l);
+      dsv = -l / W2(k, R_CV);
+      SACoef c = acoef(k, it);
+      double nx_[NX];
+      nx_[0] = dxv[0] + dt * dxv[3]; nx_[1] = dxv[1] + dt * dxv[4]; nx_[2] = dxv[2] + dt * dxv[5];
+      nx_[3] = dxv[3] + c.a32 * dxv[2] + c.a34 * dxv[4] + c.a35 * dxv[5] + dt * c.cp * duv[0];
+      nx_[4] = dxv[4] + c.a42 * dxv[2] + c.a43 * dxv[3] + c.a45 * dxv[5] + dt * c.sp * duv[0];
+      nx_[5] = dxv[5] + dt * duv[1];
+      nx_[6] = dxv[6] + dt * duv[2]; nx_[7] = dxv[7] + dt * duv[3]; nx_[8] = dxv[8] + dt * duv[4];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { dxv[i] = nx_[i] + W2(k, S_DFC + i); W2(k + 1, S_DX + i) = dxv[i]; }
+      W2(k + 1, S_DS) = dsv;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = W2(k + 1, R_PV + i);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v = fma(W2(k + 1, R_P + ssidx(i, j)), dxv[j], v);
+        if (i < 3) v = fma(W2(k + 1, Q_A + i), dsv, v);
+        if (i >= 6) v = fma(W2(k + 1, Q_A + (i - 3)), dsv, v);
+        W2(k + 1, S_LAMN + i) = v;
+      }
+    }
+  }
+
+  // results: sol.value(U/X/s/cost) :317,:329-330
+  __device__ void finish(int status) {
+    const int it = J(J_CUR) * ITSZ;
+    double fsum = 0;
+    for (int k = 0; k <= N; ++k) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = W(k, it + I_X + i), e = v - W2(k, IN_XREF + i);
+        fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
+        if (P.X) P.X[((long long)b * (N + 1) + k) * NX + i] = v;
+      }
+      if (k < N)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          double v = W(k, it + I_U + j), e = v - W2(k, IN_UREF + j), dl = v - W2(k, IN_ULAST + j);
+          fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
+          P.U[((long long)b * N + k) * NU + j] = v;
+        }
+      double s = W(k, it + I_S);
+      fsum += cfg.S * s * s;
+      if (P.s) P.s[(long long)b * (N + 1) + k] = s;
+    }
+    if (P.cost) P.cost[b] = fsum;
+    if (P.kkt) P.kkt[b] = D(D_E0);
+    if (P.iters) P.iters[b] = J(J_IT);
+    P.status[b] = status;
+    J(J_STATE) = ST_DONE;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // solve (thread per instance): KKT reduction, convergence test, barrier update, Riccati
+  // factorisation with inertia correction, roll-out.
+  __device__ void solve() {
+    const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5;
+    const double tol = cfg.tol;
+    const int it = J(J_CUR) * ITSZ;
+    KktParts kp;
+    kp.e_stat = 0; kp.e_prim = 0; kp.c_hi = -1e300; kp.c_lo = 1e300; kp.sum_lam = 0; kp.sum_z = 0;
+    double nz = 0, neq = 0;
+    for (int k = N; k >= 0; --k) {
+      kp.e_stat = fmax(kp.e_stat, W2(k, S_PART + 0)); kp.e_prim = fmax(kp.e_prim, W2(k, S_PART + 1));
+      kp.c_hi = fmax(kp.c_hi, W2(k, S_PART + 2)); kp.c_lo = fmin(kp.c_lo, W2(k, S_PART + 3));
+      kp.sum_lam += W2(k, S_PART + 4); kp.sum_z += W2(k, S_PART + 5); nz += W2(k, S_PART + 6); neq += W2(k, S_PART + 7);
+    }
+    kp.n_z = (int)nz; kp.n_eq = (int)neq;
+    double E0 = kkt_error(kp, 0.0);
+    D(D_E0) = E0;
+    if (!(E0 == E0)) { finish(MMPC_STATUS_NAN); return; }
+    if (E0 <= tol) { finish(MMPC_STATUS_CONVERGED); return; }
+    if (J(J_IT) >= cfg.max_iter) { finish(MMPC_STATUS_MAX_ITER); return; }
+    double mu = D(D_MU);
+    bool mu_changed = false;
+    while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
+      mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
+    }
+    if (mu_changed) { J(J_NFILT) = 0; D(D_MU) = mu; }
+    double reg = 0, reg_last = D(D_REGLAST);
+    int tries = 0;
+    for (;;) {
+      int fail = riccati(reg, mu, it);
+      if (!fail) { if (reg > 0) D(D_REGLAST) = reg; break; }
+      if (reg == 0) reg = (reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3);
+      else reg *= (reg_last == 0 ? 100 : 8);
+      if (++tries > 40 || reg > 1e20) { finish(MMPC_STATUS_FACTOR); return; }
+    }
+    rollout(mu, it);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // step (thread per instance and stage): slack / multiplier steps of every row and bound,
+  // fraction to the boundary, merit ingredients of the current point.
+  __device__ void step(int k) {
+    load_npl();
+    const int it = J(J_CUR) * ITSZ;
+    const double os = D(D_OS), mu = D(D_MU);
+    const double tau = fmax(0.99, 1 - mu);
+    double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0;
+    LogProd lp; lp.init();
+    double x[NX], dxv[NX], u[NU], duv[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { x[i] = W(k, it + I_X + i); dxv[i] = W2(k, S_DX + i); }
+    double s = W(k, it + I_S), dsv = W2(k, S_DS);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? W(k, it + I_U + a) : 0.0; duv[a] = (k < N) ? W2(k, S_DU + a) : 0.0; }
+    double dp[NP];
+#pragma unroll
+    for (int a = 0; a < NP; ++a) dp[a] = dxv[POSE2X[a]];
+    // cost / boxes
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - W2(k, IN_XREF + i);
+      fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
+      if (k >= 1) {
+        double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
+        if (is_fin(lo)) {
+          double d = x[i] - lo, z = W(k, it + I_ZXL + i), dz = mu / d - z - z / d * dxv[i];
+          gphi -= mu * dxv[i] / d; lp.mul(d);
+          if (dxv[i] < 0) ap = fmin(ap, -tau * d / dxv[i]);
+          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+        }
+        if (is_fin(hi)) {
+          double d = hi - x[i], z = W(k, it + I_ZXU + i), dz = mu / d - z + z / d * dxv[i];
+          gphi += mu * dxv[i] / d; lp.mul(d);
+          if (dxv[i] > 0) ap = fmin(ap, tau * d / dxv[i]);
+          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+        }
+      }
+    }
+    double S1 = os * cfg.S;
+    fsum += S1 * s * s; gphi += 2 * S1 * s * dsv;
+    if (k < N) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
+        double e = u[j] - W2(k, IN_UREF + j), dl = u[j] - W2(k, IN_ULAST + j);
+        fsum += Rj * e * e + Wj * dl * dl; gphi += (2 * Rj * e + 2 * Wj * dl) * duv[j];
+        double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
+        if (is_fin(lo)) {
+          double d = u[j] - lo, z = W(k, it + I_ZUL + j), dz = mu / d - z - z / d * duv[j];
+          gphi -= mu * duv[j] / d; lp.mul(d);
+          if (duv[j] < 0) ap = fmin(ap, -tau * d / duv[j]);
+          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+        }
+        if (is_fin(hi)) {
+          double d = hi - u[j], z = W(k, it + I_ZUU + j), dz = mu / d - z + z / d * duv[j];
+          gphi += mu * duv[j] / d; lp.mul(d);
+          if (duv[j] > 0) ap = fmin(ap, tau * d / duv[j]);
+          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) theta += fabs(W2(k, S_DFC + i));
+    }
+    FK f; f.cp = W2(k, S_FK + 0); f.sp = W2(k, S_FK + 1);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { f.vr[q] = W2(k, S_FK + 2 + q); f.vh[q] = W2(k, S_FK + 5 + q); }
+    // rows: dt_i = -res_i - (grad h_i . dx - ds)
+    auto row_step = [&](int r, double h, double gd_) {
+      double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
+      double res = h - s + t;
+      double dtv = -res - (gd_ - dsv);
+      W2(k, S_DT + r) = dtv;
+      double dz = (mu - z * (t + dtv)) / t;
+      theta += fabs(res); gphi -= mu * dtv / t; lp.mul(t);
+      if (dtv < 0) ap = fmin(ap, -tau * t / dtv);
+      if (dz < 0) ad = fmin(ad, -tau * z / dz);
+    };
+    for (int i = 0; i < nobs; ++i) {
+      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+      double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+      row_step(i, (circ(k, i, 2) + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv);
+    }
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {
+      Point p; point_eval(x[0], x[1], f, SELFD[m], p);
+      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2), d = d2 * inv;
+      double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
+      point_grad(f, p, n, g);
+      double gd_ = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) gd_ = fma(g[a], dp[a], gd_);
+      row_step(nobs + m, cfg.self_collision_radius - d, -gd_);
+    }
+    if (npl > 0) {
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        Point p; point_eval(x[0], x[1], f, BODY[i], p);
+        int jb; double h = plane_row(p, jb);
+        double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)}, g[NP];
+        point_grad(f, p, n, g);
+        double gd_ = 0;
+#pragma unroll
+        for (int a = 0; a < NP; ++a) gd_ = fma(g[a], dp[a], gd_);
+        row_step(nobs + 4 + i, h, gd_);
+      }
+    }
+    W2(k, S_PART + 0) = ap; W2(k, S_PART + 1) = ad; W2(k, S_PART + 2) = gphi; W2(k, S_PART + 3) = theta;
+    W2(k, S_PART + 4) = fsum; W2(k, S_PART + 5) = lp.value();
+  }
+
+  // ctrl_step (thread per instance): reduce the step partials, start the line search.
+  // Returns true if the instance goes on to a trial.
+  __device__ bool ctrl_step() {
+    if (J(J_STATE) != ST_ACTIVE) return false;
+    double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0, logsum = 0;
+    for (int k = 0; k <= N; ++k) {
+      ap = fmin(ap, W2(k, S_PART + 0)); ad = fmin(ad, W2(k, S_PART + 1));
+      gphi += W2(k, S_PART + 2); theta += W2(k, S_PART + 3); fsum += W2(k, S_PART + 4); logsum += W2(k, S_PART + 5);
+    }
+    if (D(D_THMAX) < 0) { D(D_THMAX) = 1e4 * fmax(1.0, theta); D(D_THMIN) = 1e-4 * fmax(1.0, theta); }
+    D(D_ALPHA) = ap; D(D_AD) = ad; D(D_GPHI) = gphi; D(D_THETA) = theta; D(D_PHI0) = fsum - D(D_MU) * logsum;
+    J(J_LS) = 0;
+    J(J_STATE) = ST_TRIAL;
+    return true;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // trial (thread per instance and stage): candidate iterate  w + alpha d  (primal and dual, with
+  // slack reset and multiplier safeguard) into the other iterate buffer; merit ingredients.
+  __device__ void trial(int k) {
+    load_npl();
+    const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
+    const double os = D(D_OS), mu = D(D_MU), alpha = D(D_ALPHA), ad = D(D_AD);
+    double theta = 0, fsum = 0; bool ok = true;
+    LogProd lp; lp.init();
+    double x[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double xo = W(k, it + I_X + i), dxi = W2(k, S_DX + i);
+      x[i] = fma(alpha, dxi, xo);
+      W(k, jt + I_X + i) = x[i];
+      if (k >= 1) {
+        double l = W(k, it + I_LAM + i);
+        W(k, jt + I_LAM + i) = l + alpha * (W2(k, S_LAMN + i) - l);
+      }
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - W2(k, IN_XREF + i);
+      fsum += Wx * e * e;
+      if (k >= 1) {
+        double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
+        if (is_fin(lo)) {
+          double d_old = xo - lo, d = x[i] - lo, z = W(k, it + I_ZXL + i);
+          double dz = mu / d_old - z - (z / d_old) * dxi;
+          z += ad * dz; z = fmax(fmin(z, 1e10 * mu / d), mu / (1e10 * d));
+          W(k, jt + I_ZXL + i) = z;
+          if (d <= 0) ok = false; else lp.mul(d);
+        }
+        if (is_fin(hi)) {
+          double d_old = hi - xo, d = hi - x[i], z = W(k, it + I_ZXU + i);
+          double dz = mu / d_old - z + (z / d_old) * dxi;
+          z += ad * dz; z = fmax(fmin(z, 1e10 * mu / d), mu / (1e10 * d));
+          W(k, jt + I_ZXU + i) = z;
+          if (d <= 0) ok = false; else lp.mul(d);
+        }
+      }
+    }
+    double s = fma(alpha, W2(k, S_DS), W(k, it + I_S));
+    W(k, jt + I_S) = s;
+    fsum += os * cfg.S * s * s;
+    FK f; fk_eval(x[2], x[6], x[7], x[8], f);
+    if (k < N) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        double uo = W(k, it + I_U + j), duj = W2(k, S_DU + j);
+        u[j] = fma(alpha, duj, uo);
+        W(k, jt + I_U + j) = u[j];
+        double e = u[j] - W2(k, IN_UREF + j), dl = u[j] - W2(k, IN_ULAST + j);
+        fsum += os * (cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl);
+        double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
+        if (is_fin(lo)) {
+          double d_old = uo - lo, d = u[j] - lo, z = W(k, it + I_ZUL + j);
+          double dz = mu / d_old - z - (z / d_old) * duj;
+          z += ad * dz; z = fmax(fmin(z, 1e10 * mu / d), mu / (1e10 * d));
+          W(k, jt + I_ZUL + j) = z;
+          if (d <= 0) ok = false; else lp.mul(d);
+        }
+        if (is_fin(hi)) {
+          double d_old = hi - uo, d = hi - u[j], z = W(k, it + I_ZUU + j);
+          double dz = mu / d_old - z + (z / d_old) * duj;
+          z += ad * dz; z = fmax(fmin(z, 1e10 * mu / d), mu / (1e10 * d));
+          W(k, jt + I_ZUU + j) = z;
+          if (d <= 0) ok = false; else lp.mul(d);
+        }
+      }
+      double xn[NX]; dyn_f(x, u, dt, f.cp, f.sp, xn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double x1 = fma(alpha, W2(k + 1, S_DX + i), W(k + 1, it + I_X + i));
+        theta += fabs(xn[i] - x1);
+      }
+    }
+    auto row_val = [&](int r, double h) {
+      double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r), dtv = W2(k, S_DT + r);
+      double tt = fma(alpha, dtv, t);
+      tt = fmax(tt, s - h);  // slack reset (Nocedal & Wright 19.30)
+      double dz = (mu - z * (t + dtv)) / t;
+      z += ad * dz; z = fmax(fmin(z, 1e10 * mu / tt), mu / (1e10 * tt));
+      W(k, jt + I_T + r) = tt; W(k, jt + I_T + R + r) = z;
+      theta += fabs(h - s + tt);
+      if (tt <= 0) ok = false; else lp.mul(tt);
+    };
+    for (int i = 0; i < nobs; ++i) {
+      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+      row_val(i, (circ(k, i, 2) + cfg.base_radius) - sqrt(ddx * ddx + ddy * ddy));
+    }
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {
+      Point p; point_eval(x[0], x[1], f, SELFD[m], p);
+      row_val(nobs + m, cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]));
+    }
+    if (npl > 0) {
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        Point p; point_eval(x[0], x[1], f, BODY[i], p);
+        int jb; row_val(nobs + 4 + i, plane_row(p, jb));
+      }
+    }
+    bool fin = ok && (fsum == fsum) && (theta == theta);
+    W2(k, S_PART + 0) = theta; W2(k, S_PART + 1) = fsum; W2(k, S_PART + 2) = fin ? lp.value() : 0.0;
+    W2(k, S_PART + 3) = fin ? 1.0 : 0.0;
+  }
+
+  // ctrl_trial (thread per instance): filter acceptance test (Waechter & Biegler 2006, Alg. A
+  // without second-order correction).  Returns 0 = accepted (next: eval), 1 = rejected (next: another
+  // trial with alpha/2), 2 = finished (line search failed).
+  __device__ int ctrl_trial() {
+    double th1 = 0, f1 = 0, logsum = 0; bool ok = true;
+    for (int k = 0; k <= N; ++k) {
+      th1 += W2(k, S_PART + 0); f1 += W2(k, S_PART + 1); logsum += W2(k, S_PART + 2);
+      ok = ok && (W2(k, S_PART + 3) > 0.5);
+    }
+    const double mu = D(D_MU), theta_k = D(D_THETA), phi0 = D(D_PHI0), gphi = D(D_GPHI), alpha = D(D_ALPHA);
+    double ph1 = f1 - mu * logsum;
+    int nfilt = J(J_NFILT);
+    bool ftype = false;
+    ok = ok && (th1 == th1) && (ph1 == ph1) && th1 < D(D_THMAX);
+    for (int q = 0; ok && q < nfilt; ++q)
+      if (th1 >= D(D_FILT + 2 * q) && ph1 >= D(D_FILT + 2 * q + 1)) ok = false;
+    if (ok) {
+      bool sw = (gphi < 0) && (alpha * pow(-gphi, 2.3) > pow(theta_k, 1.1));
+      if (theta_k <= D(D_THMIN) && sw) {
+        ok = ph1 <= phi0 + 1e-8 * alpha * gphi + 10 * 2.220446049250313e-16 * fabs(phi0); ftype = ok;
+      } else {
+        ok = (th1 <= (1 - 1e-5) * theta_k) || (ph1 <= phi0 - 1e-8 * theta_k); ftype = false;
+      }
+    }
+    if (!ok) {
+      D(D_ALPHA) = alpha * 0.5;
+      int ls = J(J_LS) + 1; J(J_LS) = ls;
+      if (ls >= 50) { finish(MMPC_STATUS_LINESEARCH); return 2; }
+      return 1;
+    }
+    if (!ftype) {
+      if (nfilt == 16) {
+        for (int q = 0; q < 30; ++q) D(D_FILT + q) = D(D_FILT + q + 2);
+        nfilt--;
+      }
+      D(D_FILT + 2 * nfilt) = (1 - 1e-5) * theta_k; D(D_FILT + 2 * nfilt + 1) = phi0 - 1e-8 * theta_k; nfilt++;
+      J(J_NFILT) = nfilt;
+    }
+    J(J_CUR) = 1 - J(J_CUR);
+    J(J_IT) = J(J_IT) + 1;
+    J(J_STATE) = ST_ACTIVE;
+    return 0;
+  }
+};
+
+// ---- lists ---------------------------------------------------------------------------------------
+// Two lists of instance indices, rebuilt in ascending order (so that the gathers of the phase
+// kernels stay as coalesced as the surviving instances allow) by an ordered compaction of the
+// per-instance state: E = instances whose next phase is eval, T = instances whose next phase is a trial.
+__device__ __forceinline__ int* list_E(const SParams& P) { return P.lists; }
+__device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.LS; }
+
+// ---- phase bodies on list items (shared by the kernels and by tests/emu) -----------------------------
+__device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init(); }
+__device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.eval(k); }
+__device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
+__device__ inline void body_step(const SParams& P, int j, int k) {
+  Inst S(P, list_E(P)[j]);
+  if (S.J(J_STATE) != ST_ACTIVE) return;
+  S.step(k);
+}
+__device__ inline void body_ctrl_step(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.ctrl_step(); }
+__device__ inline void body_trial(const SParams& P, int j, int k) { Inst S(P, list_T(P)[j]); S.trial(k); }
+__device__ inline void body_ctrl_trial(const SParams& P, int j) { Inst S(P, list_T(P)[j]); S.ctrl_trial(); }
+
+#ifdef MMPC_EMULATE_LANE
+// ordered compaction of the instances in state `want` into list `which` (0 = E, 1 = T)
+inline void compact_list(const SParams& P, int which, int want) {
+  int n = 0; int* list = which ? list_T(P) : list_E(P);
+  for (int b = 0; b < P.B; ++b) if (P.gi[(long long)J_STATE * P.LS + b] == want) list[n++] = b;
+  P.cnt[which] = n;
+}
+#else
+// One block of 1024 threads: warp w scans a contiguous chunk of the state array 32 entries at a
+// time (coalesced), counts with ballots, the warp totals are scanned through shared memory, and
+// the second pass writes the indices in ascending order.
+__global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_constant__ SParams P, int which, int want) {
+  __shared__ int wtot[32];
+  const int* st = P.gi + (long long)J_STATE * P.LS;
+  int* list = which ? list_T(P) : list_E(P);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = ((P.B + 1023) / 1024) * 32;  // entries per warp, multiple of 32
+  const int lo = warp * chunk, hi = min(P.B, lo + chunk);
+  int c = 0;
+  for (int b0 = lo; b0 < hi; b0 += 32) {
+    int b = b0 + lane;
+    bool f = b < hi && st[b] == want;
+    c += __popc(__ballot_sync(FULL, f));
+  }
+  if (lane == 0) wtot[warp] = c;
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w2 = 0; w2 < 32; ++w2) { int v = wtot[w2]; if (w2 < warp) off += v; tot += v; }
+  for (int b0 = lo; b0 < hi; b0 += 32) {
+    int b = b0 + lane;
+    bool f = b < hi && st[b] == want;
+    unsigned m = __ballot_sync(FULL, f);
+    if (f) list[off + __popc(m & ((1u << lane) - 1))] = b;
+    off += __popc(m);
+  }
+  if (threadIdx.x == 0) P.cnt[which] = tot;
+}
+
+// ---- kernels: grid-stride loops over the device-side list counts --------------------------------------
+__global__ void __launch_bounds__(128) staged_init_kernel(const __grid_constant__ SParams P) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < P.B) body_init(P, b);
+}
+__global__ void __launch_bounds__(128) staged_eval_kernel(const __grid_constant__ SParams P) {
+  const int n = P.cnt[0];
+  const long long tot = (long long)n * (P.cfg.N + 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
+    body_eval(P, (int)(t % n), (int)(t / n));
+}
+__global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant__ SParams P) {
+  const int n = P.cnt[0];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_solve(P, j);
+}
+__global__ void __launch_bounds__(128) staged_step_kernel(const __grid_constant__ SParams P) {
+  const int n = P.cnt[0];
+  const long long tot = (long long)n * (P.cfg.N + 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
+    body_step(P, (int)(t % n), (int)(t / n));
+}
+__global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
+  const int n = P.cnt[0];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_step(P, j);
+}
+__global__ void __launch_bounds__(128) staged_trial_kernel(const __grid_constant__ SParams P) {
+  const int n = P.cnt[1];
+  const long long tot = (long long)n * (P.cfg.N + 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
+    body_trial(P, (int)(t % n), (int)(t / n));
+}
+__global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
+  const int n = P.cnt[1];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_trial(P, j);
+}
+#endif
+
+}  // namespace mmpc

@@ -1,0 +1,42 @@
+// emu_staged_main.cpp -- TEST INFRASTRUCTURE: runs the phase bodies of csrc/mmpc_staged.cuh on the
+// CPU, one work item at a time, in the same round order as the CUDA host loop (mmpc_api.cu), with
+// the same C ABI argument layout as mmpc_solve (host pointers).
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "emu_lane_runtime.h"
+#include "../../mobile_manipulator_mpc_b200/csrc/mmpc_staged.cuh"
+
+using namespace mmpc;
+
+extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out,
+                                     int32_t* rounds_out) {
+  SParams P; memset(&P, 0, sizeof P);
+  P.cfg = *cfg; P.B = B;
+  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
+  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
+  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  P.R = staged_rows(*cfg); P.ITSZ = staged_itsz(*cfg); P.STG = staged_stage_doubles(*cfg); P.LS = B;
+  std::vector<double> ws((size_t)(cfg->N + 1) * P.STG * B, 0.0), gd((size_t)staged_inst_doubles(*cfg) * B, 0.0);
+  std::vector<int> gi((size_t)J_NFIELDS * B, 0), lists((size_t)2 * B, 0);
+  int cnt[2] = {0, 0};
+  P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
+  for (int b = 0; b < B; ++b) body_init(P, b);
+  int N = cfg->N, r = 0;
+  for (;; ++r) {
+    compact_list(P, 0, ST_ACTIVE);
+    int nE = cnt[0];
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_eval(P, j, k);
+    for (int j = 0; j < nE; ++j) body_solve(P, j);
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_step(P, j, k);
+    for (int j = 0; j < nE; ++j) body_ctrl_step(P, j);
+    compact_list(P, 1, ST_TRIAL);
+    int nT = cnt[1];
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) body_trial(P, j, k);
+    for (int j = 0; j < nT; ++j) body_ctrl_trial(P, j);
+    if (nT == 0) break;
+    if (r > 200000) return 1;
+  }
+  if (rounds_out) *rounds_out = r + 1;
+  return 0;
+}
