@@ -43,6 +43,28 @@ def bytes_per_solve(N, n_obs, n_pl):
     return 8 * (din + dout)
 
 
+def phase_model(N, n_obs, n_pl):
+    """Algorithmic HBM bytes and FP64 flops that ONE instance costs ONE launch of each phase kernel of
+    the staged solver (DESIGN.md "Kernels"): the doubles each stage must read and write, once, with
+    nothing cached between kernels.  R = inequality rows per stage."""
+    R = n_obs + 4 + (6 if n_pl else 0)
+    obs = 3 * n_obs + 6 * n_pl                       # static obstacle data: once per instance and launch
+    st = N + 1
+    ev_r = 24 + 18 + 28 + 2 * R + 19 + 10            # x u s lam | x+ lam+ | box z | t z | refs | u bounds
+    ev_w = 8 + 9 + 78 + 8                            # FK cache | defect | stage QP | KKT partials
+    so_r = 8 + 78 + 9 + 6 + 120 + 6                  # partials | stage QP | defect | dyn coefs | factors (roll-out) | slack column
+    so_w = 120 + 24                                  # Riccati factors | dx du ds lam+
+    sp_r = 15 + 15 + 28 + 2 * R + 8 + 19 + 10 + 9    # x u s | dx du ds | box z | t z | FK cache | refs | u bounds | defect
+    sp_w = R + 6                                     # dt | step partials
+    tr_r = 24 + 24 + 18 + 28 + 3 * R + 19 + 10       # x u s lam | step | x+ dx+ | box z | t z dt | refs | u bounds
+    tr_w = 52 + 2 * R + 4                            # candidate iterate | merit partials
+    c_ric, c_eval = 4871, 1290 + 40 * n_obs + 122 * 6 * (n_pl > 0)
+    return dict(eval=dict(bytes=8 * (st * (ev_r + ev_w) + obs), flops=st * c_eval),
+                solve=dict(bytes=8 * st * (so_r + so_w), flops=N * c_ric),
+                step=dict(bytes=8 * (st * (sp_r + sp_w) + obs), flops=0),
+                trial=dict(bytes=8 * (st * (tr_r + tr_w) + obs), flops=0))
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -140,6 +162,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--contexts", type=int, default=2, help="concurrent solver contexts (streams) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -164,43 +187,67 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
+    T = max(1, args.contexts)
     batch = make_workload(B, seed=3 + 1000 * rank)
     N, n_obs, n_pl = batch["N"], batch["n_obs"], batch["n_pl"]
-    S = BatchSolver(N=N, dt=batch["dt"], n_obs=n_obs, n_pl=n_pl, B_max=B, device=local)
-    dev_in = S.to_device(batch)
-    out = S.solve_device(dev_in)
+    # T solver contexts (handle + stream + workspace each), driven by one host thread each: the thin
+    # tail of slow instances of one batch overlaps the bulk of the next batch
+    ctx = []
+    for t in range(T):
+        S = BatchSolver(N=N, dt=batch["dt"], n_obs=n_obs, n_pl=n_pl, B_max=B, device=local)
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            dev_in = S.to_device(batch)
+            out = S.solve_device(dev_in)
+        ctx.append(dict(S=S, stream=st, dev_in=dev_in, out=out))
     torch.cuda.synchronize()
+    S = ctx[0]["S"]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) ----
-    l0 = S.launch_count()
-    for _ in range(args.warmup):
-        out = S.solve_device(dev_in, out=out)
+    def run_steps(nsteps, contexts, host=False):
+        """nsteps solves of the batch spread round-robin over `contexts` concurrent solver contexts."""
+        outs = [None] * contexts
+
+        def work(t):
+            c = ctx[t]
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(c["stream"]):
+                for _ in range(t, nsteps, contexts):
+                    outs[t] = c["S"].solve_host(batch) if host else c["S"].solve_device(c["dev_in"], out=c["out"])
+        if contexts == 1:
+            work(0)
+        else:
+            th = [threading.Thread(target=work, args=(t,)) for t in range(contexts)]
+            [x.start() for x in th]; [x.join() for x in th]
+        return outs
+
+    # ---- device-resident timing (value): K steps over T contexts ----
+    run_steps(args.warmup, T)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l1 = S.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l1 = sum(c["S"].launch_count() for c in ctx)
+    t0 = time.perf_counter()
     e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_all0.record()
-    for a, b in ev:
-        a.record(); out = S.solve_device(dev_in, out=out); b.record()
+    run_steps(args.steps, T)
+    for c in ctx:
+        torch.cuda.current_stream().wait_stream(c["stream"])
     e_all1.record()
     barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
-    launches = S.launch_count() - l1
+    launches = sum(c["S"].launch_count() for c in ctx) - l1
     total_ms = e_all0.elapsed_time(e_all1)
-    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    out = ctx[0]["out"]
     conv = int((out["status"] == 0).sum().item())
-    iters_sum = int(out["iters"].sum().item())
-    npl_inst = batch["n_pl_inst"]
-    work_flops = float(sum(flops_per_iteration(N, n_obs, int(p)) * int(i)
-                           for p, i in zip(npl_inst, out["iters"].cpu().numpy())))
+    iters_np = out["iters"].cpu().numpy()
+    iters_sum = int(iters_np.sum())
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     c = torch.tensor([conv, iters_sum, B], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -209,14 +256,31 @@ def main():
     conv_all, iters_all, B_all = (float(v) for v in c.tolist())
     value = conv_all * args.steps / (total_ms_max * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers ----
-    out_h = S.solve_host(batch)
+    # ---- one context alone, CUDA events around every launch: latency of one batched solve and the
+    #      per-kernel durations the roofline is computed from ----
+    S.set_profile(True)
+    lat_ms, phase_ms, phase_ln, rounds = [], {}, {}, 0
+    for i in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ctx[0]["stream"]):
+            a.record(); S.solve_device(ctx[0]["dev_in"], out=ctx[0]["out"]); b.record()
+        torch.cuda.synchronize()
+        lat_ms.append(a.elapsed_time(b))
+        pm, pl, rounds = S.phase_times()
+        for k in pm:
+            phase_ms[k] = phase_ms.get(k, 0.0) + pm[k] / args.steps
+            phase_ln[k] = pl[k]
+    S.set_profile(False)
+    barrier()
+
+    # ---- end to end through the C ABI with host buffers (pinned staging, H2D, solve, D2H per step) ----
+    run_steps(min(T, args.steps), T, host=True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_h = S.solve_host(batch)
+    outs_h = run_steps(args.steps, T, host=True)
     barrier()
     e2e_s = time.perf_counter() - t0
+    out_h = outs_h[0]
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     ce = torch.tensor([float((out_h["status"] == 0).sum())], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -236,32 +300,63 @@ def main():
     if rank == 0:
         fp64 = C.c_double()
         check(lib().mmpc_bench_fp64(local, C.byref(fp64)))
-        kms = float(np.mean(kern_ms))
-        achieved_tf = work_flops / (kms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except OSError:
+            peak_src = "fallback 6650 GB/s (of fallback)"
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # units = instances one launch series processed: every instance is evaluated and factorised
+        # iters+1 times, stepped and tried iters times (extra line-search trials are not credited)
+        model = phase_model(N, n_obs, n_pl)
+        units = dict(eval=iters_sum + B, solve=iters_sum + B, step=iters_sum, trial=iters_sum)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except OSError:
             pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_ach = bytes_per_solve(N, n_obs, n_pl) * B / (kms * 1e-3) / 1e9
+        step_ms = float(np.mean(lat_ms))
+        phases = {}
+        for k in ("eval", "solve", "step", "trial"):
+            ms = phase_ms.get(k, 0.0)
+            gbs = model[k]["bytes"] * units[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            tfs = model[k]["flops"] * units[k] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            phases[k] = dict(ms=ms, share=ms / step_ms, launches=phase_ln.get(k, 0), bytes_per_instance=model[k]["bytes"],
+                             hbm_gbs=gbs, hbm_frac=gbs / hbm_peak, fp64_tflops=tfs, fp64_frac=tfs / float(fp64.value))
+        for k in ("compact", "ctrl_step", "ctrl_trial", "init"):
+            phases[k] = dict(ms=phase_ms.get(k, 0.0), share=phase_ms.get(k, 0.0) / step_ms, launches=phase_ln.get(k, 0))
+        dom = max(("eval", "solve", "step", "trial"), key=lambda k: phases[k]["ms"])
+        kname = {"eval": "mmpc::staged_eval_kernel", "solve": "mmpc::staged_solve_team_kernel",
+                 "step": "mmpc::staged_step_kernel", "trial": "mmpc::staged_trial_kernel"}[dom]
+        nl = max(1, phases[dom]["launches"])
+        tr = traffic.get(dom, {}).get("dram_bytes_per_instance")
+        work_flops = float(sum(flops_per_iteration(N, n_obs, int(p)) * int(i) for p, i in zip(batch["n_pl_inst"], iters_np)))
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f64", data="synthetic",
                     config=dict(workload="BASELINE config 3 shape: batch %d per GPU, mixed scenarios 1/2 (n_pl 3/2), "
                                          "16 random circles, N=20, dt=0.1, cold start (u_last=0)" % B,
-                                batch_per_gpu=B, horizon=N, n_obs=n_obs, n_pl_max=n_pl, nlp="clean",
-                                l2_policy="inputs+outputs %.0f MB per step exceed the 126 MB L2" % ((h2d + d2h) / 1e6),
+                                batch_per_gpu=B, horizon=N, n_obs=n_obs, n_pl_max=n_pl, nlp="clean", solver="staged",
+                                contexts=T,
+                                l2_policy="solver state %.1f GB per context and inputs+outputs %.0f MB per step exceed the 126 MB L2"
+                                          % (S.workspace_bytes() / 1e9, (h2d + d2h) / 1e6),
                                 converged_fraction=conv_all / B_all, mean_iterations=iters_all / B_all,
-                                instances_per_sm=S.occupancy()["instances_per_sm"]),
+                                rounds=rounds, single_context_ms_per_step=step_ms,
+                                single_context_value=conv / (step_ms * 1e-3), wall_ms_timed_region=wall_ms),
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-                    roofline=dict(bound="fp64", achieved=achieved_tf, peak=float(fp64.value), unit="TFLOP/s",
-                                  frac=achieved_tf / float(fp64.value), traffic=None,
-                                  peak_source="same-run DFMA micro-benchmark (mmpc_bench_fp64); nominal 37.2",
-                                  kernel="mmpc::solve_kernel", kernel_ms=kms,
-                                  hbm=dict(achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=hbm_ach / hbm_peak,
-                                           note="algorithmic bytes only: shows the path is not HBM-bound")))
+                    roofline=dict(bound="hbm", achieved=phases[dom]["hbm_gbs"], peak=hbm_peak, unit="GB/s",
+                                  frac=phases[dom]["hbm_frac"],
+                                  traffic=None if tr is None else tr * units[dom] / nl,
+                                  kernel=kname, kernel_ms=phases[dom]["ms"] / nl, kernel_launches=nl,
+                                  kernel_share_of_step=phases[dom]["share"], peak_source=peak_src,
+                                  algorithmic_bytes_per_launch=model[dom]["bytes"] * units[dom] / nl,
+                                  measured_in="single-context pass of %d steps, CUDA events around every launch" % args.steps,
+                                  fp64=dict(achieved=work_flops / (step_ms * 1e-3) / 1e12, peak=float(fp64.value), unit="TFLOP/s",
+                                            frac=work_flops / (step_ms * 1e-3) / 1e12 / float(fp64.value),
+                                            note="whole solve, SURVEY 8(d) flop count; peak = same-run DFMA micro-benchmark"),
+                                  phases=phases))
         if gathered is not None:
             line["config"]["nccl_gathered_rows"] = gathered
         if not args.no_cpu_baseline:

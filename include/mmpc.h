@@ -72,7 +72,8 @@ enum {
  *          (stage-parallel evaluation / step / trial, thread-per-instance Riccati); the default
  *   LANE   one persistent thread per instance, 32 instances per warp in lock-step
  *   WARP   one warp per instance, lanes cooperate on the stages of one horizon */
-enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2, MMPC_KERNEL_STAGED = 3 };
+enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2, MMPC_KERNEL_STAGED = 3,
+       MMPC_KERNEL_STAGED_THREAD = 4 /* STAGED with the one-thread-per-instance Riccati (A/B reference) */ };
 
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */
@@ -164,6 +165,21 @@ int mmpc_shift(MmpcHandle* h, int32_t B, const double* U, double* u_guess, void*
 /* Plant step without pybullet: x_next[b] = f_kinematics(x[b], u0[b])  interface_wholebody_qref.py:143 */
 int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const double* u0, double* x_next,
                     void* stream);
+
+/* Phases of the staged solver (one kernel each per round; COMPACT runs twice per round). */
+enum { MMPC_PHASE_COMPACT = 0, MMPC_PHASE_EVAL = 1, MMPC_PHASE_SOLVE = 2, MMPC_PHASE_STEP = 3, MMPC_PHASE_CTRL_STEP = 4,
+       MMPC_PHASE_TRIAL = 5, MMPC_PHASE_CTRL_TRIAL = 6, MMPC_PHASE_INIT = 7, MMPC_NPHASE = 8 };
+
+/* Device-side timing of the phases (measurement support for bench.py's roofline).  With profiling on,
+ * mmpc_solve brackets every launch of the staged solver with CUDA events on its stream and
+ * synchronises at the end of the call; mmpc_phase_times returns, for the last mmpc_solve, the
+ * accumulated device milliseconds and the number of launches per phase and the number of rounds. */
+int mmpc_set_profile(MmpcHandle* h, int32_t on);
+int mmpc_phase_times(const MmpcHandle* h, double* ms, int64_t* launches, int32_t* rounds);
+
+/* Device bytes of the staged solver's per-instance state for B_max instances (allocated by the first
+ * mmpc_solve; memory sizing for the 180 GB of one B200). */
+int mmpc_workspace_bytes(const MmpcHandle* h, int64_t* bytes);
 
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t mmpc_launch_count(const MmpcHandle* h);

@@ -12,7 +12,7 @@ from . import _abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libmmpc_b200.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_solver.cuh", "mmpc_lane.cuh", "mmpc_staged.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_solver.cuh", "mmpc_lane.cuh", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -53,6 +53,9 @@ def lib():
     L.mmpc_destroy.argtypes = [vp]
     L.mmpc_set_weights.argtypes = [vp, dp, dp, dp, dp, C.c_double]
     L.mmpc_set_kernel.argtypes = [vp, i32]
+    L.mmpc_set_profile.argtypes = [vp, i32]
+    L.mmpc_workspace_bytes.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.mmpc_phase_times.argtypes = [vp, dp, C.POINTER(C.c_int64), C.POINTER(i32)]
     L.mmpc_solve.argtypes = [vp, i32, C.POINTER(_abi.MmpcBatchIn), C.POINTER(_abi.MmpcBatchOut), vp]
     L.mmpc_solve_host.argtypes = [vp, i32, C.POINTER(_abi.MmpcBatchIn), C.POINTER(_abi.MmpcBatchOut)]
     L.mmpc_eval_model.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, vp]
@@ -76,5 +79,5 @@ def check(rc):
 
 
 EXPORTS = ("mmpc_version", "mmpc_error_string", "mmpc_default_config", "mmpc_create", "mmpc_destroy",
-           "mmpc_set_weights", "mmpc_set_kernel", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
+           "mmpc_set_weights", "mmpc_set_kernel", "mmpc_set_profile", "mmpc_phase_times", "mmpc_workspace_bytes", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
            "mmpc_plant_step", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")

@@ -51,7 +51,7 @@ class BatchSolver:
     def set_kernel(self, kernel):
         """'auto' | 'staged' (phase kernels over active lists) | 'lane' (thread per instance) | 'warp'."""
         k = {"auto": _abi.KERNEL_AUTO, "lane": _abi.KERNEL_LANE, "warp": _abi.KERNEL_WARP,
-             "staged": _abi.KERNEL_STAGED}.get(kernel, kernel)
+             "staged": _abi.KERNEL_STAGED, "staged_thread": _abi.KERNEL_STAGED_THREAD}.get(kernel, kernel)
         check(lib().mmpc_set_kernel(self._h, int(k)))
 
     # -- lifetime -----------------------------------------------------------------------------
@@ -74,6 +74,24 @@ class BatchSolver:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         check(lib().mmpc_occupancy(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(sm_count=a.value, instances_per_sm=b.value, smem_bytes=c.value)
+
+    PHASES = ("compact", "eval", "solve", "step", "ctrl_step", "trial", "ctrl_trial", "init")
+
+    def set_profile(self, on=True):
+        check(lib().mmpc_set_profile(self._h, int(bool(on))))
+
+    def phase_times(self):
+        """Device ms and launches per phase of the last solve (needs set_profile(True)), and its rounds."""
+        ms = (C.c_double * 8)(); ln = (C.c_int64 * 8)(); rounds = C.c_int32()
+        check(lib().mmpc_phase_times(self._h, ms, ln, C.byref(rounds)))
+        return ({p: ms[i] for i, p in enumerate(self.PHASES)}, {p: int(ln[i]) for i, p in enumerate(self.PHASES)},
+                int(rounds.value))
+
+    def workspace_bytes(self):
+        """Device bytes of the staged solver's state for B_max instances (allocated on first solve)."""
+        v = C.c_int64()
+        check(lib().mmpc_workspace_bytes(self._h, C.byref(v)))
+        return int(v.value)
 
     def launch_count(self):
         return int(lib().mmpc_launch_count(self._h))

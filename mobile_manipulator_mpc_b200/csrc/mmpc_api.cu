@@ -6,11 +6,13 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 #include "../../include/mmpc.h"
 #include "mmpc_solver.cuh"
 #include "mmpc_lane.cuh"
 #include "mmpc_staged.cuh"
+#include "mmpc_team.cuh"
 
 using namespace mmpc;
 
@@ -24,12 +26,17 @@ struct MmpcHandle {
   unsigned* counter;
   long long launches;
   // lane-per-instance kernel: resident warps, interleaved workspace (allocated on first use)
-  int kernel, lane_warps_per_sm, lane_warps;
+  int kernel, lane_warps_per_sm, lane_warps, sg_team;
   long long lane_warp_stride;
   double* lane_ws;
   // staged (batch-synchronous) solver: field-major state, per-instance scalars, lists, counters
-  struct { double *ws, *gd; int *gi, *lists, *cnt; long long LS; int* pin; cudaEvent_t ev[8]; bool ready;
+  struct { double *ws, *qp, *rk, *gd; int *gi, *lists, *cnt; long long LS; int* pin; cudaEvent_t ev[8]; bool ready;
            int rounds; } sg;
+  // per-phase device timing of the staged solver (mmpc_set_profile / mmpc_phase_times)
+  int profile;
+  std::vector<cudaEvent_t>* prof_ev;
+  double phase_ms[MMPC_NPHASE];
+  long long phase_launches[MMPC_NPHASE];
   // staging for mmpc_solve_host
   struct { double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes, *U, *X, *s, *cost, *kkt;
            int32_t *n_pl_inst, *iters, *status; uint8_t* flags; } d, h;
@@ -118,7 +125,7 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   CK(cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * sizeof(double)));
   CK(cudaMalloc(&h->counter, sizeof(unsigned)));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  h->kernel = MMPC_KERNEL_AUTO;
+  h->kernel = MMPC_KERNEL_AUTO; h->sg_team = 1;
   h->lane_warps_per_sm = 8;
   h->lane_warp_stride = lane_instance_doubles(*cfg) * 32;
   {
@@ -144,8 +151,9 @@ extern "C" int mmpc_destroy(MmpcHandle* h) {
   free_staging(h);
   if (h->ws) cudaFree(h->ws);
   if (h->lane_ws) cudaFree(h->lane_ws);
+  if (h->prof_ev) { for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e); delete h->prof_ev; }
   if (h->sg.ready) {
-    cudaFree(h->sg.ws); cudaFree(h->sg.gd); cudaFree(h->sg.gi); cudaFree(h->sg.lists); cudaFree(h->sg.cnt);
+    cudaFree(h->sg.ws); cudaFree(h->sg.qp); cudaFree(h->sg.rk); cudaFree(h->sg.gd); cudaFree(h->sg.gi); cudaFree(h->sg.lists); cudaFree(h->sg.cnt);
     cudaFreeHost(h->sg.pin);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->sg.ev[i]);
   }
@@ -166,8 +174,9 @@ extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* P
 }
 
 extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
-  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_STAGED) return MMPC_ERR_ARG;
-  h->kernel = kernel;
+  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_STAGED_THREAD) return MMPC_ERR_ARG;
+  h->sg_team = kernel != MMPC_KERNEL_STAGED_THREAD;
+  h->kernel = kernel == MMPC_KERNEL_STAGED_THREAD ? MMPC_KERNEL_STAGED : kernel;
   return MMPC_OK;
 }
 
@@ -218,6 +227,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     long long LS = ((long long)h->B_max + 31) / 32 * 32;
     h->sg.LS = LS;
     CK(cudaMalloc(&h->sg.ws, (size_t)(N + 1) * STG * LS * sizeof(double)));
+    CK(cudaMalloc(&h->sg.qp, (size_t)(N + 1) * QS * LS * sizeof(double)));
+    CK(cudaMalloc(&h->sg.rk, (size_t)(N + 1) * RS * LS * sizeof(double)));
     CK(cudaMalloc(&h->sg.gd, (size_t)staged_inst_doubles(cfg) * LS * sizeof(double)));
     CK(cudaMalloc(&h->sg.gi, (size_t)J_NFIELDS * LS * sizeof(int)));
     CK(cudaMalloc(&h->sg.lists, (size_t)2 * LS * sizeof(int)));
@@ -231,8 +242,24 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
   P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
   P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
-  P.ws = h->sg.ws; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
+  P.ws = h->sg.ws; P.qp = h->sg.qp; P.rk = h->sg.rk; P.team = h->sg_team; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
   P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = STG;
+  // profiling: one timing event in front of every launch; the time up to the next event is
+  // charged to that launch's phase (events are stream-ordered, so this is device time)
+  std::vector<int> marks;
+  size_t nmark = 0;
+  auto mark = [&](int phase) -> int {
+    h->phase_launches[phase < 0 ? 0 : phase] += (phase >= 0);
+    if (!h->profile) return MMPC_OK;
+    if (!h->prof_ev) h->prof_ev = new std::vector<cudaEvent_t>();
+    if (nmark == h->prof_ev->size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->prof_ev->push_back(e); }
+    CK(cudaEventRecord((*h->prof_ev)[nmark++], st));
+    marks.push_back(phase);
+    return MMPC_OK;
+  };
+#define MARK(ph) do { int rc_ = mark(ph); if (rc_ != MMPC_OK) return rc_; } while (0)
+  for (int i = 0; i < MMPC_NPHASE; ++i) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
+  MARK(MMPC_PHASE_INIT);
   staged_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(P);
   CK(cudaGetLastError());
   h->launches += 1;
@@ -243,14 +270,24 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     long long items = ub * (N + 1);
     int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
     int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
-    if (gs < 1) gs = 1; if (gi_ < 1) gi_ = 1; if (g64 < 1) g64 = 1;
+    int gt = (int)((ub * 16 + 127) / 128);
+    if (gs < 1) gs = 1; if (gi_ < 1) gi_ = 1; if (g64 < 1) g64 = 1; if (gt < 1) gt = 1;
+    MARK(MMPC_PHASE_COMPACT);
     staged_compact_kernel<<<1, 1024, 0, st>>>(P, 0, ST_ACTIVE);
+    MARK(MMPC_PHASE_EVAL);
     staged_eval_kernel<<<gs, 128, 0, st>>>(P);
-    staged_solve_kernel<<<g64, 64, 0, st>>>(P);
+    MARK(MMPC_PHASE_SOLVE);
+    if (P.team) staged_solve_team_kernel<<<gt, 128, 0, st>>>(P);
+    else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
+    MARK(MMPC_PHASE_STEP);
     staged_step_kernel<<<gs, 128, 0, st>>>(P);
+    MARK(MMPC_PHASE_CTRL_STEP);
     staged_ctrl_step_kernel<<<gi_, 128, 0, st>>>(P);
+    MARK(MMPC_PHASE_COMPACT);
     staged_compact_kernel<<<1, 1024, 0, st>>>(P, 1, ST_TRIAL);
+    MARK(MMPC_PHASE_TRIAL);
     staged_trial_kernel<<<gs, 128, 0, st>>>(P);
+    MARK(MMPC_PHASE_CTRL_TRIAL);
     staged_ctrl_trial_kernel<<<gi_, 128, 0, st>>>(P);
     CK(cudaGetLastError());
     h->launches += 8;
@@ -269,6 +306,15 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     }
     if (r > 4000000) break;
   }
+  if (h->profile) {
+    MARK(-1);
+    CK(cudaEventSynchronize((*h->prof_ev)[nmark - 1]));
+    for (size_t i = 0; i + 1 < nmark; ++i) {
+      float ms = 0; CK(cudaEventElapsedTime(&ms, (*h->prof_ev)[i], (*h->prof_ev)[i + 1]));
+      if (marks[i] >= 0) h->phase_ms[marks[i]] += ms;
+    }
+  }
+#undef MARK
   h->sg.rounds = r + 1;
   return MMPC_OK;
 }
@@ -444,6 +490,30 @@ extern "C" int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const 
   plant_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, h->cfg.dt, x, u0, x_next);
   CK(cudaGetLastError());
   h->launches += 1;
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_workspace_bytes(const MmpcHandle* h, int64_t* bytes) {
+  if (!h || !bytes) return MMPC_ERR_ARG;
+  const MmpcConfig& c = h->cfg;
+  long long LS = ((long long)h->B_max + 31) / 32 * 32, st = c.N + 1;
+  *bytes = (int64_t)(8 * LS * (st * (staged_stage_doubles(c) + QS + RS) + staged_inst_doubles(c)) + 4 * LS * (J_NFIELDS + 2));
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_set_profile(MmpcHandle* h, int32_t on) {
+  if (!h) return MMPC_ERR_ARG;
+  h->profile = on != 0;
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_phase_times(const MmpcHandle* h, double* ms, int64_t* launches, int32_t* rounds) {
+  if (!h) return MMPC_ERR_ARG;
+  for (int i = 0; i < MMPC_NPHASE; ++i) {
+    if (ms) ms[i] = h->phase_ms[i];
+    if (launches) launches[i] = h->phase_launches[i];
+  }
+  if (rounds) *rounds = h->sg.rounds;
   return MMPC_OK;
 }
 

@@ -47,27 +47,32 @@ struct SParams {
   double *U, *X, *s, *cost, *kkt;
   int32_t *iters, *status;
   double* ws;      // per-stage records, field-major / instance-minor
+  double* qp;      // stage QP records      qp[(k*LS + b)*QS + f]
+  double* rk;      // Riccati records       rk[(k*LS + b)*RS + f]
   double* gd;      // per-instance doubles  gd[field * LS + b]
   int* gi;         // per-instance ints     gi[field * LS + b]
   int* lists;      // 2 lists of LS ints: E (next phase eval), T (next phase trial)
   int* cnt;        // their lengths
   long long LS;    // instance stride (B_max rounded up)
   int R, STG, ITSZ;
+  int team;        // 1: 16-lane column-parallel Riccati (mmpc_team.cuh), 0: one thread per instance
 };
 
 // ---- iterate buffer (two copies, ping-pong): offsets inside one copy --------------------------
 constexpr int I_X = 0, I_U = 9, I_S = 14, I_LAM = 15, I_ZXL = 24, I_ZXU = 33, I_ZUL = 42, I_ZUU = 47, I_T = 52;
-// ---- after the two iterate copies -----------------------------------------------------------------
+// ---- after the two iterate copies (field-major, like the iterate) -----------------------------------
 constexpr int S_DX = 0, S_DU = 9, S_DS = 14, S_LAMN = 15, S_FK = 24, S_DFC = 32, S_PART = 41;
-// stage QP: pose Hessian (21 packed) | velocity diagonal 3 | (dx,dpsi) (dy,dpsi) | control diagonal 5 |
-// (psi,u0) | a = H[pose][s] 6 | c = H[s][s] | bv = H[pose][v] 6 | hvv | gA 16 | gB 16   (y = x9 s u5 v)
-constexpr int Q_HP = 49, Q_HVD = 70, Q_H35 = 73, Q_H45 = 74, Q_HUU = 75, Q_HPU = 80, Q_A = 81, Q_C = 87,
-              Q_BV = 88, Q_HVV = 94, Q_GA = 95, Q_GB = 111;
-// Riccati: K 45 | kff 5 | w 14 | cv | l0 | Pxx 45 | pxx 9
-constexpr int R_K = 127, R_KFF = 172, R_W = 177, R_CV = 191, R_L0 = 192, R_P = 193, R_PV = 238;
-constexpr int IN_XREF = 247, IN_UREF = 256, IN_ULAST = 261, IN_ULO = 266, IN_UHI = 271;
-constexpr int S_DT = 276;  // dt[R], then (moving obstacles) circles[3*nobs]
-constexpr int S_FIXED = 276;
+constexpr int IN_XREF = 49, IN_UREF = 58, IN_ULAST = 63, IN_ULO = 68, IN_UHI = 73;
+constexpr int S_DT = 78;  // dt[R], then (moving obstacles) circles[3*nobs]
+constexpr int S_FIXED = 78;
+// ---- stage QP record, contiguous per (stage, instance):  qp[(k*LS + b)*QS + f] ------------------------
+// pose Hessian (21 packed) | velocity diagonal 3 | (dx,dpsi) (dy,dpsi) | control diagonal 5 | (psi,u0) |
+// a = H[pose][s] 6 | c = H[s][s] | bv = H[pose][v] 6 | hvv | gA 16 | gB 16   (y = x9 s u5 v)
+constexpr int Q_HP = 0, Q_HVD = 21, Q_H35 = 24, Q_H45 = 25, Q_HUU = 26, Q_HPU = 31, Q_A = 32, Q_C = 38,
+              Q_BV = 39, Q_HVV = 45, Q_GA = 46, Q_GB = 62, QS = 80;
+// ---- Riccati record, contiguous per (stage, instance):  rk[(k*LS + b)*RS + f] -------------------------
+// K 45 | kff 5 | w 14 | cv | l0 | Pxx 45 (packed) | pxx 9
+constexpr int R_K = 0, R_KFF = 45, R_W = 50, R_CV = 64, R_L0 = 65, R_P = 66, R_PV = 111, RS = 120;
 constexpr int SGY_S = 9, SGY_U = 10, SGY_V = 15;
 // per-instance doubles
 constexpr int D_MU = 0, D_REGLAST = 1, D_THMAX = 2, D_THMIN = 3, D_E0 = 4, D_OS = 5, D_ALPHA = 6, D_AD = 7,
@@ -105,6 +110,8 @@ struct Inst {
   }
   __device__ __forceinline__ double& W(int k, int o) const { return w[((long long)k * STG + o) * LS]; }
   __device__ __forceinline__ double& W2(int k, int o) const { return w[((long long)k * STG + B2 + o) * LS]; }
+  __device__ __forceinline__ double& Qw(int k, int o) const { return P.qp[((long long)k * LS + b) * QS + o]; }
+  __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
   __device__ __forceinline__ double& D(int o) const { return gd[(long long)o * LS]; }
   __device__ __forceinline__ int& J(int o) const { return gi[(long long)o * LS]; }
   __device__ __forceinline__ double circ(int k, int i, int c) const {
@@ -261,9 +268,9 @@ struct Inst {
       }
       n_eq = NX;
       hpp = -dt * u[0] * (lam1[3] * f.cp + lam1[4] * f.sp);
-      W2(k, Q_HPU) = dt * (-lam1[3] * f.sp + lam1[4] * f.cp);
-      W2(k, Q_H45) = -dt * lam1[3];  // (dy,dpsi)
-      W2(k, Q_H35) = dt * lam1[4];   // (dx,dpsi)
+      Qw(k, Q_HPU) = dt * (-lam1[3] * f.sp + lam1[4] * f.cp);
+      Qw(k, Q_H45) = -dt * lam1[3];  // (dy,dpsi)
+      Qw(k, Q_H35) = dt * lam1[4];   // (dx,dpsi)
       stx[0] = lam1[0]; stx[1] = lam1[1];
       stx[2] = lam1[2] + dt * u[0] * (-f.sp * lam1[3] + f.cp * lam1[4]);
       stx[3] = dt * lam1[0] + lam1[3] + dt * x[5] * lam1[4];
@@ -274,7 +281,7 @@ struct Inst {
       stu[1] = dt * lam1[5];
       stu[2] = dt * lam1[6]; stu[3] = dt * lam1[7]; stu[4] = dt * lam1[8];
     } else {
-      W2(k, Q_HPU) = 0; W2(k, Q_H45) = 0; W2(k, Q_H35) = 0;
+      Qw(k, Q_HPU) = 0; Qw(k, Q_H45) = 0; Qw(k, Q_H35) = 0;
     }
     // cost and boxes -- :192-205, :240-245.  Pose components seed the row accumulators, the
     // others are final here.
@@ -300,7 +307,7 @@ struct Inst {
         const int a = (i < 3) ? i : i - 3;
         A.H[pidx(a, a)] = Hd + (i == 2 ? hpp : 0.0); A.gA[a] = gA; A.gB[a] = gB; A.st[a] = st;
       } else {
-        W2(k, Q_HVD + (i - 3)) = Hd; W2(k, Q_GA + i) = gA; W2(k, Q_GB + i) = gB;
+        Qw(k, Q_HVD + (i - 3)) = Hd; Qw(k, Q_GA + i) = gA; Qw(k, Q_GB + i) = gB;
         if (k >= 1) es = fmax(es, fabs(st));
       }
     }
@@ -325,7 +332,7 @@ struct Inst {
         }
         es = fmax(es, fabs(st));
       }
-      W2(k, Q_HUU + j) = Hd; W2(k, Q_GA + SGY_U + j) = gA; W2(k, Q_GB + SGY_U + j) = gB;
+      Qw(k, Q_HUU + j) = Hd; Qw(k, Q_GA + SGY_U + j) = gA; Qw(k, Q_GB + SGY_U + j) = gB;
     }
     // inequality rows with slack:  h(x_k) - s_k + t = 0
     for (int i = 0; i < nobs; ++i) {  // obsAvoid :49-54
@@ -382,18 +389,18 @@ struct Inst {
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
     double S2 = 2 * os * cfg.S;
-    W2(k, Q_C) = S2 + A.csum;
-    W2(k, Q_GA + SGY_S) = S2 * s - A.be0;
-    W2(k, Q_GB + SGY_S) = -A.be1;
-    W2(k, Q_HVV) = 0; W2(k, Q_GA + SGY_V) = 0; W2(k, Q_GB + SGY_V) = 0;
+    Qw(k, Q_C) = S2 + A.csum;
+    Qw(k, Q_GA + SGY_S) = S2 * s - A.be0;
+    Qw(k, Q_GB + SGY_S) = -A.be1;
+    Qw(k, Q_HVV) = 0; Qw(k, Q_GA + SGY_V) = 0; Qw(k, Q_GB + SGY_V) = 0;
 #pragma unroll
     for (int a = 0; a < NP; ++a) {
-      W2(k, Q_A + a) = A.a[a]; W2(k, Q_BV + a) = 0;
-      W2(k, Q_GA + POSE2X[a]) = A.gA[a]; W2(k, Q_GB + POSE2X[a]) = A.gB[a];
+      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = 0;
+      Qw(k, Q_GA + POSE2X[a]) = A.gA[a]; Qw(k, Q_GB + POSE2X[a]) = A.gB[a];
       if (k >= 1) es = fmax(es, fabs(A.st[a]));
     }
 #pragma unroll
-    for (int e = 0; e < 21; ++e) W2(k, Q_HP + e) = A.H[e];
+    for (int e = 0; e < 21; ++e) Qw(k, Q_HP + e) = A.H[e];
     es = fmax(es, fabs(S2 * s - A.zrows));
     W2(k, S_PART + 0) = es; W2(k, S_PART + 1) = A.prim; W2(k, S_PART + 2) = A.chi; W2(k, S_PART + 3) = A.clo;
     W2(k, S_PART + 4) = sum_lam; W2(k, S_PART + 5) = A.sumz; W2(k, S_PART + 6) = (double)A.nz; W2(k, S_PART + 7) = (double)n_eq;
@@ -431,21 +438,21 @@ struct Inst {
 #pragma unroll
       for (int a = 0; a < NP; ++a)
 #pragma unroll
-        for (int c = a; c < NP; ++c) Pm[ssidx(POSE2X[a], POSE2X[c])] = W2(N, Q_HP + pidx(a, c));
+        for (int c = a; c < NP; ++c) Pm[ssidx(POSE2X[a], POSE2X[c])] = Qw(N, Q_HP + pidx(a, c));
 #pragma unroll
-      for (int q = 0; q < 3; ++q) Pm[ssidx(3 + q, 3 + q)] = W2(N, Q_HVD + q);
+      for (int q = 0; q < 3; ++q) Pm[ssidx(3 + q, 3 + q)] = Qw(N, Q_HVD + q);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         Pm[ssidx(i, i)] += reg;
-        pv[i] = W2(N, Q_GA + i) + mu * W2(N, Q_GB + i);
+        pv[i] = Qw(N, Q_GA + i) + mu * Qw(N, Q_GB + i);
       }
 #pragma unroll
-      for (int a = 0; a < NP; ++a) an[a] = W2(N, Q_A + a);
-      cn = W2(N, Q_C); gsn = W2(N, Q_GA + SGY_S) + mu * W2(N, Q_GB + SGY_S);
+      for (int a = 0; a < NP; ++a) an[a] = Qw(N, Q_A + a);
+      cn = Qw(N, Q_C); gsn = Qw(N, Q_GA + SGY_S) + mu * Qw(N, Q_GB + SGY_S);
 #pragma unroll
-      for (int e = 0; e < 45; ++e) W2(N, R_P + e) = Pm[e];
+      for (int e = 0; e < 45; ++e) Rw(N, R_P + e) = Pm[e];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) W2(N, R_PV + i) = pv[i];
+      for (int i = 0; i < NX; ++i) Rw(N, R_PV + i) = pv[i];
     }
     int bad = 0;
     for (int k = N - 1; k >= 0; --k) {
@@ -462,7 +469,7 @@ struct Inst {
         for (int q = 0; q < NX; ++q) v = fma(Pm[ssidx(i, q)], d[q], v);
         pd[i] = v;
       }
-      double l0 = gsn + W2(k, Q_GA + SGY_V) + mu * W2(k, Q_GB + SGY_V);
+      double l0 = gsn + Qw(k, Q_GA + SGY_V) + mu * Qw(k, Q_GB + SGY_V);
 #pragma unroll
       for (int a = 0; a < NP; ++a) l0 = fma(an[a], d[POSE2X[a]], l0);
       // C = (P A)[:, 2..5]
@@ -484,7 +491,7 @@ struct Inst {
         Mux[1][j] = c.dt * PA_(5, j);
         Mux[2][j] = c.dt * PA_(6, j); Mux[3][j] = c.dt * PA_(7, j); Mux[4][j] = c.dt * PA_(8, j);
       }
-      Mux[0][2] += W2(k, Q_HPU);
+      Mux[0][2] += Qw(k, Q_HPU);
       {
         const double dd = c.dt * c.dt;
         double q33 = Pm[ssidx(3, 3)], q34 = Pm[ssidx(3, 4)], q44 = Pm[ssidx(4, 4)];
@@ -499,11 +506,11 @@ struct Inst {
 #pragma unroll
           for (int b2 = a; b2 < NU; ++b2) Muu[a * 5 - a * (a - 1) / 2 + (b2 - a)] = dd * Pm[ssidx(4 + a, 4 + b2)];
 #pragma unroll
-        for (int a = 0; a < NU; ++a) Muu[a * 5 - a * (a - 1) / 2] += W2(k, Q_HUU + a) + reg;
+        for (int a = 0; a < NU; ++a) Muu[a * 5 - a * (a - 1) / 2] += Qw(k, Q_HUU + a) + reg;
       }
       bt_mul(pd, mvu, c);
 #pragma unroll
-      for (int a = 0; a < NU; ++a) mvu[a] += W2(k, Q_GA + SGY_U + a) + mu * W2(k, Q_GB + SGY_U + a);
+      for (int a = 0; a < NU; ++a) mvu[a] += Qw(k, Q_GA + SGY_U + a) + mu * Qw(k, Q_GB + SGY_U + a);
       // Mxx = A^T (P A) + H_xx + reg (upper triangle, packed)
       double Mxx[45], mvx[NX];
 #pragma unroll
@@ -522,15 +529,15 @@ struct Inst {
 #pragma unroll
       for (int a = 0; a < NP; ++a)
 #pragma unroll
-        for (int c2 = a; c2 < NP; ++c2) Mxx[ssidx(POSE2X[a], POSE2X[c2])] += W2(k, Q_HP + pidx(a, c2));
+        for (int c2 = a; c2 < NP; ++c2) Mxx[ssidx(POSE2X[a], POSE2X[c2])] += Qw(k, Q_HP + pidx(a, c2));
 #pragma unroll
-      for (int q = 0; q < 3; ++q) Mxx[ssidx(3 + q, 3 + q)] += W2(k, Q_HVD + q);
-      Mxx[ssidx(3, 5)] += W2(k, Q_H35); Mxx[ssidx(4, 5)] += W2(k, Q_H45);
+      for (int q = 0; q < 3; ++q) Mxx[ssidx(3 + q, 3 + q)] += Qw(k, Q_HVD + q);
+      Mxx[ssidx(3, 5)] += Qw(k, Q_H35); Mxx[ssidx(4, 5)] += Qw(k, Q_H45);
 #pragma unroll
       for (int i = 0; i < NX; ++i) { Mxx[ssidx(i, i)] += reg; mvx[i] = pd[i]; }
       at_mul(mvx, c);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) mvx[i] += W2(k, Q_GA + i) + mu * W2(k, Q_GB + i);
+      for (int i = 0; i < NX; ++i) mvx[i] += Qw(k, Q_GA + i) + mu * Qw(k, Q_GB + i);
       // eliminate v_k = s_{k+1}:  w = [A^T a(k+1) + bv(k) ; B^T a(k+1)],  cv = hvv(k) + c(k+1)
       double wx[NX], wu[NU];
 #pragma unroll
@@ -540,8 +547,8 @@ struct Inst {
       bt_mul(wx, wu, c);
       at_mul(wx, c);
 #pragma unroll
-      for (int a = 0; a < NP; ++a) wx[POSE2X[a]] += W2(k, Q_BV + a);
-      double cv = W2(k, Q_HVV) + cn, icv = 1.0 / cv;
+      for (int a = 0; a < NP; ++a) wx[POSE2X[a]] += Qw(k, Q_BV + a);
+      double cv = Qw(k, Q_HVV) + cn, icv = 1.0 / cv;
       bad |= !(cv > 1e-13);
       {
         double l0c = l0 * icv;
@@ -601,8 +608,8 @@ struct Inst {
           for (int q = i + 1; q < NU; ++q) y[i] -= L[q][i] * y[q];
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
-          if (j < NX) { Kc[a][j < NX ? j : 0] = -y[a]; W2(k, R_K + a * NX + (j < NX ? j : 0)) = -y[a]; }
-          else { kff[a] = -y[a]; W2(k, R_KFF + a) = -y[a]; }
+          if (j < NX) { Kc[a][j < NX ? j : 0] = -y[a]; Rw(k, R_K + a * NX + (j < NX ? j : 0)) = -y[a]; }
+          else { kff[a] = -y[a]; Rw(k, R_KFF + a) = -y[a]; }
         }
       }
       // P_k = Mxx + Mux^T K ; p_k = m_x + Mux^T kff
@@ -613,21 +620,21 @@ struct Inst {
           double v = Mxx[ssidx(i, j)];
 #pragma unroll
           for (int a = 0; a < NU; ++a) v = fma(Mux[a][i], Kc[a][j], v);
-          Pm[ssidx(i, j)] = v; W2(k, R_P + ssidx(i, j)) = v;
+          Pm[ssidx(i, j)] = v; Rw(k, R_P + ssidx(i, j)) = v;
         }
         double v = mvx[i];
 #pragma unroll
         for (int a = 0; a < NU; ++a) v = fma(Mux[a][i], kff[a], v);
-        pv[i] = v; W2(k, R_PV + i) = v;
+        pv[i] = v; Rw(k, R_PV + i) = v;
       }
 #pragma unroll
-      for (int i = 0; i < NX; ++i) W2(k, R_W + i) = wx[i];
+      for (int i = 0; i < NX; ++i) Rw(k, R_W + i) = wx[i];
 #pragma unroll
-      for (int a = 0; a < NU; ++a) W2(k, R_W + NX + a) = wu[a];
-      W2(k, R_CV) = cv; W2(k, R_L0) = l0;
+      for (int a = 0; a < NU; ++a) Rw(k, R_W + NX + a) = wu[a];
+      Rw(k, R_CV) = cv; Rw(k, R_L0) = l0;
 #pragma unroll
-      for (int a = 0; a < NP; ++a) an[a] = W2(k, Q_A + a);
-      cn = W2(k, Q_C); gsn = W2(k, Q_GA + SGY_S) + mu * W2(k, Q_GB + SGY_S);
+      for (int a = 0; a < NP; ++a) an[a] = Qw(k, Q_A + a);
+      cn = Qw(k, Q_C); gsn = Qw(k, Q_GA + SGY_S) + mu * Qw(k, Q_GB + SGY_S);
     }
     if (!(cn > 1e-13)) return 1;
     return 0;
@@ -639,23 +646,23 @@ struct Inst {
     double dxv[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { dxv[i] = 0; W2(0, S_DX + i) = 0; }
-    double dsv = -(W2(0, Q_GA + SGY_S) + mu * W2(0, Q_GB + SGY_S)) / W2(0, Q_C);
+    double dsv = -(Qw(0, Q_GA + SGY_S) + mu * Qw(0, Q_GB + SGY_S)) / Qw(0, Q_C);
     W2(0, S_DS) = dsv;
     for (int k = 0; k < N; ++k) {
       double duv[NU];
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        double v = W2(k, R_KFF + a);
+        double v = Rw(k, R_KFF + a);
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v = fma(W2(k, R_K + a * NX + j), dxv[j], v);
+        for (int j = 0; j < NX; ++j) v = fma(Rw(k, R_K + a * NX + j), dxv[j], v);
         duv[a] = v; W2(k, S_DU + a) = v;
       }
-      double l = W2(k, R_L0);
+      double l = Rw(k, R_L0);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) l = fma(W2(k, R_W + i), dxv[i], l);
+      for (int i = 0; i < NX; ++i) l = fma(Rw(k, R_W + i), dxv[i], l);
 #pragma unroll
-      for (int a = 0; a < NU; ++a) l = fma(W2(k, R_W + NX + a), duv[a], l);
-      dsv = -l / W2(k, R_CV);
+      for (int a = 0; a < NU; ++a) l = fma(Rw(k, R_W + NX + a), duv[a], l);
+      dsv = -l / Rw(k, R_CV);
       SACoef c = acoef(k, it);
       double nx_[NX];
       nx_[0] = dxv[0] + dt * dxv[3]; nx_[1] = dxv[1] + dt * dxv[4]; nx_[2] = dxv[2] + dt * dxv[5];
@@ -668,11 +675,11 @@ struct Inst {
       W2(k + 1, S_DS) = dsv;
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = W2(k + 1, R_PV + i);
+        double v = Rw(k + 1, R_PV + i);
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v = fma(W2(k + 1, R_P + ssidx(i, j)), dxv[j], v);
-        if (i < 3) v = fma(W2(k + 1, Q_A + i), dsv, v);
-        if (i >= 6) v = fma(W2(k + 1, Q_A + (i - 3)), dsv, v);
+        for (int j = 0; j < NX; ++j) v = fma(Rw(k + 1, R_P + ssidx(i, j)), dxv[j], v);
+        if (i < 3) v = fma(Qw(k + 1, Q_A + i), dsv, v);
+        if (i >= 6) v = fma(Qw(k + 1, Q_A + (i - 3)), dsv, v);
         W2(k + 1, S_LAMN + i) = v;
       }
     }

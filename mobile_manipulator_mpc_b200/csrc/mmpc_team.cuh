@@ -1,0 +1,455 @@
+// mmpc_team.cuh -- the sequential part of one interior-point iteration (KKT reduction, barrier
+// update, Riccati factorisation with inertia correction, roll-out of the Newton step) executed by
+// a TEAM of 16 lanes per instance, two instances per warp.
+//
+// Column-parallel Riccati.  Lane c of the team owns one column of the stage system over (x, u):
+//     c = 0..8   x-columns      c = 9..13   u-columns      c = 14   right-hand side      c = 15 idle
+// The cost-to-go P(k+1) lives in the registers of lanes 0..8 (one column each) for the whole backward
+// sweep.  A stage is:  Y = P [A B]  (the few columns A and B couple are fetched from the neighbour
+// lanes with width-16 shuffles),  M = [A B]^T Y + H  (local),  rank-one elimination of the stage slack
+// v_k = s_{k+1}  (local),  right-looking LDL^T of the u block (the pivot column is broadcast, every
+// lane updates its own column, so P(k) and p(k) simply remain in lanes 0..8 and 14), back-substitution
+// for the gains (local).  Per stage and lane: ~200 DFMA, ~190 double shuffles, no shared memory, no
+// local memory, ~20x shorter dependency chain than the one-thread-per-instance recursion -- this
+// kernel sets the latency of a round once the batch has thinned out.
+//
+// Every decision (pivot signs, convergence, barrier update) is taken on values that are bit-identical
+// in all 16 lanes (broadcast values, butterfly reductions), so a team never diverges at a shuffle; the
+// two teams of a warp may diverge from each other (they use disjoint shuffle masks).
+#pragma once
+#include "mmpc_staged.cuh"
+
+namespace mmpc {
+
+// index into the packed stage-QP record of entry (r, c) of the (x, u) Hessian, -1 if structurally zero
+__host__ __device__ constexpr int team_hidx(int r, int c) {
+  if (r > c) { int t = r; r = c; c = t; }
+  const int X2P[9] = {0, 1, 2, -1, -1, -1, 3, 4, 5};
+  if (c < 9) {
+    int pr = X2P[r], pc = X2P[c];
+    if (pr >= 0 && pc >= 0) return Q_HP + pidx(pr, pc);
+    if (pr < 0 && pc < 0) {
+      if (r == c) return Q_HVD + (r - 3);
+      if (r == 3 && c == 5) return Q_H35;
+      if (r == 4 && c == 5) return Q_H45;
+    }
+    return -1;
+  }
+  if (r >= 9) return r == c ? Q_HUU + (r - 9) : -1;
+  return (r == 2 && c == 9) ? Q_HPU : -1;
+}
+struct TeamTable {
+  signed char v[14][16];
+  constexpr TeamTable() : v() {
+    for (int r = 0; r < 14; ++r)
+      for (int c = 0; c < 16; ++c) v[r][c] = (signed char)(c < 14 ? team_hidx(r, c) : -1);
+  }
+};
+__device__ constexpr TeamTable TEAM_TABLE = TeamTable();
+
+struct Team {
+  Inst S;
+  const signed char* ht;  // [14][16] table (shared memory on the GPU)
+  int c;                  // lane of the team
+  __device__ __forceinline__ Team(const SParams& p, int b, int c_, const signed char* ht_, double* sm_) : S(p, b), ht(ht_), c(c_), sm(sm_) {}
+
+  __device__ __forceinline__ static double tsum(double v) {
+#pragma unroll
+    for (int m = 8; m > 0; m >>= 1) v += shfl16_xor(v, m);
+    return v;
+  }
+  __device__ __forceinline__ static double tmax(double v) {
+#pragma unroll
+    for (int m = 8; m > 0; m >>= 1) v = fmax(v, shfl16_xor(v, m));
+    return v;
+  }
+  __device__ __forceinline__ static double tmin(double v) {
+#pragma unroll
+    for (int m = 8; m > 0; m >>= 1) v = fmin(v, shfl16_xor(v, m));
+    return v;
+  }
+
+  // m[0..13] = [A B]^T y
+  __device__ __forceinline__ static void abt_mul(const double (&y)[9], const SACoef& a, double (&m)[14]) {
+    m[0] = y[0]; m[1] = y[1];
+    m[2] = y[2] + a.a32 * y[3] + a.a42 * y[4];
+    m[3] = y[3] + a.dt * y[0] + a.a43 * y[4];
+    m[4] = y[4] + a.dt * y[1] + a.a34 * y[3];
+    m[5] = y[5] + a.dt * y[2] + a.a35 * y[3] + a.a45 * y[4];
+    m[6] = y[6]; m[7] = y[7]; m[8] = y[8];
+    m[9] = a.dt * (a.cp * y[3] + a.sp * y[4]); m[10] = a.dt * y[5];
+    m[11] = a.dt * y[6]; m[12] = a.dt * y[7]; m[13] = a.dt * y[8];
+  }
+
+  // ---- shared-memory prefetch ring (cp.async) ---------------------------------------------------------
+  // backward sweep, one record per stage:  QP[80] | dfc[9] | u0 x3 x4 x5 cos sin | pad   (2 slots)
+  // roll-out, one record per stage:        RK[120] | a[6] | dfc[9] | u0 x3 x4 x5 cos sin | pad   (4 slots)
+  static constexpr int BW_DFC = 80, BW_AC = 89, BW_SZ = 96, BW_SLOTS = 2;
+  static constexpr int RO_A = 120, RO_DFC = 126, RO_AC = 135, RO_SZ = 144, RO_SLOTS = 4;
+  static constexpr int SMEM_DOUBLES = RO_SZ * RO_SLOTS;  // per team (>= BW_SZ * BW_SLOTS)
+  double* sm;  // this team's ring
+
+  // the dynamics coefficients of stage k: lanes 9..14 fetch u0 x3 x4 x5 cos sin
+  __device__ __forceinline__ void fetch_ac(double* dst, int k, int it) {
+    if (c >= 9 && c < 15) {
+      const int q = c - 9;
+      const double* src = q == 0 ? &S.W(k, it + I_U + 0) : q < 4 ? &S.W(k, it + I_X + 2 + q) : &S.W2(k, S_FK + (q - 4));
+      async_copy8(dst + q, src);
+    }
+  }
+  __device__ __forceinline__ static SACoef ac_from(const double* q, double dt) {
+    SACoef a; a.dt = dt; a.cp = q[4]; a.sp = q[5];
+    const double u0 = q[0], x3 = q[1], x4 = q[2], x5 = q[3];
+    a.a32 = -dt * u0 * a.sp; a.a42 = dt * u0 * a.cp; a.a34 = -dt * x5; a.a43 = dt * x5; a.a35 = -dt * x4; a.a45 = dt * x3;
+    return a;
+  }
+  __device__ __forceinline__ void bw_issue(int k, int it) {
+    if (k >= 0) {
+      double* dst = sm + (k & 1) * BW_SZ;
+      const double* src = &S.Qw(k, 0);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { int i = c + 16 * r; if (i < QS / 2) async_copy16(dst + 2 * i, src + 2 * i); }
+      if (k < S.N) {
+        if (c < 9) async_copy8(dst + BW_DFC + c, &S.W2(k, S_DFC + c));
+        fetch_ac(dst + BW_AC, k, it);
+      }
+    }
+    async_commit();
+  }
+  __device__ __forceinline__ void ro_issue(int k, int it) {
+    if (k <= S.N) {
+      double* dst = sm + (k & 3) * RO_SZ;
+      const double* src = &S.Rw(k, 0);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { int i = c + 16 * r; if (i < RS / 2) async_copy16(dst + 2 * i, src + 2 * i); }
+      if (c < 3) async_copy16(dst + RO_A + 2 * c, &S.Qw(k, Q_A + 2 * c));
+      if (k < S.N) {
+        if (c < 9) async_copy8(dst + RO_DFC + c, &S.W2(k, S_DFC + c));
+        fetch_ac(dst + RO_AC, k, it);
+      }
+    }
+    async_commit();
+  }
+
+  // Backward sweep.  Returns 0, or 1 on a non-positive pivot (wrong inertia).
+  __device__ int riccati(double reg, double mu, int it) {
+    const int N = S.N;
+    const bool rhs = (c == 14);
+    double Pc[9];            // lanes 0..8: column c of Pxx(k+1); lane 14: pxx(k+1)
+    double an[NP], cn, gsn;  // slack column of stage k+1 (replicated)
+    team_sync();             // the ring may still be read by a slower lane of the previous phase
+    bw_issue(N, it); bw_issue(N - 1, it);
+    async_wait<1>(); team_sync();
+    {
+      const double* q = sm + (N & 1) * BW_SZ;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        double v = 0;
+        if (rhs) v = q[Q_GA + r] + mu * q[Q_GB + r];
+        else if (c < 9) { int idx = ht[r * 16 + c]; if (idx >= 0) v = q[idx]; if (r == c) v += reg; }
+        Pc[r] = v;
+      }
+#pragma unroll
+      for (int a = 0; a < NP; ++a) an[a] = q[Q_A + a];
+      cn = q[Q_C]; gsn = q[Q_GA + SGY_S] + mu * q[Q_GB + SGY_S];
+      if (c < 9) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) if (r <= c) S.Rw(N, R_P + ssidx(r, c)) = Pc[r];
+      } else if (rhs) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) S.Rw(N, R_PV + r) = Pc[r];
+      }
+    }
+    team_sync();
+    bw_issue(N - 2, it);
+    int bad = 0;
+    for (int k = N - 1; k >= 0; --k) {
+      async_wait<1>(); team_sync();
+      const double* q = sm + (k & 1) * BW_SZ;
+      const SACoef a = ac_from(q + BW_AC, S.dt);
+      double d[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) d[i] = q[BW_DFC + i];
+      // (Pxx d)[c] in lane c (symmetry), gathered into the right-hand-side lane: pd = pxx + Pxx d
+      double zd = 0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) zd = fma(Pc[i], d[i], zd);
+      double Y[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { double g = shfl16(zd, i); Y[i] = Pc[i] + (rhs ? g : 0.0); }  // u lanes: Pc = 0
+      // Y += coef * Pxx[:, src]: the columns A and B couple (A = I + sparse, B sparse)
+      int s1 = c, s2 = c, s3 = c; double c1 = 0, c2 = 0, c3 = 0;
+      switch (c) {
+        case 2: s1 = 3; c1 = a.a32; s2 = 4; c2 = a.a42; break;
+        case 3: s1 = 0; c1 = a.dt;  s2 = 4; c2 = a.a43; break;
+        case 4: s1 = 1; c1 = a.dt;  s2 = 3; c2 = a.a34; break;
+        case 5: s1 = 2; c1 = a.dt;  s2 = 3; c2 = a.a35; s3 = 4; c3 = a.a45; break;
+        case 9: s1 = 3; c1 = a.dt * a.cp; s2 = 4; c2 = a.dt * a.sp; break;
+        case 10: s1 = 5; c1 = a.dt; break;
+        case 11: s1 = 6; c1 = a.dt; break;
+        case 12: s1 = 7; c1 = a.dt; break;
+        case 13: s1 = 8; c1 = a.dt; break;
+        default: break;
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        double g1 = shfl16(Pc[i], s1), g2 = shfl16(Pc[i], s2), g3 = shfl16(Pc[i], s3);
+        Y[i] = fma(c1, g1, fma(c2, g2, fma(c3, g3, Y[i])));
+      }
+      double M[14];
+      abt_mul(Y, a, M);
+      // + H(:, c) + reg on the diagonal; right-hand side: + g
+      if (rhs) {
+#pragma unroll
+        for (int r = 0; r < 14; ++r) { const int y = r < 9 ? r : r + 1; M[r] += q[Q_GA + y] + mu * q[Q_GB + y]; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 14; ++r) {
+          int idx = ht[r * 16 + c];
+          if (idx >= 0) M[r] += q[idx];
+          if (r == c) M[r] += reg;
+        }
+      }
+      // eliminate v_k = s_{k+1}:  w = [A B]^T a(k+1) + bv(k),  cv = hvv(k) + c(k+1),  l0 = g_s(k+1) + a.d + g_v(k)
+      double wv[14];
+      {
+        double ae[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ae[i] = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) ae[POSE2X[p]] = an[p];
+        abt_mul(ae, a, wv);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) wv[POSE2X[p]] += q[Q_BV + p];
+      }
+      double l0 = gsn + q[Q_GA + SGY_V] + mu * q[Q_GB + SGY_V];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) l0 = fma(an[p], d[POSE2X[p]], l0);
+      const double cv = q[Q_HVV] + cn, icv = 1.0 / cv;
+      bad |= !(cv > 1e-13);
+      double wc = 0;
+#pragma unroll
+      for (int r = 0; r < 14; ++r) wc = (r == c) ? wv[r] : wc;
+      {
+        const double fac = (rhs ? l0 : wc) * icv;
+#pragma unroll
+        for (int r = 0; r < 14; ++r) M[r] = fma(-wv[r], fac, M[r]);
+      }
+      // this stage's slack column is the next iteration's a(k+1); the ring slot is then free
+#pragma unroll
+      for (int p = 0; p < NP; ++p) an[p] = q[Q_A + p];
+      cn = q[Q_C]; gsn = q[Q_GA + SGY_S] + mu * q[Q_GB + SGY_S];
+      team_sync();
+      bw_issue(k - 2, it);
+      // right-looking LDL^T of the u block: broadcast the pivot column, update the own column
+      double yv[NU], Lm[NU][NU];
+#pragma unroll
+      for (int p = 0; p < NU; ++p) {
+        const int pl = 9 + p;
+        double col[14];
+#pragma unroll
+        for (int r = 0; r < 14; ++r) if (r < 9 || r >= pl) col[r] = shfl16(M[r], pl);
+        const double piv = col[pl];
+        bad |= !(piv > 1e-13);
+        const double ip = 1.0 / piv;
+        const double f = M[pl] * ip;
+        yv[p] = f;
+#pragma unroll
+        for (int r = 0; r < 14; ++r) if (r < 9 || r > pl) M[r] = fma(-col[r], f, M[r]);
+#pragma unroll
+        for (int q2 = p + 1; q2 < NU; ++q2) Lm[q2][p] = col[9 + q2] * ip;
+      }
+      if (bad) { async_wait<0>(); return 1; }
+      // gains: K(:, c) = -L^-T y  (lane 14: kff)
+      double kc[NU];
+#pragma unroll
+      for (int p = NU - 1; p >= 0; --p) {
+        double v = yv[p];
+#pragma unroll
+        for (int q2 = p + 1; q2 < NU; ++q2) v = fma(-Lm[q2][p], kc[q2], v);
+        kc[p] = v;
+      }
+      if (c < 9) {
+#pragma unroll
+        for (int p = 0; p < NU; ++p) S.Rw(k, R_K + p * NX + c) = -kc[p];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) if (r <= c) S.Rw(k, R_P + ssidx(r, c)) = M[r];
+      } else if (rhs) {
+#pragma unroll
+        for (int p = 0; p < NU; ++p) S.Rw(k, R_KFF + p) = -kc[p];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) S.Rw(k, R_PV + r) = M[r];
+        S.Rw(k, R_CV) = cv; S.Rw(k, R_L0) = l0;
+      }
+      if (c < 14) S.Rw(k, R_W + c) = wc;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) Pc[r] = (c < 9 || rhs) ? M[r] : 0.0;
+    }
+    async_wait<0>();
+    if (!(cn > 1e-13)) return 1;
+    return 0;
+  }
+
+  // roll-out of the Newton step: dx, du, ds and the new costates lam+ = P [dx; ds] + p.
+  // dx is replicated in the team; lane a < 5 forms du[a], lane i < 9 forms lam+[i].
+  __device__ void rollout(double mu, int it) {
+    const int N = S.N; const double dt = S.dt;
+    team_sync();
+    ro_issue(0, it); ro_issue(1, it); ro_issue(2, it); ro_issue(3, it);
+    double dxv[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dxv[i] = 0;
+    if (c < 9) S.W2(0, S_DX + c) = 0;
+    double dsv = -(S.Qw(0, Q_GA + SGY_S) + mu * S.Qw(0, Q_GB + SGY_S)) / S.Qw(0, Q_C);
+    if (c == 14) S.W2(0, S_DS) = dsv;
+    for (int k = 0; k < N; ++k) {
+      async_wait<2>(); team_sync();
+      const double* r0 = sm + (k & 3) * RO_SZ;
+      const double* r1 = sm + ((k + 1) & 3) * RO_SZ;
+      double mine = 0;
+      if (c < NU) {
+        mine = r0[R_KFF + c];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) mine = fma(r0[R_K + c * NX + j], dxv[j], mine);
+        S.W2(k, S_DU + c) = mine;
+      }
+      double duv[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) duv[a] = shfl16(mine, a);
+      double l = r0[R_L0];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) l = fma(r0[R_W + i], dxv[i], l);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) l = fma(r0[R_W + NX + a], duv[a], l);
+      dsv = -l / r0[R_CV];
+      const SACoef a = ac_from(r0 + RO_AC, dt);
+      double nx_[NX];
+      nx_[0] = dxv[0] + dt * dxv[3]; nx_[1] = dxv[1] + dt * dxv[4]; nx_[2] = dxv[2] + dt * dxv[5];
+      nx_[3] = dxv[3] + a.a32 * dxv[2] + a.a34 * dxv[4] + a.a35 * dxv[5] + dt * a.cp * duv[0];
+      nx_[4] = dxv[4] + a.a42 * dxv[2] + a.a43 * dxv[3] + a.a45 * dxv[5] + dt * a.sp * duv[0];
+      nx_[5] = dxv[5] + dt * duv[1];
+      nx_[6] = dxv[6] + dt * duv[2]; nx_[7] = dxv[7] + dt * duv[3]; nx_[8] = dxv[8] + dt * duv[4];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dxv[i] = nx_[i] + r0[RO_DFC + i];
+      if (c < 9) {
+        double mx = 0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) mx = (i == c) ? dxv[i] : mx;
+        S.W2(k + 1, S_DX + c) = mx;
+        double v = r1[R_PV + c];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v = fma(r1[R_P + (c <= j ? c * 9 - c * (c - 1) / 2 + (j - c) : j * 9 - j * (j - 1) / 2 + (c - j))], dxv[j], v);
+        if (c < 3) v = fma(r1[RO_A + c], dsv, v);
+        if (c >= 6) v = fma(r1[RO_A + (c - 3)], dsv, v);
+        S.W2(k + 1, S_LAMN + c) = v;
+      }
+      if (c == 14) S.W2(k + 1, S_DS) = dsv;
+      team_sync();  // slot k & 3 is free
+      ro_issue(k + 4, it);
+    }
+    async_wait<0>();
+  }
+
+  // results: sol.value(U/X/s/cost) :317,:329-330; stage k is written by lane k mod 16
+  __device__ void finish(int status) {
+    const MmpcConfig& cfg = S.cfg; const SParams& P = S.P;
+    const int N = S.N, b = S.b;
+    const int it = S.J(J_CUR) * S.ITSZ;
+    double fsum = 0;
+    for (int k = c; k <= N; k += 16) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = S.W(k, it + I_X + i), e = v - S.W2(k, IN_XREF + i);
+        fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
+        if (P.X) P.X[((long long)b * (N + 1) + k) * NX + i] = v;
+      }
+      if (k < N)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          double v = S.W(k, it + I_U + j), e = v - S.W2(k, IN_UREF + j), dl = v - S.W2(k, IN_ULAST + j);
+          fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
+          P.U[((long long)b * N + k) * NU + j] = v;
+        }
+      double s = S.W(k, it + I_S);
+      fsum += cfg.S * s * s;
+      if (P.s) P.s[(long long)b * (N + 1) + k] = s;
+    }
+    fsum = tsum(fsum);
+    if (c == 0) {
+      if (P.cost) P.cost[b] = fsum;
+      if (P.kkt) P.kkt[b] = S.D(D_E0);
+      if (P.iters) P.iters[b] = S.J(J_IT);
+      P.status[b] = status;
+      S.J(J_STATE) = ST_DONE;
+    }
+  }
+
+  // KKT reduction, convergence test, barrier update, factorisation with inertia correction, roll-out
+  __device__ void solve() {
+    const MmpcConfig& cfg = S.cfg;
+    const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5;
+    const double tol = cfg.tol;
+    const int N = S.N;
+    const int it = S.J(J_CUR) * S.ITSZ;
+    KktParts kp;
+    kp.e_stat = 0; kp.e_prim = 0; kp.c_hi = -1e300; kp.c_lo = 1e300; kp.sum_lam = 0; kp.sum_z = 0;
+    double nz = 0, neq = 0;
+    for (int k = c; k <= N; k += 16) {
+      kp.e_stat = fmax(kp.e_stat, S.W2(k, S_PART + 0)); kp.e_prim = fmax(kp.e_prim, S.W2(k, S_PART + 1));
+      kp.c_hi = fmax(kp.c_hi, S.W2(k, S_PART + 2)); kp.c_lo = fmin(kp.c_lo, S.W2(k, S_PART + 3));
+      kp.sum_lam += S.W2(k, S_PART + 4); kp.sum_z += S.W2(k, S_PART + 5); nz += S.W2(k, S_PART + 6); neq += S.W2(k, S_PART + 7);
+    }
+    kp.e_stat = tmax(kp.e_stat); kp.e_prim = tmax(kp.e_prim); kp.c_hi = tmax(kp.c_hi); kp.c_lo = tmin(kp.c_lo);
+    kp.sum_lam = tsum(kp.sum_lam); kp.sum_z = tsum(kp.sum_z); nz = tsum(nz); neq = tsum(neq);
+    kp.n_z = (int)nz; kp.n_eq = (int)neq;
+    const double E0 = kkt_error(kp, 0.0);
+    // every lane of the team reads the scalar state before lane 0 rewrites any of it
+    const int iter = S.J(J_IT);
+    double mu = S.D(D_MU);
+    const double reg_last = S.D(D_REGLAST);
+    team_sync();
+    if (c == 0) S.D(D_E0) = E0;
+    team_sync();
+    if (!(E0 == E0)) { finish(MMPC_STATUS_NAN); return; }
+    if (E0 <= tol) { finish(MMPC_STATUS_CONVERGED); return; }
+    if (iter >= cfg.max_iter) { finish(MMPC_STATUS_MAX_ITER); return; }
+    bool mu_changed = false;
+    while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
+      mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
+    }
+    if (mu_changed && c == 0) { S.J(J_NFILT) = 0; S.D(D_MU) = mu; }
+    double reg = 0;
+    int tries = 0;
+    for (;;) {
+      int fail = riccati(reg, mu, it);
+      if (!fail) { if (reg > 0 && c == 0) S.D(D_REGLAST) = reg; break; }
+      if (reg == 0) reg = (reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3);
+      else reg *= (reg_last == 0 ? 100 : 8);
+      if (++tries > 40 || reg > 1e20) { finish(MMPC_STATUS_FACTOR); return; }
+    }
+    team_sync();  // the Riccati records written by the other lanes are read back in the roll-out
+    rollout(mu, it);
+  }
+};
+
+__device__ inline void body_solve_team(const SParams& P, int j, int c, const signed char* ht, double* sm) {
+  Team T(P, list_E(P)[j], c, ht, sm);
+  T.solve();
+}
+
+#if !defined(MMPC_EMULATE) && !defined(MMPC_EMULATE_LANE)
+__global__ void __launch_bounds__(128, 4) staged_solve_team_kernel(const __grid_constant__ SParams P) {
+  __shared__ signed char ht[14 * 16];
+  __shared__ __align__(16) double ring[8 * Team::SMEM_DOUBLES];  // 8 teams per block
+  for (int i = threadIdx.x; i < 14 * 16; i += blockDim.x) ht[i] = TEAM_TABLE.v[i / 16][i % 16];
+  __syncthreads();
+  const int n = P.cnt[0];
+  const int c = threadIdx.x & 15;
+  // a team (half warp) strides over the list; both halves of a warp run the same trip count
+  const int teams = (gridDim.x * blockDim.x) >> 4;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; j < n; j += teams)
+    body_solve_team(P, j, c, ht, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
+}
+#endif
+
+}  // namespace mmpc

@@ -6,6 +6,7 @@
 #include "emu_lane_runtime.h"
 #include "../../mobile_manipulator_mpc_b200/csrc/mmpc_lane.cuh"
 
+namespace mmpc { EmuTeam* g_team = nullptr; }
 using namespace mmpc;
 
 extern "C" int mmpc_emu_lane_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out) {

@@ -5,12 +5,38 @@
 #include <string.h>
 #include <vector>
 #include "emu_lane_runtime.h"
-#include "../../mobile_manipulator_mpc_b200/csrc/mmpc_staged.cuh"
+#include "../../mobile_manipulator_mpc_b200/csrc/mmpc_team.cuh"
 
+namespace mmpc { EmuTeam* g_team = nullptr; }
 using namespace mmpc;
 
+// one instance of the team phase: 16 coroutines in lock step
+struct TeamArg { const SParams* P; int j; };
+static TeamArg g_targ;
+static void team_entry() {
+  EmuTeam* w = g_team;
+  int me = w->cur;
+  static double ring[Team::SMEM_DOUBLES];
+  body_solve_team(*g_targ.P, g_targ.j, me, &TEAM_TABLE.v[0][0], ring);
+  w->done++;
+  if (w->done < 16) { int nx = (me + 1) & 15; w->cur = nx; swapcontext(&w->ctx[me], &w->ctx[nx]); }
+  else swapcontext(&w->ctx[me], &w->main_ctx);
+}
+static void run_team(const SParams& P, int j, std::vector<char*>& stacks) {
+  EmuTeam* w = g_team;
+  g_targ.P = &P; g_targ.j = j;
+  const size_t STK = 1 << 18;
+  for (int i = 0; i < 16; ++i) {
+    getcontext(&w->ctx[i]);
+    w->ctx[i].uc_stack.ss_sp = stacks[i]; w->ctx[i].uc_stack.ss_size = STK; w->ctx[i].uc_link = &w->main_ctx;
+    makecontext(&w->ctx[i], team_entry, 0);
+  }
+  w->cur = 0; w->done = 0;
+  swapcontext(&w->main_ctx, &w->ctx[0]);
+}
+
 extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out,
-                                     int32_t* rounds_out) {
+                                     int32_t* rounds_out, int32_t team) {
   SParams P; memset(&P, 0, sizeof P);
   P.cfg = *cfg; P.B = B;
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
@@ -18,6 +44,11 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
   P.R = staged_rows(*cfg); P.ITSZ = staged_itsz(*cfg); P.STG = staged_stage_doubles(*cfg); P.LS = B;
   std::vector<double> ws((size_t)(cfg->N + 1) * P.STG * B, 0.0), gd((size_t)staged_inst_doubles(*cfg) * B, 0.0);
+  std::vector<double> qp((size_t)(cfg->N + 1) * QS * B, 0.0), rk((size_t)(cfg->N + 1) * RS * B, 0.0);
+  P.qp = qp.data(); P.rk = rk.data(); P.team = team;
+  EmuTeam* tw = new EmuTeam(); g_team = tw;
+  std::vector<char*> stacks(16);
+  for (int i = 0; i < 16; ++i) stacks[i] = (char*)malloc(1 << 18);
   std::vector<int> gi((size_t)J_NFIELDS * B, 0), lists((size_t)2 * B, 0);
   int cnt[2] = {0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
@@ -27,7 +58,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     compact_list(P, 0, ST_ACTIVE);
     int nE = cnt[0];
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_eval(P, j, k);
-    for (int j = 0; j < nE; ++j) body_solve(P, j);
+    for (int j = 0; j < nE; ++j) { if (team) run_team(P, j, stacks); else body_solve(P, j); }
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_step(P, j, k);
     for (int j = 0; j < nE; ++j) body_ctrl_step(P, j);
     compact_list(P, 1, ST_TRIAL);
@@ -37,6 +68,8 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     if (nT == 0) break;
     if (r > 200000) return 1;
   }
+  for (int i = 0; i < 16; ++i) free(stacks[i]);
+  delete tw; g_team = nullptr;
   if (rounds_out) *rounds_out = r + 1;
   return 0;
 }
