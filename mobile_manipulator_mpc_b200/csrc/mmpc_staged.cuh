@@ -55,16 +55,18 @@ struct SParams {
   int* cnt;        // their lengths
   long long LS;    // instance stride (B_max rounded up)
   int R, STG, ITSZ;
+  int fused;       // 1: the trial kernel also evaluates the next iteration's derivatives (no eval kernel per round)
   int team;        // 1: 16-lane column-parallel Riccati (mmpc_team.cuh), 0: one thread per instance
 };
 
 // ---- iterate buffer (two copies, ping-pong): offsets inside one copy --------------------------
 constexpr int I_X = 0, I_U = 9, I_S = 14, I_LAM = 15, I_ZXL = 24, I_ZXU = 33, I_ZUL = 42, I_ZUU = 47, I_T = 52;
 // ---- after the two iterate copies (field-major, like the iterate) -----------------------------------
-constexpr int S_DX = 0, S_DU = 9, S_DS = 14, S_LAMN = 15, S_FK = 24, S_DFC = 32, S_PART = 41;
-constexpr int IN_XREF = 49, IN_UREF = 58, IN_ULAST = 63, IN_ULO = 68, IN_UHI = 73;
-constexpr int S_DT = 78;  // dt[R], then (moving obstacles) circles[3*nobs]
-constexpr int S_FIXED = 78;
+constexpr int S_DX = 0, S_DU = 9, S_DS = 14, S_LAMN = 15, S_FK = 24, S_DFC = 32, S_PART = 41;  // 12 partial slots
+constexpr int IN_XREF = 53, IN_UREF = 62, IN_ULAST = 67, IN_ULO = 72, IN_UHI = 77;
+constexpr int S_DT = 82;  // dt[R], then (moving obstacles) circles[3*nobs]
+constexpr int S_FIXED = 82;
+constexpr int PT_MERIT = 8;  // partial slots 0..7: KKT parts (eval) or step parts; 8..11: merit of the trial point
 // ---- stage QP record, contiguous per (stage, instance):  qp[(k*LS + b)*QS + f] ------------------------
 // pose Hessian (21 packed) | velocity diagonal 3 | (dx,dpsi) (dy,dpsi) | control diagonal 5 | (psi,u0) |
 // a = H[pose][s] 6 | c = H[s][s] | bv = H[pose][v] 6 | hvv | gA 16 | gB 16   (y = x9 s u5 v)
@@ -756,9 +758,16 @@ struct Inst {
   // ------------------------------------------------------------------------------------------
   // step (thread per instance and stage): slack / multiplier steps of every row and bound,
   // fraction to the boundary, merit ingredients of the current point.
-  __device__ void step(int k) {
+  __device__ void step(int k, double* sm, int bs) {
     load_npl();
     const int it = J(J_CUR) * ITSZ;
+    for (int r = 0; r < R; ++r) {
+      async_copy8(sm + r * bs, &W(k, it + I_T + r));
+      async_copy8(sm + (R + r) * bs, &W(k, it + I_T + R + r));
+    }
+    for (int i = 0; i < 3 * nobs; ++i) async_copy8(sm + (2 * R + i) * bs, cfg.obs_per_stage ? &W2(k, S_DT + R + i) : &D(D_CIRC + i));
+    async_commit();
+    const double* smc = sm + 2 * R * bs;  // circles
     const double os = D(D_OS), mu = D(D_MU);
     const double tau = fmax(0.99, 1 - mu);
     double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0;
@@ -822,8 +831,9 @@ struct Inst {
 #pragma unroll
     for (int q = 0; q < 3; ++q) { f.vr[q] = W2(k, S_FK + 2 + q); f.vh[q] = W2(k, S_FK + 5 + q); }
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
+    async_wait<0>();
     auto row_step = [&](int r, double h, double gd_) {
-      double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
+      double t = sm[r * bs], z = sm[(R + r) * bs];
       double res = h - s + t;
       double dtv = -res - (gd_ - dsv);
       W2(k, S_DT + r) = dtv;
@@ -833,9 +843,9 @@ struct Inst {
       if (dz < 0) ad = fmin(ad, -tau * z / dz);
     };
     for (int i = 0; i < nobs; ++i) {
-      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+      double ddx = x[0] - smc[(3 * i) * bs], ddy = x[1] - smc[(3 * i + 1) * bs];
       double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
-      row_step(i, (circ(k, i, 2) + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv);
+      row_step(i, (smc[(3 * i + 2) * bs] + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv);
     }
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
@@ -982,8 +992,256 @@ struct Inst {
       }
     }
     bool fin = ok && (fsum == fsum) && (theta == theta);
-    W2(k, S_PART + 0) = theta; W2(k, S_PART + 1) = fsum; W2(k, S_PART + 2) = fin ? lp.value() : 0.0;
-    W2(k, S_PART + 3) = fin ? 1.0 : 0.0;
+    W2(k, S_PART + PT_MERIT + 0) = theta; W2(k, S_PART + PT_MERIT + 1) = fsum; W2(k, S_PART + PT_MERIT + 2) = fin ? lp.value() : 0.0;
+    W2(k, S_PART + PT_MERIT + 3) = fin ? 1.0 : 0.0;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // trial_eval (thread per instance and stage): the trial kernel fused with the evaluation of the
+  // NEXT iteration.  Builds the candidate iterate  w + alpha d  (primal and dual, slack reset, multiplier
+  // safeguard) in the other iterate buffer, its merit ingredients, and -- because an accepted candidate
+  // is exactly where the next iteration linearises -- the stage QP, defect, FK cache and KKT partials at
+  // the candidate, all from registers.  A rejected candidate only wastes the derivative arithmetic: its
+  // records are overwritten by the next trial before anything reads them.
+  // sm/bs: this thread's column of the block's shared-memory row buffer (element i at sm[i * bs]): the
+  // row slacks, multipliers, steps and the circles are fetched with cp.async up front, so the row loops
+  // below never wait on HBM.
+  __device__ void trial_eval(int k, double* sm, int bs) {
+    load_npl();
+    const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
+    const double os = D(D_OS), mu = D(D_MU), alpha = D(D_ALPHA), ad = D(D_AD);
+    for (int r = 0; r < R; ++r) {
+      async_copy8(sm + r * bs, &W(k, it + I_T + r));
+      async_copy8(sm + (R + r) * bs, &W(k, it + I_T + R + r));
+      async_copy8(sm + (2 * R + r) * bs, &W2(k, S_DT + r));
+    }
+    for (int i = 0; i < 3 * nobs; ++i) async_copy8(sm + (3 * R + i) * bs, cfg.obs_per_stage ? &W2(k, S_DT + R + i) : &D(D_CIRC + i));
+    async_commit();
+    const double* smc = sm + 3 * R * bs;  // circles
+    double theta = 0, fsum = 0; bool ok = true;
+    LogProd lp; lp.init();
+    RowAcc A;
+    A.chi = -1e300; A.clo = 1e300; A.prim = 0; A.sumz = 0; A.zrows = 0; A.nz = 0; A.csum = A.be0 = A.be1 = 0;
+#pragma unroll
+    for (int e = 0; e < 21; ++e) A.H[e] = 0;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) A.a[a] = A.gA[a] = A.gB[a] = A.st[a] = 0;
+    double x[NX], u[NU], lam[NX], lam1[NX], xo[NX], dxo[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      xo[i] = W(k, it + I_X + i); dxo[i] = W2(k, S_DX + i);
+      x[i] = fma(alpha, dxo[i], xo[i]);
+      W(k, jt + I_X + i) = x[i];
+      lam[i] = 0;
+      if (k >= 1) {
+        double l = W(k, it + I_LAM + i);
+        lam[i] = l + alpha * (W2(k, S_LAMN + i) - l);
+        W(k, jt + I_LAM + i) = lam[i];
+      }
+    }
+    const double s = fma(alpha, W2(k, S_DS), W(k, it + I_S));
+    W(k, jt + I_S) = s;
+    double uo[NU], duo[NU];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      uo[j] = (k < N) ? W(k, it + I_U + j) : 0.0; duo[j] = (k < N) ? W2(k, S_DU + j) : 0.0;
+      u[j] = fma(alpha, duo[j], uo[j]);
+      if (k < N) W(k, jt + I_U + j) = u[j];
+    }
+    FK f; fk_eval(x[2], x[6], x[7], x[8], f);
+    W2(k, S_FK + 0) = f.cp; W2(k, S_FK + 1) = f.sp;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { W2(k, S_FK + 2 + q) = f.vr[q]; W2(k, S_FK + 5 + q) = f.vh[q]; }
+    double es = 0, hpp = 0, sum_lam = 0;
+    int n_eq = 0;
+    // dynamics :180 at the candidate -- defect and costate terms (A^T lam_{k+1}, B^T lam_{k+1})
+    double stx[NX], stu[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) stx[i] = 0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) stu[j] = 0;
+    if (k < N) {
+      double xn[NX];
+      dyn_f(x, u, dt, f.cp, f.sp, xn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double l1 = W(k + 1, it + I_LAM + i);
+        lam1[i] = l1 + alpha * (W2(k + 1, S_LAMN + i) - l1);
+        double x1 = fma(alpha, W2(k + 1, S_DX + i), W(k + 1, it + I_X + i));
+        double d = xn[i] - x1;
+        W2(k, S_DFC + i) = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
+        theta += fabs(d);
+      }
+      n_eq = NX;
+      hpp = -dt * u[0] * (lam1[3] * f.cp + lam1[4] * f.sp);
+      Qw(k, Q_HPU) = dt * (-lam1[3] * f.sp + lam1[4] * f.cp);
+      Qw(k, Q_H45) = -dt * lam1[3];  // (dy,dpsi)
+      Qw(k, Q_H35) = dt * lam1[4];   // (dx,dpsi)
+      stx[0] = lam1[0]; stx[1] = lam1[1];
+      stx[2] = lam1[2] + dt * u[0] * (-f.sp * lam1[3] + f.cp * lam1[4]);
+      stx[3] = dt * lam1[0] + lam1[3] + dt * x[5] * lam1[4];
+      stx[4] = dt * lam1[1] - dt * x[5] * lam1[3] + lam1[4];
+      stx[5] = dt * lam1[2] - dt * x[4] * lam1[3] + dt * x[3] * lam1[4] + lam1[5];
+      stx[6] = lam1[6]; stx[7] = lam1[7]; stx[8] = lam1[8];
+      stu[0] = dt * (f.cp * lam1[3] + f.sp * lam1[4]);
+      stu[1] = dt * lam1[5];
+      stu[2] = dt * lam1[6]; stu[3] = dt * lam1[7]; stu[4] = dt * lam1[8];
+    } else {
+      Qw(k, Q_HPU) = 0; Qw(k, Q_H45) = 0; Qw(k, Q_H35) = 0;
+    }
+    // candidate multiplier of a bound at distance d_old -> d (sgn = +1 lower, -1 upper); merit + KKT bookkeeping
+    auto box = [&](double zold, double d_old, double d, double sgn_dv, int slot) -> double {
+      double dz = mu / d_old - zold - (zold / d_old) * sgn_dv;
+      double z = zold + ad * dz;
+      z = fmax(fmin(z, 1e10 * mu / d), mu / (1e10 * d));
+      W(k, slot) = z;
+      if (d <= 0) ok = false; else lp.mul(d);
+      A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
+      return z;
+    };
+    // cost and boxes -- :192-205, :240-245
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+      double e = x[i] - W2(k, IN_XREF + i);
+      fsum += Wx * e * e;
+      double gr = 2 * Wx * e;
+      double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
+      if (k >= 1) {
+        double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
+        if (is_fin(lo)) {
+          double d = x[i] - lo, z = box(W(k, it + I_ZXL + i), xo[i] - lo, d, dxo[i], jt + I_ZXL + i), id = 1.0 / d;
+          Hd += z * id; gB -= id; st -= z;
+        }
+        if (is_fin(hi)) {
+          double d = hi - x[i], z = box(W(k, it + I_ZXU + i), hi - xo[i], d, -dxo[i], jt + I_ZXU + i), id = 1.0 / d;
+          Hd += z * id; gB += id; st += z;
+        }
+      }
+      if (i < 3 || i >= 6) {
+        const int a = (i < 3) ? i : i - 3;
+        A.H[pidx(a, a)] = Hd + (i == 2 ? hpp : 0.0); A.gA[a] = gA; A.gB[a] = gB; A.st[a] = st;
+      } else {
+        Qw(k, Q_HVD + (i - 3)) = Hd; Qw(k, Q_GA + i) = gA; Qw(k, Q_GB + i) = gB;
+        if (k >= 1) es = fmax(es, fabs(st));
+      }
+    }
+    fsum += os * cfg.S * s * s;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      double Hd = 0, gA = 0, gB = 0;
+      if (k < N) {
+        double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
+        double e = u[j] - W2(k, IN_UREF + j), dl = u[j] - W2(k, IN_ULAST + j);
+        fsum += os * (cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl);
+        double gr = 2 * Rj * e + 2 * Wj * dl;
+        Hd = 2 * Rj + 2 * Wj; gA = gr;
+        double st = gr + stu[j];
+        double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
+        if (is_fin(lo)) {
+          double d = u[j] - lo, z = box(W(k, it + I_ZUL + j), uo[j] - lo, d, duo[j], jt + I_ZUL + j), id = 1.0 / d;
+          Hd += z * id; gB -= id; st -= z;
+        }
+        if (is_fin(hi)) {
+          double d = hi - u[j], z = box(W(k, it + I_ZUU + j), hi - uo[j], d, -duo[j], jt + I_ZUU + j), id = 1.0 / d;
+          Hd += z * id; gB += id; st += z;
+        }
+        es = fmax(es, fabs(st));
+      }
+      Qw(k, Q_HUU + j) = Hd; Qw(k, Q_GA + SGY_U + j) = gA; Qw(k, Q_GB + SGY_U + j) = gB;
+    }
+    // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
+    async_wait<0>();
+    auto row = [&](int r, double h, double& z, double& it_, double& res) {
+      double t = sm[r * bs], dtv = sm[(2 * R + r) * bs];
+      z = sm[(R + r) * bs];
+      double tt = fmax(fma(alpha, dtv, t), s - h);  // slack reset (Nocedal & Wright 19.30)
+      double dz = (mu - z * (t + dtv)) / t;
+      z += ad * dz; z = fmax(fmin(z, 1e10 * mu / tt), mu / (1e10 * tt));
+      W(k, jt + I_T + r) = tt; W(k, jt + I_T + R + r) = z;
+      res = h - s + tt;
+      theta += fabs(res);
+      if (tt <= 0) ok = false; else lp.mul(tt);
+      it_ = 1.0 / tt;
+      A.prim = fmax(A.prim, fabs(res));
+      double zt = z * tt;
+      A.chi = fmax(A.chi, zt); A.clo = fmin(A.clo, zt);
+      A.sumz += z; A.zrows += z; A.nz++;
+      double sig = z * it_;
+      A.csum += sig; A.be0 += sig * res; A.be1 += it_;
+    };
+    for (int i = 0; i < nobs; ++i) {  // obsAvoid :49-54
+      double ddx = x[0] - smc[(3 * i) * bs], ddy = x[1] - smc[(3 * i + 1) * bs];
+      double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+      double h = (smc[(3 * i + 2) * bs] + cfg.base_radius) - d;
+      double z, it_, res; row(i, h, z, it_, res);
+      double sig = z * it_, nx = ddx * inv, ny = ddy * inv, zd = z * inv;
+      A.H[pidx(0, 0)] += sig * nx * nx - zd * (1 - nx * nx);
+      A.H[pidx(0, 1)] += (sig + zd) * nx * ny;
+      A.H[pidx(1, 1)] += sig * ny * ny - zd * (1 - ny * ny);
+      double cb = sig * res;
+      A.a[0] += sig * nx; A.a[1] += sig * ny; A.gA[0] -= cb * nx; A.gA[1] -= cb * ny;
+      A.gB[0] -= it_ * nx; A.gB[1] -= it_ * ny; A.st[0] -= z * nx; A.st[1] -= z * ny;
+    }
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {  // self collision :219-222
+      Point p; point_eval(x[0], x[1], f, SELFD[m], p);
+      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2);
+      double h = cfg.self_collision_radius - d2 * inv;
+      double z, it_, res; row(nobs + m, h, z, it_, res);
+      double sig = z * it_, zd = z * inv;
+      double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
+      point_grad(f, p, n, g);  // grad h = -g
+      double cgg = sig + zd;
+#pragma unroll
+      for (int a = 0; a < NP; ++a)
+#pragma unroll
+        for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += cgg * g[a] * g[c];
+      point_jtj_acc(f, p, -zd, A.H);
+      point_hess_acc(f, p, n, -z, A.H);
+      double cb = sig * res;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { A.a[a] += sig * g[a]; A.gA[a] -= cb * g[a]; A.gB[a] -= it_ * g[a]; A.st[a] -= z * g[a]; }
+    }
+    if (npl > 0) {
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {  // obsAvoidConvex :57-89 (proper row)
+        Point p; point_eval(x[0], x[1], f, BODY[i], p);
+        int jb; double h = plane_row(p, jb);
+        double z, it_, res; row(nobs + 4 + i, h, z, it_, res);
+        double sig = z * it_;
+        double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)}, g[NP];
+        point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g
+#pragma unroll
+        for (int a = 0; a < NP; ++a)
+#pragma unroll
+          for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += sig * g[a] * g[c];
+        point_hess_acc(f, p, n, z, A.H);
+        double cb = sig * res;
+#pragma unroll
+        for (int a = 0; a < NP; ++a) { A.a[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
+      }
+    }
+    // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
+    double S2 = 2 * os * cfg.S;
+    Qw(k, Q_C) = S2 + A.csum;
+    Qw(k, Q_GA + SGY_S) = S2 * s - A.be0;
+    Qw(k, Q_GB + SGY_S) = -A.be1;
+    Qw(k, Q_HVV) = 0; Qw(k, Q_GA + SGY_V) = 0; Qw(k, Q_GB + SGY_V) = 0;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = 0;
+      Qw(k, Q_GA + POSE2X[a]) = A.gA[a]; Qw(k, Q_GB + POSE2X[a]) = A.gB[a];
+      if (k >= 1) es = fmax(es, fabs(A.st[a]));
+    }
+#pragma unroll
+    for (int e = 0; e < 21; ++e) Qw(k, Q_HP + e) = A.H[e];
+    es = fmax(es, fabs(S2 * s - A.zrows));
+    W2(k, S_PART + 0) = es; W2(k, S_PART + 1) = A.prim; W2(k, S_PART + 2) = A.chi; W2(k, S_PART + 3) = A.clo;
+    W2(k, S_PART + 4) = sum_lam; W2(k, S_PART + 5) = A.sumz; W2(k, S_PART + 6) = (double)A.nz; W2(k, S_PART + 7) = (double)n_eq;
+    bool fin = ok && (fsum == fsum) && (theta == theta);
+    W2(k, S_PART + PT_MERIT + 0) = theta; W2(k, S_PART + PT_MERIT + 1) = fsum; W2(k, S_PART + PT_MERIT + 2) = fin ? lp.value() : 0.0;
+    W2(k, S_PART + PT_MERIT + 3) = fin ? 1.0 : 0.0;
   }
 
   // ctrl_trial (thread per instance): filter acceptance test (Waechter & Biegler 2006, Alg. A
@@ -992,8 +1250,8 @@ struct Inst {
   __device__ int ctrl_trial() {
     double th1 = 0, f1 = 0, logsum = 0; bool ok = true;
     for (int k = 0; k <= N; ++k) {
-      th1 += W2(k, S_PART + 0); f1 += W2(k, S_PART + 1); logsum += W2(k, S_PART + 2);
-      ok = ok && (W2(k, S_PART + 3) > 0.5);
+      th1 += W2(k, S_PART + PT_MERIT + 0); f1 += W2(k, S_PART + PT_MERIT + 1); logsum += W2(k, S_PART + PT_MERIT + 2);
+      ok = ok && (W2(k, S_PART + PT_MERIT + 3) > 0.5);
     }
     const double mu = D(D_MU), theta_k = D(D_THETA), phi0 = D(D_PHI0), gphi = D(D_GPHI), alpha = D(D_ALPHA);
     double ph1 = f1 - mu * logsum;
@@ -1042,13 +1300,19 @@ __device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.LS
 __device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init(); }
 __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.eval(k); }
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
-__device__ inline void body_step(const SParams& P, int j, int k) {
+// doubles of shared-memory row buffer one thread of the step / trial kernels needs
+__host__ __device__ inline int staged_rowbuf_doubles(const MmpcConfig& c) { return 3 * staged_rows(c) + 3 * c.n_obs; }
+
+__device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {
   Inst S(P, list_E(P)[j]);
   if (S.J(J_STATE) != ST_ACTIVE) return;
-  S.step(k);
+  S.step(k, sm, bs);
 }
 __device__ inline void body_ctrl_step(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.ctrl_step(); }
-__device__ inline void body_trial(const SParams& P, int j, int k) { Inst S(P, list_T(P)[j]); S.trial(k); }
+__device__ inline void body_trial(const SParams& P, int j, int k, double* sm, int bs) {
+  Inst S(P, list_T(P)[j]);
+  if (P.fused) S.trial_eval(k, sm, bs); else S.trial(k);
+}
 __device__ inline void body_ctrl_trial(const SParams& P, int j) { Inst S(P, list_T(P)[j]); S.ctrl_trial(); }
 
 #ifdef MMPC_EMULATE_LANE
@@ -1104,21 +1368,23 @@ __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant_
   const int n = P.cnt[0];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_solve(P, j);
 }
-__global__ void __launch_bounds__(128) staged_step_kernel(const __grid_constant__ SParams P) {
+__global__ void __launch_bounds__(64) staged_step_kernel(const __grid_constant__ SParams P) {
+  extern __shared__ double rowbuf[];
   const int n = P.cnt[0];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_step(P, (int)(t % n), (int)(t / n));
+    body_step(P, (int)(t % n), (int)(t / n), rowbuf + threadIdx.x, blockDim.x);
 }
 __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_step(P, j);
 }
-__global__ void __launch_bounds__(128) staged_trial_kernel(const __grid_constant__ SParams P) {
+__global__ void __launch_bounds__(64) staged_trial_kernel(const __grid_constant__ SParams P) {
+  extern __shared__ double rowbuf[];
   const int n = P.cnt[1];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_trial(P, (int)(t % n), (int)(t / n));
+    body_trial(P, (int)(t % n), (int)(t / n), rowbuf + threadIdx.x, blockDim.x);
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[1];

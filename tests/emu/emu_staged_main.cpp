@@ -36,7 +36,7 @@ static void run_team(const SParams& P, int j, std::vector<char*>& stacks) {
 }
 
 extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out,
-                                     int32_t* rounds_out, int32_t team) {
+                                     int32_t* rounds_out, int32_t team, int32_t fused) {
   SParams P; memset(&P, 0, sizeof P);
   P.cfg = *cfg; P.B = B;
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
@@ -45,7 +45,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   P.R = staged_rows(*cfg); P.ITSZ = staged_itsz(*cfg); P.STG = staged_stage_doubles(*cfg); P.LS = B;
   std::vector<double> ws((size_t)(cfg->N + 1) * P.STG * B, 0.0), gd((size_t)staged_inst_doubles(*cfg) * B, 0.0);
   std::vector<double> qp((size_t)(cfg->N + 1) * QS * B, 0.0), rk((size_t)(cfg->N + 1) * RS * B, 0.0);
-  P.qp = qp.data(); P.rk = rk.data(); P.team = team;
+  P.qp = qp.data(); P.rk = rk.data(); P.team = team; P.fused = fused;
   EmuTeam* tw = new EmuTeam(); g_team = tw;
   std::vector<char*> stacks(16);
   for (int i = 0; i < 16; ++i) stacks[i] = (char*)malloc(1 << 18);
@@ -53,17 +53,19 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   int cnt[2] = {0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
   for (int b = 0; b < B; ++b) body_init(P, b);
+  std::vector<double> rowbuf(staged_rowbuf_doubles(*cfg) + 1, 0.0);
   int N = cfg->N, r = 0;
   for (;; ++r) {
     compact_list(P, 0, ST_ACTIVE);
     int nE = cnt[0];
-    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_eval(P, j, k);
+    if (!fused || r == 0)  // fused: only the starting point needs the stand-alone evaluation
+      for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_eval(P, j, k);
     for (int j = 0; j < nE; ++j) { if (team) run_team(P, j, stacks); else body_solve(P, j); }
-    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_step(P, j, k);
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_step(P, j, k, rowbuf.data(), 1);
     for (int j = 0; j < nE; ++j) body_ctrl_step(P, j);
     compact_list(P, 1, ST_TRIAL);
     int nT = cnt[1];
-    for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) body_trial(P, j, k);
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) body_trial(P, j, k, rowbuf.data(), 1);
     for (int j = 0; j < nT; ++j) body_ctrl_trial(P, j);
     if (nT == 0) break;
     if (r > 200000) return 1;
