@@ -74,7 +74,8 @@ enum {
  *   WARP   one warp per instance, lanes cooperate on the stages of one horizon */
 enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2, MMPC_KERNEL_STAGED = 3,
        MMPC_KERNEL_STAGED_THREAD = 4,  /* STAGED with the one-thread-per-instance Riccati (A/B reference) */
-       MMPC_KERNEL_STAGED_UNFUSED = 5  /* STAGED with separate eval and trial kernels (A/B reference)       */ };
+       MMPC_KERNEL_STAGED_UNFUSED = 5, /* STAGED with separate eval and trial kernels (A/B reference)       */
+       MMPC_KERNEL_STAGED_FAT = 6      /* STAGED with one thread per (instance, stage) item (A/B reference) */ };
 
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */

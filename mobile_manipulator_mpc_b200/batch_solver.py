@@ -52,7 +52,7 @@ class BatchSolver:
         """'auto' | 'staged' (phase kernels over active lists) | 'lane' (thread per instance) | 'warp'."""
         k = {"auto": _abi.KERNEL_AUTO, "lane": _abi.KERNEL_LANE, "warp": _abi.KERNEL_WARP,
              "staged": _abi.KERNEL_STAGED, "staged_thread": _abi.KERNEL_STAGED_THREAD,
-             "staged_unfused": _abi.KERNEL_STAGED_UNFUSED}.get(kernel, kernel)
+             "staged_unfused": _abi.KERNEL_STAGED_UNFUSED, "staged_fat": _abi.KERNEL_STAGED_FAT}.get(kernel, kernel)
         check(lib().mmpc_set_kernel(self._h, int(k)))
 
     # -- lifetime -----------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 #include "mmpc_lane.cuh"
 #include "mmpc_staged.cuh"
 #include "mmpc_team.cuh"
+#include "mmpc_parts.cuh"
 
 using namespace mmpc;
 
@@ -26,7 +27,7 @@ struct MmpcHandle {
   unsigned* counter;
   long long launches;
   // lane-per-instance kernel: resident warps, interleaved workspace (allocated on first use)
-  int kernel, lane_warps_per_sm, lane_warps, sg_team, sg_fused;
+  int kernel, lane_warps_per_sm, lane_warps, sg_team, sg_fused, sg_parts;
   long long lane_warp_stride;
   double* lane_ws;
   // staged (batch-synchronous) solver: field-major state, per-instance scalars, lists, counters
@@ -125,7 +126,7 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   CK(cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * sizeof(double)));
   CK(cudaMalloc(&h->counter, sizeof(unsigned)));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  h->kernel = MMPC_KERNEL_AUTO; h->sg_team = 1; h->sg_fused = 1;
+  h->kernel = MMPC_KERNEL_AUTO; h->sg_team = 1; h->sg_fused = 1; h->sg_parts = 1;
   h->lane_warps_per_sm = 8;
   h->lane_warp_stride = lane_instance_doubles(*cfg) * 32;
   {
@@ -174,7 +175,8 @@ extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* P
 }
 
 extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
-  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_STAGED_UNFUSED) return MMPC_ERR_ARG;
+  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_STAGED_FAT) return MMPC_ERR_ARG;
+  h->sg_parts = kernel != MMPC_KERNEL_STAGED_FAT;
   h->sg_team = kernel != MMPC_KERNEL_STAGED_THREAD;
   h->sg_fused = kernel != MMPC_KERNEL_STAGED_UNFUSED;
   h->kernel = kernel >= MMPC_KERNEL_STAGED ? MMPC_KERNEL_STAGED : kernel;
@@ -243,8 +245,10 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
   P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
   P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
-  P.ws = h->sg.ws; P.qp = h->sg.qp; P.rk = h->sg.rk; P.team = h->sg_team; P.fused = h->sg_fused; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
-  P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = STG;
+  P.ws = h->sg.ws; P.qp = h->sg.qp; P.rk = h->sg.rk; P.team = h->sg_team; P.fused = h->sg_fused;
+  const PartPlan plan = part_plan(cfg);
+  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10) ? 1 : 0; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
+  P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = STG; P.ND = staged_inst_doubles(cfg);
   // profiling: one timing event in front of every launch; the time up to the next event is
   // charged to that launch's phase (events are stream-ordered, so this is device time)
   std::vector<int> marks;
@@ -265,13 +269,6 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   CK(cudaGetLastError());
   h->launches += 1;
   const int LAG = 2, cap = h->sm_count * 16;
-  const size_t rowbuf_bytes = (size_t)staged_rowbuf_doubles(cfg) * 64 * sizeof(double);
-  if (!h->sg.attr_set) {
-    if (rowbuf_bytes > 200 * 1024) { snprintf(g_err, sizeof g_err, "row buffer of %zu bytes exceeds shared memory", rowbuf_bytes); return MMPC_ERR_CUDA; }
-    CK(cudaFuncSetAttribute(staged_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowbuf_bytes));
-    CK(cudaFuncSetAttribute(staged_trial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowbuf_bytes));
-    h->sg.attr_set = true;
-  }
   long long ub = B;  // upper bound of the active instances (the lists only shrink)
   int r = 0;
   for (;; ++r) {
@@ -279,8 +276,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
     int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
     int gt = (int)((ub * 16 + 127) / 128);
-    int gs64 = (int)((items + 63) / 64 < 2 * cap ? (items + 63) / 64 : 2 * cap);
-    if (gs64 < 1) gs64 = 1;
+    int gtile = (int)((items + 31) / 32 < 8 * cap ? (items + 31) / 32 : 8 * cap);
+    if (gtile < 1) gtile = 1;
     if (gs < 1) gs = 1; if (gi_ < 1) gi_ = 1; if (g64 < 1) g64 = 1; if (gt < 1) gt = 1;
     MARK(MMPC_PHASE_COMPACT);
     staged_compact_kernel<<<1, 1024, 0, st>>>(P, 0, ST_ACTIVE);
@@ -292,13 +289,16 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     if (P.team) staged_solve_team_kernel<<<gt, 128, 0, st>>>(P);
     else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
     MARK(MMPC_PHASE_STEP);
-    staged_step_kernel<<<gs64, 64, rowbuf_bytes, st>>>(P);
+    const bool thin = P.parts && (items + 31) / 32 <= (long long)h->sm_count;  // every tile gets its own SM
+    if (thin) staged_parts_kernel<false><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
+    else staged_step_kernel<<<gs, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_CTRL_STEP);
     staged_ctrl_step_kernel<<<gi_, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_COMPACT);
     staged_compact_kernel<<<1, 1024, 0, st>>>(P, 1, ST_TRIAL);
     MARK(MMPC_PHASE_TRIAL);
-    staged_trial_kernel<<<gs64, 64, rowbuf_bytes, st>>>(P);
+    if (thin) staged_parts_kernel<true><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
+    else staged_trial_kernel<<<gs, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_CTRL_TRIAL);
     staged_ctrl_trial_kernel<<<gi_, 128, 0, st>>>(P);
     CK(cudaGetLastError());

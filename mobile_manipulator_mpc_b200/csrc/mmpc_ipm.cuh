@@ -31,6 +31,24 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi) {
   return v;
 }
 
+// Reciprocal instead of an IEEE division (a double division is ~35 instructions with its slow-path
+// check; one reciprocal feeds every quotient with the same denominator).
+#if defined(MMPC_EMULATE) || defined(MMPC_EMULATE_LANE)
+__device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+#else
+__device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+#endif
+// IPOPT's multiplier safeguard  z <- max(min(z, kappa mu/d), mu/(kappa d)),  kappa = 1e10, id = 1/d
+__device__ __forceinline__ double zclamp(double z, double mu, double id) { double r = mu * id; return fmax(fmin(z, 1e10 * r), 1e-10 * r); }
+// Fraction to the boundary without a division per candidate: the smallest quotient num/den (num > 0,
+// den > 0) is tracked as a pair and compared by cross-multiplication; den = 0 stands for +infinity.
+struct MinRatio {
+  double num, den;
+  __device__ __forceinline__ void init() { num = 1.0; den = 0.0; }
+  __device__ __forceinline__ void add(double n, double d) { if (n * den < num * d) { num = n; den = d; } }  // n/d < num/den
+  __device__ __forceinline__ double value(double tau) const { return den > 0 ? fmin(1.0, tau * num / den) : 1.0; }
+};
+
 // log of a running product without one log() per factor
 struct LogProd {
   double prod, acc;

@@ -53,8 +53,10 @@ struct SParams {
   int* gi;         // per-instance ints     gi[field * LS + b]
   int* lists;      // 2 lists of LS ints: E (next phase eval), T (next phase trial)
   int* cnt;        // their lengths
-  long long LS;    // instance stride (B_max rounded up)
+  long long LS;    // B_max rounded up to a multiple of 32 (whole tiles)
+  int ND;          // per-instance doubles (staged_inst_doubles)
   int R, STG, ITSZ;
+  int parts;       // 1: step and trial run as warp-specialised parts (mmpc_parts.cuh); needs fused
   int fused;       // 1: the trial kernel also evaluates the next iteration's derivatives (no eval kernel per round)
   int team;        // 1: 16-lane column-parallel Riccati (mmpc_team.cuh), 0: one thread per instance
 };
@@ -80,8 +82,9 @@ constexpr int SGY_S = 9, SGY_U = 10, SGY_V = 15;
 constexpr int D_MU = 0, D_REGLAST = 1, D_THMAX = 2, D_THMIN = 3, D_E0 = 4, D_OS = 5, D_ALPHA = 6, D_AD = 7,
               D_GPHI = 8, D_THETA = 9, D_PHI0 = 10, D_FILT = 11, D_PL = 43, D_CIRC = 43 + 6 * MMPC_MAX_PLANES;
 // per-instance ints
-constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_NFIELDS = 6;
-constexpr int ST_ACTIVE = 0, ST_DONE = 1, ST_TRIAL = 2;  // ACTIVE: next phase is eval; TRIAL: next phase is a trial
+constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_NFIELDS = 7;
+constexpr int ST_ACTIVE = 0, ST_DONE = 1, ST_TRIAL = 2, ST_FINISH = 3;  // FINISH: results are written by the step kernels of this round
+//  // ACTIVE: next phase is eval; TRIAL: next phase is a trial
 // partial slots
 constexpr int NPART = 8;
 
@@ -99,27 +102,51 @@ struct Inst {
   const SParams& P;
   const MmpcConfig& cfg;
   double* w;   // ws + b
-  double* gd;  // P.gd + b
-  int* gi;     // P.gi + b
+  double* gd;  // this instance's lane in its tile of P.gd
+  int* gi;     // this instance's lane in its tile of P.gi
   long long LS;
   int N, R, STG, ITSZ, B2, nobs, npl, b;
   double dt;
 
   __device__ __forceinline__ Inst(const SParams& p, int b_) : P(p), cfg(p.cfg) {
-    b = b_; w = p.ws + b_; gd = p.gd + b_; gi = p.gi + b_; LS = p.LS;
+    b = b_; LS = p.LS;
+    // tile-major layout: the 32 instances of a tile keep all their fields together, lane-interleaved
+    //   ws[((tile*(N+1) + k)*STG + f)*32 + lane]   gd[(tile*ND + f)*32 + lane]   gi[(tile*J_NFIELDS + f)*32 + lane]
+    // so a warp of neighbouring instances reads one 256-byte line per field, consecutive fields are
+    // consecutive lines (DRAM page locality), and the lane stride is a compile-time constant.
+    const long long tile = b_ >> 5; const int ln = b_ & 31;
+    w = p.ws + ((tile * (cfg.N + 1) * p.STG) << 5) + ln;
+    gd = p.gd + ((tile * p.ND) << 5) + ln;
+    gi = p.gi + ((tile * J_NFIELDS) << 5) + ln;
     N = cfg.N; R = p.R; STG = p.STG; ITSZ = p.ITSZ; B2 = 2 * p.ITSZ; nobs = cfg.n_obs; dt = cfg.dt;
     npl = 0;
   }
-  __device__ __forceinline__ double& W(int k, int o) const { return w[((long long)k * STG + o) * LS]; }
-  __device__ __forceinline__ double& W2(int k, int o) const { return w[((long long)k * STG + B2 + o) * LS]; }
+  __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << 5]; }
+  __device__ __forceinline__ double& W2(int k, int o) const { return w[(k * STG + B2 + o) << 5]; }
   __device__ __forceinline__ double& Qw(int k, int o) const { return P.qp[((long long)k * LS + b) * QS + o]; }
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
-  __device__ __forceinline__ double& D(int o) const { return gd[(long long)o * LS]; }
-  __device__ __forceinline__ int& J(int o) const { return gi[(long long)o * LS]; }
+  __device__ __forceinline__ double& D(int o) const { return gd[o << 5]; }
+  __device__ __forceinline__ int& J(int o) const { return gi[o << 5]; }
   __device__ __forceinline__ double circ(int k, int i, int c) const {
     return cfg.obs_per_stage ? W2(k, S_DT + R + 3 * i + c) : D(D_CIRC + 3 * i + c);
   }
   __device__ __forceinline__ void load_npl() { npl = J(J_NPL); }
+  // L2 prefetch of every field of stage k this thread is going to read (current iterate, step, references,
+  // rows): the loads further down then find their lines in L2 instead of paying a full HBM round trip
+  // one after the other.  A warp touches one 256-byte line per field, so this is one request per field.
+  __device__ __forceinline__ void prefetch_stage(int k, int it, bool with_step) const {
+#ifdef MMPC_PREFETCH_L2
+    const int n_it = I_T + 2 * R;
+    for (int o = 0; o < n_it; ++o) prefetch_l2(&W(k, it + o));
+    const int o0 = with_step ? S_DX : S_FK, o1 = S_DT + (with_step ? R : 0) + (cfg.obs_per_stage ? 3 * nobs : 0);
+    for (int o = o0; o < S_DFC + 9; ++o) prefetch_l2(&W2(k, o));
+    for (int o = IN_XREF; o < o1; ++o) prefetch_l2(&W2(k, o));
+    if (with_step && k < N) {
+      for (int i = 0; i < NX; ++i) { prefetch_l2(&W(k + 1, it + I_X + i)); prefetch_l2(&W(k + 1, it + I_LAM + i)); }
+      for (int i = 0; i < NX; ++i) { prefetch_l2(&W2(k + 1, S_DX + i)); prefetch_l2(&W2(k + 1, S_LAMN + i)); }
+    }
+#endif
+  }
 
   // -max_j c[i][j] for body point i (:76-87); returns the arg-max plane
   __device__ __forceinline__ double plane_row(const Point& p, int& jbest) const {
@@ -758,19 +785,14 @@ struct Inst {
   // ------------------------------------------------------------------------------------------
   // step (thread per instance and stage): slack / multiplier steps of every row and bound,
   // fraction to the boundary, merit ingredients of the current point.
-  __device__ void step(int k, double* sm, int bs) {
+  __device__ void step(int k) {
     load_npl();
     const int it = J(J_CUR) * ITSZ;
-    for (int r = 0; r < R; ++r) {
-      async_copy8(sm + r * bs, &W(k, it + I_T + r));
-      async_copy8(sm + (R + r) * bs, &W(k, it + I_T + R + r));
-    }
-    for (int i = 0; i < 3 * nobs; ++i) async_copy8(sm + (2 * R + i) * bs, cfg.obs_per_stage ? &W2(k, S_DT + R + i) : &D(D_CIRC + i));
-    async_commit();
-    const double* smc = sm + 2 * R * bs;  // circles
+    prefetch_stage(k, it, false);
     const double os = D(D_OS), mu = D(D_MU);
     const double tau = fmax(0.99, 1 - mu);
-    double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0;
+    MinRatio rp, rd; rp.init(); rd.init();  // fraction to the boundary: primal, dual
+    double gphi = 0, theta = 0, fsum = 0;
     LogProd lp; lp.init();
     double x[NX], dxv[NX], u[NU], duv[NU];
 #pragma unroll
@@ -789,16 +811,16 @@ struct Inst {
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, z = W(k, it + I_ZXL + i), dz = mu / d - z - z / d * dxv[i];
-          gphi -= mu * dxv[i] / d; lp.mul(d);
-          if (dxv[i] < 0) ap = fmin(ap, -tau * d / dxv[i]);
-          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+          double d = x[i] - lo, id = rcp(d), z = W(k, it + I_ZXL + i), dz = mu * id - z - z * id * dxv[i];
+          gphi -= mu * dxv[i] * id; lp.mul(d);
+          if (dxv[i] < 0) rp.add(d, -dxv[i]);
+          if (dz < 0) rd.add(z, -dz);
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], z = W(k, it + I_ZXU + i), dz = mu / d - z + z / d * dxv[i];
-          gphi += mu * dxv[i] / d; lp.mul(d);
-          if (dxv[i] > 0) ap = fmin(ap, tau * d / dxv[i]);
-          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+          double d = hi - x[i], id = rcp(d), z = W(k, it + I_ZXU + i), dz = mu * id - z + z * id * dxv[i];
+          gphi += mu * dxv[i] * id; lp.mul(d);
+          if (dxv[i] > 0) rp.add(d, dxv[i]);
+          if (dz < 0) rd.add(z, -dz);
         }
       }
     }
@@ -812,16 +834,16 @@ struct Inst {
         fsum += Rj * e * e + Wj * dl * dl; gphi += (2 * Rj * e + 2 * Wj * dl) * duv[j];
         double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
         if (is_fin(lo)) {
-          double d = u[j] - lo, z = W(k, it + I_ZUL + j), dz = mu / d - z - z / d * duv[j];
-          gphi -= mu * duv[j] / d; lp.mul(d);
-          if (duv[j] < 0) ap = fmin(ap, -tau * d / duv[j]);
-          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+          double d = u[j] - lo, id = rcp(d), z = W(k, it + I_ZUL + j), dz = mu * id - z - z * id * duv[j];
+          gphi -= mu * duv[j] * id; lp.mul(d);
+          if (duv[j] < 0) rp.add(d, -duv[j]);
+          if (dz < 0) rd.add(z, -dz);
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], z = W(k, it + I_ZUU + j), dz = mu / d - z + z / d * duv[j];
-          gphi += mu * duv[j] / d; lp.mul(d);
-          if (duv[j] > 0) ap = fmin(ap, tau * d / duv[j]);
-          if (dz < 0) ad = fmin(ad, -tau * z / dz);
+          double d = hi - u[j], id = rcp(d), z = W(k, it + I_ZUU + j), dz = mu * id - z + z * id * duv[j];
+          gphi += mu * duv[j] * id; lp.mul(d);
+          if (duv[j] > 0) rp.add(d, duv[j]);
+          if (dz < 0) rd.add(z, -dz);
         }
       }
 #pragma unroll
@@ -831,21 +853,20 @@ struct Inst {
 #pragma unroll
     for (int q = 0; q < 3; ++q) { f.vr[q] = W2(k, S_FK + 2 + q); f.vh[q] = W2(k, S_FK + 5 + q); }
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
-    async_wait<0>();
     auto row_step = [&](int r, double h, double gd_) {
-      double t = sm[r * bs], z = sm[(R + r) * bs];
+      double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
       double res = h - s + t;
       double dtv = -res - (gd_ - dsv);
       W2(k, S_DT + r) = dtv;
-      double dz = (mu - z * (t + dtv)) / t;
-      theta += fabs(res); gphi -= mu * dtv / t; lp.mul(t);
-      if (dtv < 0) ap = fmin(ap, -tau * t / dtv);
-      if (dz < 0) ad = fmin(ad, -tau * z / dz);
+      double itv = rcp(t), dz = (mu - z * (t + dtv)) * itv;
+      theta += fabs(res); gphi -= mu * dtv * itv; lp.mul(t);
+      if (dtv < 0) rp.add(t, -dtv);
+      if (dz < 0) rd.add(z, -dz);
     };
     for (int i = 0; i < nobs; ++i) {
-      double ddx = x[0] - smc[(3 * i) * bs], ddy = x[1] - smc[(3 * i + 1) * bs];
+      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
       double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
-      row_step(i, (smc[(3 * i + 2) * bs] + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv);
+      row_step(i, (circ(k, i, 2) + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv);
     }
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
@@ -871,13 +892,47 @@ struct Inst {
         row_step(nobs + 4 + i, h, gd_);
       }
     }
-    W2(k, S_PART + 0) = ap; W2(k, S_PART + 1) = ad; W2(k, S_PART + 2) = gphi; W2(k, S_PART + 3) = theta;
+    W2(k, S_PART + 0) = rp.value(tau); W2(k, S_PART + 1) = rd.value(tau); W2(k, S_PART + 2) = gphi; W2(k, S_PART + 3) = theta;
     W2(k, S_PART + 4) = fsum; W2(k, S_PART + 5) = lp.value();
+  }
+
+  // Stage k of the results of an instance that left the solve in this round (state ST_FINISH):
+  // sol.value(U/X/s) :329-330 and the stage's share of the unscaled cost :317
+  __device__ void finish_stage(int k) const {
+    const int it = J(J_CUR) * ITSZ;
+    double fsum = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v = W(k, it + I_X + i), e = v - W2(k, IN_XREF + i);
+      fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
+      if (P.X) P.X[((long long)b * (N + 1) + k) * NX + i] = v;
+    }
+    if (k < N)
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        double v = W(k, it + I_U + j), e = v - W2(k, IN_UREF + j), dl = v - W2(k, IN_ULAST + j);
+        fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
+        P.U[((long long)b * N + k) * NU + j] = v;
+      }
+    double s = W(k, it + I_S);
+    fsum += cfg.S * s * s;
+    if (P.s) P.s[(long long)b * (N + 1) + k] = s;
+    W2(k, S_PART + 0) = fsum;
   }
 
   // ctrl_step (thread per instance): reduce the step partials, start the line search.
   // Returns true if the instance goes on to a trial.
   __device__ bool ctrl_step() {
+    if (J(J_STATE) == ST_FINISH) {  // close an instance whose stages were written by finish_stage
+      double fsum = 0;
+      for (int k = 0; k <= N; ++k) fsum += W2(k, S_PART + 0);
+      if (P.cost) P.cost[b] = fsum;
+      if (P.kkt) P.kkt[b] = D(D_E0);
+      if (P.iters) P.iters[b] = J(J_IT);
+      P.status[b] = J(J_STATUS);
+      J(J_STATE) = ST_DONE;
+      return false;
+    }
     if (J(J_STATE) != ST_ACTIVE) return false;
     double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0, logsum = 0;
     for (int k = 0; k <= N; ++k) {
@@ -1003,21 +1058,11 @@ struct Inst {
   // is exactly where the next iteration linearises -- the stage QP, defect, FK cache and KKT partials at
   // the candidate, all from registers.  A rejected candidate only wastes the derivative arithmetic: its
   // records are overwritten by the next trial before anything reads them.
-  // sm/bs: this thread's column of the block's shared-memory row buffer (element i at sm[i * bs]): the
-  // row slacks, multipliers, steps and the circles are fetched with cp.async up front, so the row loops
-  // below never wait on HBM.
-  __device__ void trial_eval(int k, double* sm, int bs) {
+  __device__ void trial_eval(int k) {
     load_npl();
     const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
     const double os = D(D_OS), mu = D(D_MU), alpha = D(D_ALPHA), ad = D(D_AD);
-    for (int r = 0; r < R; ++r) {
-      async_copy8(sm + r * bs, &W(k, it + I_T + r));
-      async_copy8(sm + (R + r) * bs, &W(k, it + I_T + R + r));
-      async_copy8(sm + (2 * R + r) * bs, &W2(k, S_DT + r));
-    }
-    for (int i = 0; i < 3 * nobs; ++i) async_copy8(sm + (3 * R + i) * bs, cfg.obs_per_stage ? &W2(k, S_DT + R + i) : &D(D_CIRC + i));
-    async_commit();
-    const double* smc = sm + 3 * R * bs;  // circles
+    prefetch_stage(k, it, true);
     double theta = 0, fsum = 0; bool ok = true;
     LogProd lp; lp.init();
     RowAcc A;
@@ -1090,10 +1135,10 @@ struct Inst {
       Qw(k, Q_HPU) = 0; Qw(k, Q_H45) = 0; Qw(k, Q_H35) = 0;
     }
     // candidate multiplier of a bound at distance d_old -> d (sgn = +1 lower, -1 upper); merit + KKT bookkeeping
-    auto box = [&](double zold, double d_old, double d, double sgn_dv, int slot) -> double {
-      double dz = mu / d_old - zold - (zold / d_old) * sgn_dv;
-      double z = zold + ad * dz;
-      z = fmax(fmin(z, 1e10 * mu / d), mu / (1e10 * d));
+    auto box = [&](double zold, double d_old, double d, double sgn_dv, int slot, double& id) -> double {
+      double ido = rcp(d_old); id = rcp(d);
+      double dz = mu * ido - zold - (zold * ido) * sgn_dv;
+      double z = zclamp(zold + ad * dz, mu, id);
       W(k, slot) = z;
       if (d <= 0) ok = false; else lp.mul(d);
       A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
@@ -1110,11 +1155,11 @@ struct Inst {
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, z = box(W(k, it + I_ZXL + i), xo[i] - lo, d, dxo[i], jt + I_ZXL + i), id = 1.0 / d;
+          double d = x[i] - lo, id, z = box(W(k, it + I_ZXL + i), xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], z = box(W(k, it + I_ZXU + i), hi - xo[i], d, -dxo[i], jt + I_ZXU + i), id = 1.0 / d;
+          double d = hi - x[i], id, z = box(W(k, it + I_ZXU + i), hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
           Hd += z * id; gB += id; st += z;
         }
       }
@@ -1139,11 +1184,11 @@ struct Inst {
         double st = gr + stu[j];
         double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
         if (is_fin(lo)) {
-          double d = u[j] - lo, z = box(W(k, it + I_ZUL + j), uo[j] - lo, d, duo[j], jt + I_ZUL + j), id = 1.0 / d;
+          double d = u[j] - lo, id, z = box(W(k, it + I_ZUL + j), uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], z = box(W(k, it + I_ZUU + j), hi - uo[j], d, -duo[j], jt + I_ZUU + j), id = 1.0 / d;
+          double d = hi - u[j], id, z = box(W(k, it + I_ZUU + j), hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
           Hd += z * id; gB += id; st += z;
         }
         es = fmax(es, fabs(st));
@@ -1151,18 +1196,17 @@ struct Inst {
       Qw(k, Q_HUU + j) = Hd; Qw(k, Q_GA + SGY_U + j) = gA; Qw(k, Q_GB + SGY_U + j) = gB;
     }
     // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
-    async_wait<0>();
     auto row = [&](int r, double h, double& z, double& it_, double& res) {
-      double t = sm[r * bs], dtv = sm[(2 * R + r) * bs];
-      z = sm[(R + r) * bs];
+      double t = W(k, it + I_T + r), dtv = W2(k, S_DT + r);
+      z = W(k, it + I_T + R + r);
       double tt = fmax(fma(alpha, dtv, t), s - h);  // slack reset (Nocedal & Wright 19.30)
-      double dz = (mu - z * (t + dtv)) / t;
-      z += ad * dz; z = fmax(fmin(z, 1e10 * mu / tt), mu / (1e10 * tt));
+      double dz = (mu - z * (t + dtv)) * rcp(t);
+      it_ = rcp(tt);
+      z = zclamp(z + ad * dz, mu, it_);
       W(k, jt + I_T + r) = tt; W(k, jt + I_T + R + r) = z;
       res = h - s + tt;
       theta += fabs(res);
       if (tt <= 0) ok = false; else lp.mul(tt);
-      it_ = 1.0 / tt;
       A.prim = fmax(A.prim, fabs(res));
       double zt = z * tt;
       A.chi = fmax(A.chi, zt); A.clo = fmin(A.clo, zt);
@@ -1171,9 +1215,9 @@ struct Inst {
       A.csum += sig; A.be0 += sig * res; A.be1 += it_;
     };
     for (int i = 0; i < nobs; ++i) {  // obsAvoid :49-54
-      double ddx = x[0] - smc[(3 * i) * bs], ddy = x[1] - smc[(3 * i + 1) * bs];
+      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
       double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
-      double h = (smc[(3 * i + 2) * bs] + cfg.base_radius) - d;
+      double h = (circ(k, i, 2) + cfg.base_radius) - d;
       double z, it_, res; row(i, h, z, it_, res);
       double sig = z * it_, nx = ddx * inv, ny = ddy * inv, zd = z * inv;
       A.H[pidx(0, 0)] += sig * nx * nx - zd * (1 - nx * nx);
@@ -1289,6 +1333,11 @@ struct Inst {
   }
 };
 
+// state (ST_*) of instance b
+__device__ __forceinline__ int& inst_state(const SParams& P, int b) {
+  return P.gi[((((long long)(b >> 5)) * J_NFIELDS + J_STATE) << 5) + (b & 31)];
+}
+
 // ---- lists ---------------------------------------------------------------------------------------
 // Two lists of instance indices, rebuilt in ascending order (so that the gathers of the phase
 // kernels stay as coalesced as the surviving instances allow) by an ordered compaction of the
@@ -1300,18 +1349,16 @@ __device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.LS
 __device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init(); }
 __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.eval(k); }
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
-// doubles of shared-memory row buffer one thread of the step / trial kernels needs
-__host__ __device__ inline int staged_rowbuf_doubles(const MmpcConfig& c) { return 3 * staged_rows(c) + 3 * c.n_obs; }
-
-__device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {
+__device__ inline void body_step(const SParams& P, int j, int k) {
   Inst S(P, list_E(P)[j]);
-  if (S.J(J_STATE) != ST_ACTIVE) return;
-  S.step(k, sm, bs);
+  const int st = S.J(J_STATE);
+  if (st == ST_FINISH) S.finish_stage(k);
+  else if (st == ST_ACTIVE) S.step(k);
 }
 __device__ inline void body_ctrl_step(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.ctrl_step(); }
-__device__ inline void body_trial(const SParams& P, int j, int k, double* sm, int bs) {
+__device__ inline void body_trial(const SParams& P, int j, int k) {
   Inst S(P, list_T(P)[j]);
-  if (P.fused) S.trial_eval(k, sm, bs); else S.trial(k);
+  if (P.fused) S.trial_eval(k); else S.trial(k);
 }
 __device__ inline void body_ctrl_trial(const SParams& P, int j) { Inst S(P, list_T(P)[j]); S.ctrl_trial(); }
 
@@ -1319,7 +1366,7 @@ __device__ inline void body_ctrl_trial(const SParams& P, int j) { Inst S(P, list
 // ordered compaction of the instances in state `want` into list `which` (0 = E, 1 = T)
 inline void compact_list(const SParams& P, int which, int want) {
   int n = 0; int* list = which ? list_T(P) : list_E(P);
-  for (int b = 0; b < P.B; ++b) if (P.gi[(long long)J_STATE * P.LS + b] == want) list[n++] = b;
+  for (int b = 0; b < P.B; ++b) if (inst_state(P, b) == want) list[n++] = b;
   P.cnt[which] = n;
 }
 #else
@@ -1328,7 +1375,6 @@ inline void compact_list(const SParams& P, int which, int want) {
 // the second pass writes the indices in ascending order.
 __global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_constant__ SParams P, int which, int want) {
   __shared__ int wtot[32];
-  const int* st = P.gi + (long long)J_STATE * P.LS;
   int* list = which ? list_T(P) : list_E(P);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = ((P.B + 1023) / 1024) * 32;  // entries per warp, multiple of 32
@@ -1336,7 +1382,7 @@ __global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_const
   int c = 0;
   for (int b0 = lo; b0 < hi; b0 += 32) {
     int b = b0 + lane;
-    bool f = b < hi && st[b] == want;
+    bool f = b < hi && inst_state(P, b) == want;
     c += __popc(__ballot_sync(FULL, f));
   }
   if (lane == 0) wtot[warp] = c;
@@ -1345,7 +1391,7 @@ __global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_const
   for (int w2 = 0; w2 < 32; ++w2) { int v = wtot[w2]; if (w2 < warp) off += v; tot += v; }
   for (int b0 = lo; b0 < hi; b0 += 32) {
     int b = b0 + lane;
-    bool f = b < hi && st[b] == want;
+    bool f = b < hi && inst_state(P, b) == want;
     unsigned m = __ballot_sync(FULL, f);
     if (f) list[off + __popc(m & ((1u << lane) - 1))] = b;
     off += __popc(m);
@@ -1368,23 +1414,28 @@ __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant_
   const int n = P.cnt[0];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_solve(P, j);
 }
-__global__ void __launch_bounds__(64) staged_step_kernel(const __grid_constant__ SParams P) {
-  extern __shared__ double rowbuf[];
+// resident blocks per SM the step / trial kernels are compiled for (A/B on B200: 3 beats 1 and 4)
+#ifndef MMPC_STEP_MINB
+#define MMPC_STEP_MINB 3
+#endif
+#ifndef MMPC_TRIAL_MINB
+#define MMPC_TRIAL_MINB 3
+#endif
+__global__ void __launch_bounds__(128, MMPC_STEP_MINB) staged_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_step(P, (int)(t % n), (int)(t / n), rowbuf + threadIdx.x, blockDim.x);
+    body_step(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_step(P, j);
 }
-__global__ void __launch_bounds__(64) staged_trial_kernel(const __grid_constant__ SParams P) {
-  extern __shared__ double rowbuf[];
+__global__ void __launch_bounds__(128, MMPC_TRIAL_MINB) staged_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[1];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_trial(P, (int)(t % n), (int)(t / n), rowbuf + threadIdx.x, blockDim.x);
+    body_trial(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[1];

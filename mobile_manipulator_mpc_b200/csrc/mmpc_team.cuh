@@ -14,8 +14,9 @@
 // kernel sets the latency of a round once the batch has thinned out.
 //
 // Every decision (pivot signs, convergence, barrier update) is taken on values that are bit-identical
-// in all 16 lanes (broadcast values, butterfly reductions), so a team never diverges at a shuffle; the
-// two teams of a warp may diverge from each other (they use disjoint shuffle masks).
+// in all 16 lanes (broadcast values, butterfly reductions), so a team never diverges at a shuffle, and
+// the two teams of a warp run the same instruction stream (full-mask, width-16 shuffles; a team that
+// needs no further factorisation repeats its last one while its partner retries with a larger delta_w).
 #pragma once
 #include "mmpc_staged.cuh"
 
@@ -259,7 +260,7 @@ struct Team {
 #pragma unroll
         for (int q2 = p + 1; q2 < NU; ++q2) Lm[q2][p] = col[9 + q2] * ip;
       }
-      if (bad) { async_wait<0>(); return 1; }
+      if (warp_all(bad != 0)) { async_wait<0>(); return 1; }  // both teams of the warp failed: no point in going on
       // gains: K(:, c) = -L^-T y  (lane 14: kff)
       double kc[NU];
 #pragma unroll
@@ -287,7 +288,7 @@ struct Team {
     }
     async_wait<0>();
     if (!(cn > 1e-13)) return 1;
-    return 0;
+    return bad;
   }
 
   // roll-out of the Newton step: dx, du, ds and the new costates lam+ = P [dx; ds] + p.
@@ -350,41 +351,11 @@ struct Team {
     async_wait<0>();
   }
 
-  // results: sol.value(U/X/s/cost) :317,:329-330; stage k is written by lane k mod 16
-  __device__ void finish(int status) {
-    const MmpcConfig& cfg = S.cfg; const SParams& P = S.P;
-    const int N = S.N, b = S.b;
-    const int it = S.J(J_CUR) * S.ITSZ;
-    double fsum = 0;
-    for (int k = c; k <= N; k += 16) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        double v = S.W(k, it + I_X + i), e = v - S.W2(k, IN_XREF + i);
-        fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
-        if (P.X) P.X[((long long)b * (N + 1) + k) * NX + i] = v;
-      }
-      if (k < N)
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-          double v = S.W(k, it + I_U + j), e = v - S.W2(k, IN_UREF + j), dl = v - S.W2(k, IN_ULAST + j);
-          fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
-          P.U[((long long)b * N + k) * NU + j] = v;
-        }
-      double s = S.W(k, it + I_S);
-      fsum += cfg.S * s * s;
-      if (P.s) P.s[(long long)b * (N + 1) + k] = s;
-    }
-    fsum = tsum(fsum);
-    if (c == 0) {
-      if (P.cost) P.cost[b] = fsum;
-      if (P.kkt) P.kkt[b] = S.D(D_E0);
-      if (P.iters) P.iters[b] = S.J(J_IT);
-      P.status[b] = status;
-      S.J(J_STATE) = ST_DONE;
-    }
-  }
-
-  // KKT reduction, convergence test, barrier update, factorisation with inertia correction, roll-out
+  // KKT reduction, convergence test, barrier update, factorisation with inertia correction, roll-out.
+  // Both teams of a warp execute exactly the same instruction stream (full-mask shuffles): a team whose
+  // instance needs no (further) factorisation simply repeats its last one, which rewrites the same values.
+  // An instance that leaves here is only marked (state ST_FINISH + status); its results are written by
+  // the stage-parallel step kernel of the same round.
   __device__ void solve() {
     const MmpcConfig& cfg = S.cfg;
     const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5;
@@ -403,32 +374,41 @@ struct Team {
     kp.sum_lam = tsum(kp.sum_lam); kp.sum_z = tsum(kp.sum_z); nz = tsum(nz); neq = tsum(neq);
     kp.n_z = (int)nz; kp.n_eq = (int)neq;
     const double E0 = kkt_error(kp, 0.0);
-    // every lane of the team reads the scalar state before lane 0 rewrites any of it
+    // every lane reads the scalar state before lane 0 rewrites any of it
     const int iter = S.J(J_IT);
     double mu = S.D(D_MU);
     const double reg_last = S.D(D_REGLAST);
     team_sync();
     if (c == 0) S.D(D_E0) = E0;
-    team_sync();
-    if (!(E0 == E0)) { finish(MMPC_STATUS_NAN); return; }
-    if (E0 <= tol) { finish(MMPC_STATUS_CONVERGED); return; }
-    if (iter >= cfg.max_iter) { finish(MMPC_STATUS_MAX_ITER); return; }
-    bool mu_changed = false;
-    while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
-      mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
+    int fin = -1;  // status with which the instance leaves the solve, -1: goes on
+    if (!(E0 == E0)) fin = MMPC_STATUS_NAN;
+    else if (E0 <= tol) fin = MMPC_STATUS_CONVERGED;
+    else if (iter >= cfg.max_iter) fin = MMPC_STATUS_MAX_ITER;
+    if (fin < 0) {
+      bool mu_changed = false;
+      while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
+        mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
+      }
+      if (mu_changed && c == 0) { S.J(J_NFILT) = 0; S.D(D_MU) = mu; }
     }
-    if (mu_changed && c == 0) { S.J(J_NFILT) = 0; S.D(D_MU) = mu; }
+    bool need = fin < 0;
     double reg = 0;
     int tries = 0;
     for (;;) {
-      int fail = riccati(reg, mu, it);
-      if (!fail) { if (reg > 0 && c == 0) S.D(D_REGLAST) = reg; break; }
-      if (reg == 0) reg = (reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3);
-      else reg *= (reg_last == 0 ? 100 : 8);
-      if (++tries > 40 || reg > 1e20) { finish(MMPC_STATUS_FACTOR); return; }
+      const int fail = riccati(reg, mu, it);
+      if (need) {
+        if (!fail) { need = false; if (reg > 0 && c == 0) S.D(D_REGLAST) = reg; }
+        else {
+          if (reg == 0) reg = (reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3);
+          else reg *= (reg_last == 0 ? 100 : 8);
+          if (++tries > 40 || reg > 1e20) { fin = MMPC_STATUS_FACTOR; need = false; }
+        }
+      }
+      if (!warp_any(need)) break;
     }
     team_sync();  // the Riccati records written by the other lanes are read back in the roll-out
     rollout(mu, it);
+    if (fin >= 0 && c == 0) { S.J(J_STATUS) = fin; S.J(J_STATE) = ST_FINISH; }
   }
 };
 
@@ -445,10 +425,13 @@ __global__ void __launch_bounds__(128, 4) staged_solve_team_kernel(const __grid_
   __syncthreads();
   const int n = P.cnt[0];
   const int c = threadIdx.x & 15;
-  // a team (half warp) strides over the list; both halves of a warp run the same trip count
-  const int teams = (gridDim.x * blockDim.x) >> 4;
-  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; j < n; j += teams)
+  // a warp strides over pairs of list entries; with an odd count the last warp's second team repeats the
+  // first team's instance (same computation, same stores) so that the warp stays in lock step
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; j0 < n; j0 += 2 * warps) {
+    const int j = min(j0 + ((threadIdx.x >> 4) & 1), n - 1);
     body_solve_team(P, j, c, ht, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
+  }
 }
 #endif
 

@@ -21,7 +21,7 @@ def lib():
         _LIB.lane = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_lane.so"))
         _LIB.lane.mmpc_emu_lane_solve.argtypes = _LIB.mmpc_emu_solve.argtypes
         _LIB.staged = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_staged.so"))
-        _LIB.staged.mmpc_emu_staged_solve.argtypes = _LIB.mmpc_emu_solve.argtypes + [C.POINTER(C.c_int32), C.c_int32, C.c_int32]
+        _LIB.staged.mmpc_emu_staged_solve.argtypes = _LIB.mmpc_emu_solve.argtypes + [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]
     return _LIB
 
 
@@ -37,11 +37,14 @@ def solve(batch, cfg, kernel="warp"):
     out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
                kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])
-    if kernel in ("staged", "staged_thread", "staged_unfused"):
+    if kernel.startswith("staged"):
+        # staged: product default (team Riccati, fused trial+evaluation, warp-specialised parts);
+        # staged_thread: one-thread Riccati; staged_fat: one thread per item; staged_unfused: separate eval
         rounds = C.c_int32(0)
         team = 1 if kernel == "staged" else 0
         fused = 0 if kernel == "staged_unfused" else 1
-        assert lib().staged.mmpc_emu_staged_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo), C.byref(rounds), team, fused) == 0
+        parts = 1 if kernel in ("staged", "staged_thread") else 0
+        assert lib().staged.mmpc_emu_staged_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo), C.byref(rounds), team, fused, parts) == 0
         out["rounds"] = rounds.value
         return out
     fn = lib().mmpc_emu_solve if kernel == "warp" else lib().lane.mmpc_emu_lane_solve

@@ -18,6 +18,7 @@ constexpr unsigned FULL = 0xffffffffu;
 inline int lane_id() { return 0; }
 inline void sync_warp() {}
 inline bool warp_any(bool p) { return p; }
+inline bool warp_all(bool p) { return p; }
 inline double shfl_xor(double v, int) { return v; }
 inline int shfl_xor(int v, int) { return v; }
 inline unsigned lane_next_instance(unsigned* counter) { return (*counter)++; }
@@ -50,5 +51,6 @@ inline void async_copy8(double* dst, const double* src) { dst[0] = src[0]; }
 inline void async_copy16(double* dst, const double* src) { dst[0] = src[0]; dst[1] = src[1]; }
 inline void async_commit() {}
 template <int PENDING> inline void async_wait() {}
+inline void prefetch_l2(const void*) {}
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 }  // namespace mmpc

@@ -45,6 +45,7 @@ inline bool warp_any(bool p) {
   bool r = false; for (int i = 0; i < 32; ++i) r = r || g_emu->slot_i[i];
   emu_barrier(); return r;
 }
+inline bool warp_all(bool p) { return !warp_any(!p); }
 inline unsigned next_instance(unsigned* counter) {
   if (lane_id() == 0) { g_emu->slot_i[0] = *counter; *counter += 1; }
   emu_barrier(); unsigned v = (unsigned)g_emu->slot_i[0]; emu_barrier(); return v;

@@ -6,6 +6,7 @@
 #include <vector>
 #include "emu_lane_runtime.h"
 #include "../../mobile_manipulator_mpc_b200/csrc/mmpc_team.cuh"
+#include "../../mobile_manipulator_mpc_b200/csrc/mmpc_parts.cuh"
 
 namespace mmpc { EmuTeam* g_team = nullptr; }
 using namespace mmpc;
@@ -36,24 +37,23 @@ static void run_team(const SParams& P, int j, std::vector<char*>& stacks) {
 }
 
 extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out,
-                                     int32_t* rounds_out, int32_t team, int32_t fused) {
+                                     int32_t* rounds_out, int32_t team, int32_t fused, int32_t parts) {
   SParams P; memset(&P, 0, sizeof P);
   P.cfg = *cfg; P.B = B;
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
   P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
   P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
-  P.R = staged_rows(*cfg); P.ITSZ = staged_itsz(*cfg); P.STG = staged_stage_doubles(*cfg); P.LS = B;
-  std::vector<double> ws((size_t)(cfg->N + 1) * P.STG * B, 0.0), gd((size_t)staged_inst_doubles(*cfg) * B, 0.0);
-  std::vector<double> qp((size_t)(cfg->N + 1) * QS * B, 0.0), rk((size_t)(cfg->N + 1) * RS * B, 0.0);
-  P.qp = qp.data(); P.rk = rk.data(); P.team = team; P.fused = fused;
+  P.R = staged_rows(*cfg); P.ITSZ = staged_itsz(*cfg); P.STG = staged_stage_doubles(*cfg); P.LS = (B + 31) / 32 * 32; P.ND = staged_inst_doubles(*cfg);
+  std::vector<double> ws((size_t)(cfg->N + 1) * P.STG * P.LS, 0.0), gd((size_t)staged_inst_doubles(*cfg) * P.LS, 0.0);
+  std::vector<double> qp((size_t)(cfg->N + 1) * QS * P.LS, 0.0), rk((size_t)(cfg->N + 1) * RS * P.LS, 0.0);
+  P.qp = qp.data(); P.rk = rk.data(); P.team = team; P.fused = fused; P.parts = parts;
   EmuTeam* tw = new EmuTeam(); g_team = tw;
   std::vector<char*> stacks(16);
   for (int i = 0; i < 16; ++i) stacks[i] = (char*)malloc(1 << 18);
-  std::vector<int> gi((size_t)J_NFIELDS * B, 0), lists((size_t)2 * B, 0);
+  std::vector<int> gi((size_t)J_NFIELDS * P.LS, 0), lists((size_t)2 * P.LS, 0);
   int cnt[2] = {0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
   for (int b = 0; b < B; ++b) body_init(P, b);
-  std::vector<double> rowbuf(staged_rowbuf_doubles(*cfg) + 1, 0.0);
   int N = cfg->N, r = 0;
   for (;; ++r) {
     compact_list(P, 0, ST_ACTIVE);
@@ -61,11 +61,18 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     if (!fused || r == 0)  // fused: only the starting point needs the stand-alone evaluation
       for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_eval(P, j, k);
     for (int j = 0; j < nE; ++j) { if (team) run_team(P, j, stacks); else body_solve(P, j); }
-    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_step(P, j, k, rowbuf.data(), 1);
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) {
+      if (!parts) body_step(P, j, k);
+      else if (inst_state(P, list_E(P)[j]) == ST_ACTIVE) body_parts_item(P, list_E(P)[j], k, false);
+      else if (inst_state(P, list_E(P)[j]) == ST_FINISH) { Inst F(P, list_E(P)[j]); F.finish_stage(k); }
+    }
     for (int j = 0; j < nE; ++j) body_ctrl_step(P, j);
     compact_list(P, 1, ST_TRIAL);
     int nT = cnt[1];
-    for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) body_trial(P, j, k, rowbuf.data(), 1);
+    for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) {
+      if (!parts) body_trial(P, j, k);
+      else body_parts_item(P, list_T(P)[j], k, true);
+    }
     for (int j = 0; j < nT; ++j) body_ctrl_trial(P, j);
     if (nT == 0) break;
     if (r > 200000) return 1;
