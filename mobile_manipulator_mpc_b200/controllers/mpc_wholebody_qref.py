@@ -195,8 +195,6 @@ class MPCWholeBody:
     def solve_batch(self, x_init, traj_ref, u_ref, u_last=None, u_guess=None, circles=None, planes=None,
                     n_pl_inst=None):
         """B instances at once (host arrays).  circles/planes default to the constructor's lists."""
-        if self.terminal_xy_eq:
-            raise NotImplementedError("terminal xy equality (interface_wholebody_qref.py:167) is not implemented yet")
         x_init = np.asarray(x_init, float)
         B = x_init.shape[0]
         N = self.N
@@ -211,6 +209,8 @@ class MPCWholeBody:
         if c.n_pl:
             batch["planes"] = np.broadcast_to(self._planes_array(), (B, c.n_pl, 6)) if planes is None else planes
         batch["n_pl_inst"] = n_pl_inst
+        if self.terminal_xy_eq:   # opti.subject_to(X[N, :2] == X_ref[N, :2])  interface_wholebody_qref.py:167
+            batch["flags"] = np.ones(B, np.uint8)
         out = self._solver.solve_host(batch)
         self.last_info = {k: out[k] for k in ("status", "iters", "kkt", "cost")}
         return out

@@ -247,7 +247,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
   P.ws = h->sg.ws; P.qp = h->sg.qp; P.rk = h->sg.rk; P.team = h->sg_team; P.fused = h->sg_fused;
   const PartPlan plan = part_plan(cfg);
-  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10) ? 1 : 0; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
+  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10 && cfg.mode == MMPC_MODE_CLEAN) ? 1 : 0; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
   P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = STG; P.ND = staged_inst_doubles(cfg);
   // profiling: one timing event in front of every launch; the time up to the next event is
   // charged to that launch's phase (events are stream-ordered, so this is device time)
@@ -335,12 +335,15 @@ extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const
   if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
   if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
   if ((h->cfg.n_obs > 0 && !in->circles) || (h->cfg.n_pl > 0 && !in->planes)) return MMPC_ERR_ARG;
-  if (h->cfg.mode != MMPC_MODE_CLEAN) return MMPC_ERR_UNSUPPORTED;
   if (B == 0) return MMPC_OK;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
   int kernel = h->kernel == MMPC_KERNEL_AUTO ? MMPC_KERNEL_STAGED : h->kernel;
+  // the terminal equality (flags) is implemented by the staged solver with the fused trial kernel only
+  if (in->flags && (kernel != MMPC_KERNEL_STAGED || !h->sg_fused)) return MMPC_ERR_UNSUPPORTED;
+  // so are the reference NLP's bug-for-bug rows (MMPC_MODE_REFERENCE)
+  if (h->cfg.mode != MMPC_MODE_CLEAN && (kernel != MMPC_KERNEL_STAGED || !h->sg_fused)) return MMPC_ERR_UNSUPPORTED;
   if (kernel == MMPC_KERNEL_STAGED) return launch_staged(h, B, in, out, st);
   int rc = kernel == MMPC_KERNEL_LANE ? launch_lane(h, B, in, out, st) : launch_warp(h, B, in, out, st);
   if (rc != MMPC_OK) return rc;

@@ -359,6 +359,16 @@ struct Parts {
 #pragma unroll
       for (int i = 0; i < NX; ++i) B.c.theta += fabs(S.W2(k, S_DFC + i));
     }
+    const bool teq = S.term_eq(k);
+    double nu[2] = {0, 0};
+    if (teq && trial) {  // candidate multipliers of the terminal equality
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        double no = S.W(0, it + I_LAM + i);
+        nu[i] = no + alpha * (S.W2(0, S_LAMN + i) - no);
+        S.W(0, jt + I_LAM + i) = nu[i];
+      }
+    }
     // cost and boxes -- :192-205, :240-245
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
@@ -378,6 +388,11 @@ struct Parts {
           double d = hi - x[i], id, z = box(S.W(k, it + I_ZXU + i), hi - xo[i], d, -dxo[i], jt + I_ZXU + i, B.c, id);
           Hd += z * id; gB += id; st += z;
         }
+      }
+      if (i < 2 && teq) {  // terminal equality row  x_N[i] - xref_N[i] = 0  with multiplier nu[i]
+        Hd += 1.0 / MMPC_DELTA_C; gA += nu[i] + e / MMPC_DELTA_C; st += nu[i];
+        B.c.theta += fabs(e);
+        if (trial) { B.c.prim = fmax(B.c.prim, fabs(e)); B.sum_lam += fabs(nu[i]); B.n_eq += 1; }
       }
       if (i < 3 || i >= 6) {
         const int a = (i < 3) ? i : i - 3;

@@ -82,13 +82,23 @@ constexpr int SGY_S = 9, SGY_U = 10, SGY_V = 15;
 constexpr int D_MU = 0, D_REGLAST = 1, D_THMAX = 2, D_THMIN = 3, D_E0 = 4, D_OS = 5, D_ALPHA = 6, D_AD = 7,
               D_GPHI = 8, D_THETA = 9, D_PHI0 = 10, D_FILT = 11, D_PL = 43, D_CIRC = 43 + 6 * MMPC_MAX_PLANES;
 // per-instance ints
-constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_NFIELDS = 7;
+constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_FLAGS = 7, J_NFIELDS = 8;
 constexpr int ST_ACTIVE = 0, ST_DONE = 1, ST_TRIAL = 2, ST_FINISH = 3;  // FINISH: results are written by the step kernels of this round
 //  // ACTIVE: next phase is eval; TRIAL: next phase is a trial
 // partial slots
 constexpr int NPART = 8;
+// Terminal equality  (x_N, y_N) = (xref_N[0], xref_N[1])  (flags bit 0; interface_wholebody_qref.py:167):
+// multipliers nu[2] with the regularised Newton step  d nu = (dx_N + c) / delta_c  (IPOPT's delta_c), i.e.
+// the terminal Hessian gets 1/delta_c on x and y.  nu lives in the otherwise unused lam slots of stage 0
+// (x_0 is fixed, it has no costate), its Newton target in stage 0's lam+ slots.
+#define MMPC_DELTA_C 1e-6
 
-__host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + 4 + (c.n_pl > 0 ? 6 : 0); }
+// rows per stage: circles | 4 self-collision | 6 proper plane rows | (MMPC_MODE_REFERENCE) 6 x (n_pl - 1) rows with
+// stale plane columns, row (i, j) at index n_obs + 10 + i * (n_pl - 1) + j
+__host__ __device__ inline int staged_stale_rows(const MmpcConfig& c) {
+  return (c.mode == MMPC_MODE_REFERENCE && c.n_pl > 1) ? 6 * (c.n_pl - 1) : 0;
+}
+__host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + 4 + (c.n_pl > 0 ? 6 : 0) + staged_stale_rows(c); }
 __host__ __device__ inline int staged_itsz(const MmpcConfig& c) { return I_T + 2 * staged_rows(c); }
 __host__ __device__ inline int staged_stage_doubles(const MmpcConfig& c) {
   return 2 * staged_itsz(c) + S_FIXED + staged_rows(c) + (c.obs_per_stage ? 3 * c.n_obs : 0);
@@ -131,6 +141,7 @@ struct Inst {
     return cfg.obs_per_stage ? W2(k, S_DT + R + 3 * i + c) : D(D_CIRC + 3 * i + c);
   }
   __device__ __forceinline__ void load_npl() { npl = J(J_NPL); }
+  __device__ __forceinline__ bool term_eq(int k) const { return k == N && (J(J_FLAGS) & 1); }
   // L2 prefetch of every field of stage k this thread is going to read (current iterate, step, references,
   // rows): the loads further down then find their lines in L2 instead of paying a full HBM round trip
   // one after the other.  A warp touches one 256-byte line per field, so this is one request per field.
@@ -177,6 +188,8 @@ struct Inst {
     if (!cfg.obs_per_stage)
       for (int i = 0; i < 3 * nobs; ++i) D(D_CIRC + i) = ldg(P.circles + (long long)b * 3 * nobs + i);
     double gmax = 0;
+    const bool refmode = cfg.mode == MMPC_MODE_REFERENCE && npl > 1;
+    double cprev[6][MMPC_MAX_PLANES], ccur[6][MMPC_MAX_PLANES];
     for (int k = 0; k <= N; ++k) {
       double x[NX];
       if (cfg.obs_per_stage)
@@ -225,6 +238,21 @@ struct Inst {
           W(k, I_T + nobs + 4 + i) = h; hmax = fmax(hmax, h);
         }
       }
+      if (staged_stale_rows(cfg) > 0) {  // rows with stale plane columns: slack k >= 1, j < npl - 1
+        const int nst = cfg.n_pl - 1, r0 = nobs + 10;
+        for (int r = r0; r < R; ++r) W(k, I_T + r) = 0;
+        if (refmode) {
+          double pp[NP] = {x[0], x[1], x[2], x[6], x[7], x[8]}; FK ff;
+          margins(pp, ff, ccur);
+          if (k >= 1)
+            for (int i = 0; i < 6; ++i)
+              for (int j = 0; j < npl - 1; ++j) {
+                int jb; double h = stale_max(ccur, cprev, i, j, jb);
+                W(k, I_T + r0 + i * nst + j) = h; hmax = fmax(hmax, h);
+              }
+          for (int i = 0; i < 6; ++i) for (int j = 0; j < npl; ++j) cprev[i][j] = ccur[i][j];
+        }
+      }
       double s = fmax(0.0, hmax + 1e-2);
       W(k, I_S) = s;
       gmax = fmax(gmax, fabs(2 * cfg.S * s));
@@ -233,6 +261,7 @@ struct Inst {
     D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
     D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
     J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0;
+    J(J_FLAGS) = P.flags ? (int)P.flags[b] : 0;
   }
 
   struct RowAcc {
@@ -240,6 +269,165 @@ struct Inst {
     double csum, be0, be1, zrows, chi, clo, prim, sumz;
     int nz;
   };
+
+  // ------------------------------------------------------------------------------------------
+  // MMPC_MODE_REFERENCE: the rows with stale plane columns (controllers/mpc_wholebody_qref.py:76-89 with the
+  // subject_to inside the j loop).  Row (m, i, j), m >= 1, i < 6, j < npl - 1:
+  //     -max( c_m[i][0..j], c_{m-1}[i][j+1..] ) <= s_m
+  // Thread (instance, k) OWNS the rows of slack s_k (their candidate (t, z), the s_k terms, merit and KKT
+  // bookkeeping and, when the arg-max column belongs to stage k, their pose terms) and ADDS the pose
+  // terms of the rows of slack s_{k+1} whose arg-max column is a stale one, i.e. belongs to x_k: those
+  // couple x_k with v_k = s_{k+1} (Q_BV) in the augmented Riccati form.  Kept out of line: it only
+  // runs in reference mode and needs forward kinematics at three stages.
+  //   phase 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step
+  // The terminal self-collision rows stay on s_N (quirk 3 puts them on s_{N-1}): they can never be active
+  // (the check points are at least 0.058 m > 0.05 m from the end point for every joint configuration,
+  // tests/test_oracle_model.py), so the optimum is the same.
+  struct StaleIO {
+    RowAcc* A; double* bv;                   // phase 0/1: accumulators of stage k; bv[6] = H[pose][v]
+    double theta, logsum; bool ok;           // merit ingredients (phase 1, 2)
+    MinRatio rp, rd; double gphi;            // phase 2
+  };
+  __device__ __forceinline__ void pose_at(int kk, int it, bool cand, double alpha, double (&p)[NP]) const {
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      double v = W(kk, it + I_X + POSE2X[a]);
+      p[a] = cand ? fma(alpha, W2(kk, S_DX + POSE2X[a]), v) : v;
+    }
+  }
+  // plane margins c[i][j] of the six body points at one pose (:78-80)
+  __device__ __forceinline__ void margins(const double (&p)[NP], FK& f, double (&c)[6][MMPC_MAX_PLANES]) const {
+    fk_eval(p[2], p[3], p[4], p[5], f);
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+      Point pt; point_eval(p[0], p[1], f, BODY[i], pt);
+      for (int j = 0; j < npl; ++j) {
+        double n0 = D(D_PL + 6 * j + 3), n1 = D(D_PL + 6 * j + 4), n2 = D(D_PL + 6 * j + 5), e = cfg.obstacle_expand_dist;
+        double off = n0 * (D(D_PL + 6 * j + 0) - e * n0) + n1 * (D(D_PL + 6 * j + 1) - e * n1) + n2 * (D(D_PL + 6 * j + 2) - e * n2);
+        c[i][j] = off - (n0 * pt.P[0] + n1 * pt.P[1] + n2 * pt.P[2]);
+      }
+    }
+  }
+  // arg-max column of row (i, j) built from the margins of stage m (columns <= j) and m-1 (columns > j)
+  __device__ __forceinline__ double stale_max(const double (&cm)[6][MMPC_MAX_PLANES], const double (&cm1)[6][MMPC_MAX_PLANES],
+                                              int i, int j, int& best) const {
+    double cb = 0; best = 0;
+    for (int jj = 0; jj < npl; ++jj) {
+      double c = jj <= j ? cm[i][jj] : cm1[i][jj];
+      bool take = (jj == 0) || (npl == 2 ? !(cb > c) : (c > cb));  // if_else(c0 > c1, c0, c1) :85 ; mmax :87
+      if (take) { cb = c; best = jj; }
+    }
+    return -cb;
+  }
+  __device__ __noinline__ void stale_rows(int k, int phase, StaleIO& io) const {
+    if (npl < 2) return;
+    const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
+    const bool cand = phase == 1;
+    const double mu = D(D_MU), alpha = cand ? D(D_ALPHA) : 0.0, ad = cand ? D(D_AD) : 0.0;
+    const int nst = cfg.n_pl - 1, r0 = nobs + 10;
+    double pk[NP], pm[NP], pn[NP];
+    double ck[6][MMPC_MAX_PLANES], cm[6][MMPC_MAX_PLANES], cn[6][MMPC_MAX_PLANES];
+    FK fk, fm, fn;
+    pose_at(k, it, cand, alpha, pk); margins(pk, fk, ck);
+    if (k >= 1) { pose_at(k - 1, it, cand, alpha, pm); margins(pm, fm, cm); }
+    if (k < N && phase != 2) { pose_at(k + 1, it, cand, alpha, pn); margins(pn, fn, cn); }
+    const double s_k = cand ? fma(alpha, W2(k, S_DS), W(k, it + I_S)) : W(k, it + I_S);
+    // ---- rows of slack s_k (owned) ----
+    if (k >= 1) {
+      double dpk[NP], dpm[NP], dsk = 0;
+      if (phase == 2) {
+#pragma unroll
+        for (int a = 0; a < NP; ++a) { dpk[a] = W2(k, S_DX + POSE2X[a]); dpm[a] = W2(k - 1, S_DX + POSE2X[a]); }
+        dsk = W2(k, S_DS);
+      }
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < npl - 1; ++j) {
+          const int r = r0 + i * nst + j;
+          int jb; const double h = stale_max(ck, cm, i, j, jb);
+          const bool here = jb <= j;  // the arg-max column belongs to stage k
+          const double (&pp)[NP] = here ? pk : pm;
+          const FK& ff = here ? fk : fm;
+          Point pt; point_eval(pp[0], pp[1], ff, BODY[i], pt);
+          const double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)};
+          double g[NP]; point_grad(ff, pt, n, g);  // grad h = +g (at the arg-max stage)
+          double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
+          if (phase == 2) {
+            double gd_ = 0;
+#pragma unroll
+            for (int a = 0; a < NP; ++a) gd_ = fma(g[a], here ? dpk[a] : dpm[a], gd_);
+            double res = h - s_k + t, dtv = -res - (gd_ - dsk);
+            W2(k, S_DT + r) = dtv;
+            double itv = rcp(t), dz = (mu - z * (t + dtv)) * itv;
+            io.theta += fabs(res); io.gphi -= mu * dtv * itv; io.logsum += log(t);
+            if (dtv < 0) io.rp.add(t, -dtv);
+            if (dz < 0) io.rd.add(z, -dz);
+            continue;
+          }
+          double it_;
+          if (cand) {
+            double dtv = W2(k, S_DT + r);
+            double tt = fmax(fma(alpha, dtv, t), s_k - h);
+            double dz = (mu - z * (t + dtv)) * rcp(t);
+            it_ = rcp(tt);
+            z = zclamp(z + ad * dz, mu, it_);
+            W(k, jt + I_T + r) = tt; W(k, jt + I_T + R + r) = z;
+            t = tt;
+            if (tt <= 0) io.ok = false; else io.logsum += log(tt);
+          } else it_ = 1.0 / t;
+          const double res = h - s_k + t;
+          io.theta += fabs(res);
+          RowAcc& A = *io.A;
+          A.prim = fmax(A.prim, fabs(res));
+          const double zt = z * t;
+          A.chi = fmax(A.chi, zt); A.clo = fmin(A.clo, zt); A.sumz += z; A.zrows += z; A.nz++;
+          const double sig = z * it_;
+          A.csum += sig; A.be0 += sig * res; A.be1 += it_;
+          if (here) {
+#pragma unroll
+            for (int a = 0; a < NP; ++a)
+#pragma unroll
+              for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += sig * g[a] * g[c];
+            point_hess_acc(ff, pt, n, z, A.H);
+            const double cb = sig * res;
+#pragma unroll
+            for (int a = 0; a < NP; ++a) { A.a[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
+          }
+        }
+    }
+    // ---- rows of slack s_{k+1} whose arg-max column belongs to x_k: pose terms and H[pose][v] of stage k ----
+    if (k < N && phase != 2) {
+      const double s_n = cand ? fma(alpha, W2(k + 1, S_DS), W(k + 1, it + I_S)) : W(k + 1, it + I_S);
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < npl - 1; ++j) {
+          const int r = r0 + i * nst + j;
+          int jb; const double h = stale_max(cn, ck, i, j, jb);
+          if (jb <= j) continue;  // belongs to stage k+1: its owner handles it
+          Point pt; point_eval(pk[0], pk[1], fk, BODY[i], pt);
+          const double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)};
+          double g[NP]; point_grad(fk, pt, n, g);
+          double t = W(k + 1, it + I_T + r), z = W(k + 1, it + I_T + R + r), it_;
+          if (cand) {  // the owner's candidate, recomputed with the same arithmetic
+            double dtv = W2(k + 1, S_DT + r);
+            double tt = fmax(fma(alpha, dtv, t), s_n - h);
+            double dz = (mu - z * (t + dtv)) * rcp(t);
+            it_ = rcp(tt);
+            z = zclamp(z + ad * dz, mu, it_);
+            t = tt;
+          } else it_ = 1.0 / t;
+          const double res = h - s_n + t, sig = z * it_, cb = sig * res;
+          RowAcc& A = *io.A;
+#pragma unroll
+          for (int a = 0; a < NP; ++a)
+#pragma unroll
+            for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += sig * g[a] * g[c];
+          point_hess_acc(fk, pt, n, z, A.H);
+#pragma unroll
+          for (int a = 0; a < NP; ++a) { io.bv[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
+        }
+    }
+  }
 
   // bookkeeping of one slack row  h - s + t = 0  with multiplier z
   __device__ __forceinline__ void row_state(int it, int r, int k, double h, double s, double& z, double& it_, double& res, RowAcc& A) const {
@@ -312,6 +500,9 @@ struct Inst {
     } else {
       Qw(k, Q_HPU) = 0; Qw(k, Q_H45) = 0; Qw(k, Q_H35) = 0;
     }
+    const bool teq = term_eq(k);
+    double nu[2] = {0, 0};
+    if (teq) { nu[0] = W(0, it + I_LAM + 0); nu[1] = W(0, it + I_LAM + 1); }
     // cost and boxes -- :192-205, :240-245.  Pose components seed the row accumulators, the
     // others are final here.
 #pragma unroll
@@ -331,6 +522,11 @@ struct Inst {
           Hd += z * id; gB += id; st += z;
           A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
         }
+      }
+      if (i < 2 && teq) {  // terminal equality row  x_N[i] - xref_N[i] = 0  with multiplier nu[i]
+        double cq = x[i] - W2(k, IN_XREF + i);
+        Hd += 1.0 / MMPC_DELTA_C; gA += nu[i] + cq / MMPC_DELTA_C; st += nu[i];
+        A.prim = fmax(A.prim, fabs(cq)); sum_lam += fabs(nu[i]); n_eq += 1;
       }
       if (i < 3 || i >= 6) {
         const int a = (i < 3) ? i : i - 3;
@@ -416,6 +612,11 @@ struct Inst {
         for (int a = 0; a < NP; ++a) { A.a[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
       }
     }
+    double bv[NP] = {0, 0, 0, 0, 0, 0};
+    if (cfg.mode == MMPC_MODE_REFERENCE) {
+      StaleIO io; io.A = &A; io.bv = bv; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp.init(); io.rd.init();
+      stale_rows(k, 0, io);
+    }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
     double S2 = 2 * os * cfg.S;
     Qw(k, Q_C) = S2 + A.csum;
@@ -424,7 +625,7 @@ struct Inst {
     Qw(k, Q_HVV) = 0; Qw(k, Q_GA + SGY_V) = 0; Qw(k, Q_GB + SGY_V) = 0;
 #pragma unroll
     for (int a = 0; a < NP; ++a) {
-      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = 0;
+      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = bv[a];
       Qw(k, Q_GA + POSE2X[a]) = A.gA[a]; Qw(k, Q_GB + POSE2X[a]) = A.gB[a];
       if (k >= 1) es = fmax(es, fabs(A.st[a]));
     }
@@ -712,6 +913,13 @@ struct Inst {
         W2(k + 1, S_LAMN + i) = v;
       }
     }
+    if (term_eq(N)) {  // Newton target of the terminal-equality multipliers
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        double cq = W(N, it + I_X + i) - W2(N, IN_XREF + i);
+        W2(0, S_LAMN + i) = W(0, it + I_LAM + i) + (dxv[i] + cq) / MMPC_DELTA_C;
+      }
+    }
   }
 
   // results: sol.value(U/X/s/cost) :317,:329-330
@@ -849,6 +1057,7 @@ struct Inst {
 #pragma unroll
       for (int i = 0; i < NX; ++i) theta += fabs(W2(k, S_DFC + i));
     }
+    if (term_eq(k)) theta += fabs(x[0] - W2(k, IN_XREF + 0)) + fabs(x[1] - W2(k, IN_XREF + 1));
     FK f; f.cp = W2(k, S_FK + 0); f.sp = W2(k, S_FK + 1);
 #pragma unroll
     for (int q = 0; q < 3; ++q) { f.vr[q] = W2(k, S_FK + 2 + q); f.vh[q] = W2(k, S_FK + 5 + q); }
@@ -892,8 +1101,14 @@ struct Inst {
         row_step(nobs + 4 + i, h, gd_);
       }
     }
+    double log_extra = 0;
+    if (cfg.mode == MMPC_MODE_REFERENCE) {
+      StaleIO io; io.A = nullptr; io.bv = nullptr; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp = rp; io.rd = rd;
+      stale_rows(k, 2, io);
+      theta += io.theta; gphi += io.gphi; log_extra = io.logsum; rp = io.rp; rd = io.rd;
+    }
     W2(k, S_PART + 0) = rp.value(tau); W2(k, S_PART + 1) = rd.value(tau); W2(k, S_PART + 2) = gphi; W2(k, S_PART + 3) = theta;
-    W2(k, S_PART + 4) = fsum; W2(k, S_PART + 5) = lp.value();
+    W2(k, S_PART + 4) = fsum; W2(k, S_PART + 5) = lp.value() + log_extra;
   }
 
   // Stage k of the results of an instance that left the solve in this round (state ST_FINISH):
@@ -1144,6 +1359,16 @@ struct Inst {
       A.chi = fmax(A.chi, z * d); A.clo = fmin(A.clo, z * d); A.sumz += z; A.nz++;
       return z;
     };
+    const bool teq = term_eq(k);
+    double nu[2] = {0, 0};
+    if (teq) {  // candidate multipliers of the terminal equality
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        double no = W(0, it + I_LAM + i);
+        nu[i] = no + alpha * (W2(0, S_LAMN + i) - no);
+        W(0, jt + I_LAM + i) = nu[i];
+      }
+    }
     // cost and boxes -- :192-205, :240-245
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
@@ -1162,6 +1387,10 @@ struct Inst {
           double d = hi - x[i], id, z = box(W(k, it + I_ZXU + i), hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
           Hd += z * id; gB += id; st += z;
         }
+      }
+      if (i < 2 && teq) {  // terminal equality row  x_N[i] - xref_N[i] = 0  with multiplier nu[i]
+        Hd += 1.0 / MMPC_DELTA_C; gA += nu[i] + e / MMPC_DELTA_C; st += nu[i];
+        A.prim = fmax(A.prim, fabs(e)); theta += fabs(e); sum_lam += fabs(nu[i]); n_eq += 1;
       }
       if (i < 3 || i >= 6) {
         const int a = (i < 3) ? i : i - 3;
@@ -1266,6 +1495,12 @@ struct Inst {
         for (int a = 0; a < NP; ++a) { A.a[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
       }
     }
+    double bv[NP] = {0, 0, 0, 0, 0, 0}, log_extra = 0;
+    if (cfg.mode == MMPC_MODE_REFERENCE) {
+      StaleIO io; io.A = &A; io.bv = bv; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp.init(); io.rd.init();
+      stale_rows(k, 1, io);
+      theta += io.theta; log_extra = io.logsum; ok = ok && io.ok;
+    }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
     double S2 = 2 * os * cfg.S;
     Qw(k, Q_C) = S2 + A.csum;
@@ -1274,7 +1509,7 @@ struct Inst {
     Qw(k, Q_HVV) = 0; Qw(k, Q_GA + SGY_V) = 0; Qw(k, Q_GB + SGY_V) = 0;
 #pragma unroll
     for (int a = 0; a < NP; ++a) {
-      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = 0;
+      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = bv[a];
       Qw(k, Q_GA + POSE2X[a]) = A.gA[a]; Qw(k, Q_GB + POSE2X[a]) = A.gB[a];
       if (k >= 1) es = fmax(es, fabs(A.st[a]));
     }
@@ -1284,7 +1519,7 @@ struct Inst {
     W2(k, S_PART + 0) = es; W2(k, S_PART + 1) = A.prim; W2(k, S_PART + 2) = A.chi; W2(k, S_PART + 3) = A.clo;
     W2(k, S_PART + 4) = sum_lam; W2(k, S_PART + 5) = A.sumz; W2(k, S_PART + 6) = (double)A.nz; W2(k, S_PART + 7) = (double)n_eq;
     bool fin = ok && (fsum == fsum) && (theta == theta);
-    W2(k, S_PART + PT_MERIT + 0) = theta; W2(k, S_PART + PT_MERIT + 1) = fsum; W2(k, S_PART + PT_MERIT + 2) = fin ? lp.value() : 0.0;
+    W2(k, S_PART + PT_MERIT + 0) = theta; W2(k, S_PART + PT_MERIT + 1) = fsum; W2(k, S_PART + PT_MERIT + 2) = fin ? lp.value() + log_extra : 0.0;
     W2(k, S_PART + PT_MERIT + 3) = fin ? 1.0 : 0.0;
   }
 

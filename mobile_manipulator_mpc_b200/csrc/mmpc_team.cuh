@@ -349,6 +349,11 @@ struct Team {
       ro_issue(k + 4, it);
     }
     async_wait<0>();
+    if (c < 2 && S.term_eq(N)) {  // Newton target of the terminal-equality multipliers
+      double cq = S.W(N, it + I_X + c) - S.W2(N, IN_XREF + c);
+      double dxc = c == 0 ? dxv[0] : dxv[1];
+      S.W2(0, S_LAMN + c) = S.W(0, it + I_LAM + c) + (dxc + cq) / MMPC_DELTA_C;
+    }
   }
 
   // KKT reduction, convergence test, barrier update, factorisation with inertia correction, roll-out.

@@ -176,3 +176,16 @@ def manipulate_instance(N=20, dt=0.1, q_target=(0.12261333, -1.36948989, 3.02634
                 u_last=np.zeros((1, N, 5)), circles=DEMO_CIRCLES[None].copy(), planes=planes[None].copy(),
                 n_pl_inst=np.full(1, 3, np.int32),
                 Qd=np.array([500, 500, 500, 0, 0, 1, 1, 1, 1.0]))
+
+
+def approach_instance(N=20, dt=0.1):
+    """An 'approach'-phase instance (interface_wholebody_qref.py:155-167): scenario 1, the base within
+    2 m of its goal (5, 5) and still moving, reference window = the tail of the global plan (last row
+    repeated), and the one-time terminal equality X[N,:2] == X_ref[N,:2] switched on (flags bit 0)."""
+    x_start, tgt, planes = demo_scenario(1)
+    ref, uref = global_plan_2d(x_start, base_target(x_start, tgt), 5, dt)
+    x = np.array([3.7, 3.9, 0.6, 0.9, 0.8, 0.1, -PI / 4, -PI, PI])
+    xr, ur = local_window(ref, uref, x, [0, 1], N)
+    return dict(N=N, dt=dt, n_obs=3, n_pl=3, obs_per_stage=0, x_init=x[None], x_ref=xr[None], u_ref=ur[None],
+                u_last=np.zeros((1, N, 5)), circles=DEMO_CIRCLES[None].copy(), planes=planes[None].copy(),
+                n_pl_inst=np.full(1, 3, np.int32), flags=np.ones(1, np.uint8))

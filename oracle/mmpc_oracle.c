@@ -47,6 +47,7 @@ int mmpc_oracle_verbose = 0;
 #define IU 10  /* index of u0 in y */
 #define IV 15  /* index of v in y */
 #define NP 6   /* pose variables x y psi q1 q2 q3 */
+#define DELTA_C 1e-6 /* IPOPT's delta_c: regularisation of the terminal-equality block of the KKT matrix */
 
 static const int POSE2X[NP] = {0, 1, 2, 6, 7, 8};
 
@@ -194,6 +195,7 @@ typedef struct {
   int circ_stride; /* doubles between stages of the circle table (0 = static) */
   unsigned flags;
   double x0[NX];
+  double nu[2], nun[2]; /* multipliers of the terminal xy equality (flags bit 0; interface_wholebody_qref.py:167) and their Newton target */
   double ulo[64][NU], uhi[64][NU]; /* merged u box (ulim and dulim about u_last), filled per stage */
   /* iterate */
   double *x, *u, *s, *lam;       /* x[(N+1)*9], u[N*5], s[N+1], lam[(N+1)*9] */
@@ -320,6 +322,8 @@ static Merit merit_eval(const Work* w, const double* x, const double* u, const d
       if (is_fin(lo)) { if (v - lo <= 0) mt.ok = 0; else mt.logsum += log(v - lo); }
       if (is_fin(hi)) { if (hi - v <= 0) mt.ok = 0; else mt.logsum += log(hi - v); }
     }
+  if (w->flags & 1)
+    for (int i = 0; i < 2; ++i) mt.theta += fabs(x[N * NX + i] - w->xref[N * NX + i]);
   for (int m = 0; m <= N; ++m)
     for (int r = 0; r < w->nrow[m]; ++r) {
       int kst, emb; double tt = t[m * w->rmax + r];
@@ -407,6 +411,15 @@ static void evaluate(Work* w, double mu, KktParts* kp) {
           kp->e_comp_hi = fmax(kp->e_comp_hi, zz * d); kp->e_comp_lo = fmin(kp->e_comp_lo, zz * d); kp->sum_z += zz; kp->n_z++; }
       }
   }
+  /* terminal equality (x_N, y_N) = (xref_N[0], xref_N[1]):  d nu = (dx + c) / delta_c */
+  if (w->flags & 1)
+    for (int i = 0; i < 2; ++i) {
+      double cq = XK(w, N)[i] - w->xref[N * NX + i];
+      w->H[(size_t)N * NY * NY + i * NY + i] += 1.0 / DELTA_C;
+      w->g[N * NY + i] += w->nu[i] + cq / DELTA_C;
+      stat[N * NY + i] += w->nu[i];
+      kp->e_prim = fmax(kp->e_prim, fabs(cq)); kp->sum_lam += fabs(w->nu[i]); kp->n_all += 1;
+    }
   /* dynamics: defects, second-order terms, multiplier terms of the stationarity residual */
   for (int k = 0; k < N; ++k) {
     double A[NX][NX], B[NX][NU], xn[NX];
@@ -568,6 +581,9 @@ static int riccati(Work* w, double reg) {
     for (int i = 0; i < NX; ++i) { double s = pn[i]; for (int q = 0; q < NXA; ++q) s += Pn[i * NXA + q] * dxa[q]; w->lamn[(k + 1) * NX + i] = s; }
   }
   w->ds[N] = dxa[IS];
+  if (w->flags & 1)
+    for (int i = 0; i < 2; ++i)
+      w->nun[i] = w->nu[i] + (dxa[i] + XK(w, N)[i] - w->xref[N * NX + i]) / DELTA_C;
   return 0;
 }
 
@@ -768,6 +784,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     memcpy(w->x, xt, sizeof(double) * (N + 1) * NX); memcpy(w->u, ut, sizeof(double) * N * NU);
     memcpy(w->s, st, sizeof(double) * (N + 1)); memcpy(w->t, tt, sizeof(double) * nr);
     for (int i = NX; i < (N + 1) * NX; ++i) w->lam[i] += alpha * (w->lamn[i] - w->lam[i]);
+    for (int i = 0; i < 2; ++i) w->nu[i] += alpha * (w->nun[i] - w->nu[i]);
     const double ks = 1e10;
 #define ZUPD(zv, dzv, dist) do { double zn = (zv) + ad * (dzv); double dd = (dist); zn = fmax(fmin(zn, ks * mu / dd), mu / (ks * dd)); (zv) = zn; } while (0)
     for (size_t i = 0; i < nr; ++i) if (w->t[i] > 0) ZUPD(w->z[i], w->dz[i], w->t[i]);

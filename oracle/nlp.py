@@ -17,7 +17,7 @@ from . import model as M
 
 class NLP:
     def __init__(self, N, dt, x_init, x_ref, u_ref, u_last, circles, planes, mode="reference",
-                 Qd=None, Pd=None, Rd=None, Wd=None, S=1e5, ulim=None, xlim=None, dulim=None):
+                 Qd=None, Pd=None, Rd=None, Wd=None, S=1e5, ulim=None, xlim=None, dulim=None, terminal_xy_eq=False):
         pi, inf = np.pi, np.inf
         self.N, self.dt = N, dt
         self.Qd = np.array([25, 25, 0, 0, 0, 5, 5, 5, 5.0]) if Qd is None else np.asarray(Qd, float)   # :12
@@ -36,6 +36,7 @@ class NLP:
         self.circles = circles if circles.ndim == 3 else np.broadcast_to(circles, (N + 1,) + circles.shape)
         self.planes = [(np.asarray(p[:3], float), np.asarray(p[3:], float)) for p in planes]
         self.mode = mode
+        self.terminal_xy_eq = bool(terminal_xy_eq)   # interface_wholebody_qref.py:167
         self.nw = 9 * N + 5 * N + N + 1
 
     # -- packing ---------------------------------------------------------------------------
@@ -75,7 +76,10 @@ class NLP:
     # -- equalities :180 ------------------------------------------------------------------------
     def eq(self, w):
         X, U, _ = self.unpack(w)
-        return (M.f_kinematics(X[:-1], U, self.dt) - X[1:]).ravel()
+        e = (M.f_kinematics(X[:-1], U, self.dt) - X[1:]).ravel()
+        if self.terminal_xy_eq:   # opti.subject_to(X[N, :2] == X_ref[N, :2])  interface_wholebody_qref.py:167
+            e = np.concatenate([e, X[self.N, :2] - self.x_ref[self.N, :2]])
+        return e
 
     # -- inequalities, all as g(w) <= 0 -----------------------------------------------------------
     def ineq(self, w, with_boxes=True):
@@ -158,5 +162,7 @@ def from_batch(batch, b=0, mode="reference"):
     kw = {}
     if "Qd" in batch:
         kw["Qd"] = batch["Qd"]; kw["Pd"] = batch.get("Pd", batch["Qd"])
+    if batch.get("flags") is not None:
+        kw["terminal_xy_eq"] = bool(int(batch["flags"][b]) & 1)
     return NLP(batch["N"], batch["dt"], batch["x_init"][b], batch["x_ref"][b], batch["u_ref"][b], batch["u_last"][b],
                circ, batch["planes"][b][:npl], mode=mode, **kw)

@@ -9,6 +9,7 @@ from oracle import solver as osolver
 
 print(torch.cuda.get_device_name(0))
 KERNELS = sys.argv[1].split(",") if len(sys.argv) > 1 else ["lane", "warp"]
+MODE = 0 if (len(sys.argv) > 3 and sys.argv[3] == "reference") else 1
 CASES = ((1, 1, 1), (2, 4096, 256), (3, 8192, 256), (3, 65536, 64), (5, 2048, 32))
 if len(sys.argv) > 2 and sys.argv[2] == "quick":
     CASES = ((1, 1, 1), (3, 8192, 128), (3, 65536, 32))
@@ -16,7 +17,7 @@ for kern in KERNELS:
     for cid, B, nchk in CASES:
         b = scenarios.make_batch(cid, B)
         S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B,
-                        obs_per_stage=b["obs_per_stage"], kernel=kern)
+                        obs_per_stage=b["obs_per_stage"], kernel=kern, mode=MODE)
         print("kernel", kern, "config", cid, "B", B, S.occupancy(), flush=True)
         t = time.time(); o = S.solve_host(b); th = time.time() - t
         t = time.time(); o = S.solve_host(b); th2 = time.time() - t
@@ -32,7 +33,7 @@ for kern in KERNELS:
         conv = int((out["status"] == 0).sum())
         print("  device path %.2f ms -> %.0f converged solves/s" % (ms, conv / ms * 1e3), flush=True)
         sub = {k: (v[:nchk] if isinstance(v, np.ndarray) else v) for k, v in b.items()}
-        oc = osolver.solve(sub, mode=1, threads=8)
+        oc = osolver.solve(sub, mode=MODE, threads=8)
         both = (oc["status"] == 0) & (o["status"][:nchk] == 0)
         rel = np.abs(oc["cost"] - o["cost"][:nchk]) / np.abs(oc["cost"])
         du0 = np.abs(oc["U"][:, 0] - o["U"][:nchk, 0]).max(axis=1)

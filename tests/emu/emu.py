@@ -32,8 +32,10 @@ def solve(batch, cfg, kernel="warp"):
     arrs = {k: f(batch.get(k)) for k in ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")}
     npl = batch.get("n_pl_inst")
     npl = None if npl is None else np.ascontiguousarray(npl, dtype=np.int32)
+    flags = batch.get("flags")
+    flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
     bi = _abi.MmpcBatchIn(*[_abi.ptr(arrs[k]) for k in ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")],
-                          _abi.ptr(npl), None)
+                          _abi.ptr(npl), _abi.ptr(flags))
     out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
                kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])

@@ -11,6 +11,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __global__
+#define __noinline__
 #define MMPC_LSTR 1
 
 namespace mmpc {

@@ -27,6 +27,7 @@ def instances():
     yield "cfg1_N10_reference", scenarios.make_batch(1, 1, N=10), "reference"
     yield "manip_N20_reference", scenarios.manipulate_instance(), "reference"
     yield "manip_N20_clean", scenarios.manipulate_instance(), "clean"
+    yield "approach_N20_clean", scenarios.approach_instance(), "clean"   # terminal xy equality (flags bit 0)
     b2 = scenarios.make_batch(2, 4)
     for i in range(2):
         one = {k: (v[i:i + 1] if isinstance(v, np.ndarray) else v) for k, v in b2.items()}

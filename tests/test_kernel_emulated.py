@@ -49,3 +49,19 @@ def test_staged_rounds_and_list_compaction():
     assert a["rounds"] >= a["iters"].max() + 1 and a["rounds"] <= a["iters"].max() + 60
     assert (a["iters"] == t["iters"]).all()
     assert np.abs(a["U"] - t["U"]).max() < 1e-8 and np.abs(a["cost"] - t["cost"]).max() < 1e-8 * np.abs(a["cost"]).max()
+
+
+@pytest.mark.parametrize("kernel", ["staged", "staged_thread", "staged_fat"])
+def test_terminal_xy_equality_flag(kernel):
+    """flags bit 0 = opti.subject_to(X[N,:2] == X_ref[N,:2]) (interface_wholebody_qref.py:167)."""
+    b = scenarios.approach_instance()
+    cfg = solver.config_from_batch(b, mode=_abi.MODE_CLEAN)
+    o = solver.solve(b, cfg=cfg, threads=1)
+    e = emu.solve(b, cfg, kernel=kernel)
+    assert o["status"][0] == 0 and e["status"][0] == 0
+    assert np.abs(e["X"][0, -1, :2] - b["x_ref"][0, -1, :2]).max() < 1e-8          # the equality holds
+    assert abs(e["cost"][0] - o["cost"][0]) <= 1e-9 * abs(o["cost"][0])
+    assert np.abs(e["U"][0, 0] - o["U"][0, 0]).max() < 1e-7
+    free = dict(b); free["flags"] = None                                            # and it binds: without it x_N differs
+    f = emu.solve(free, cfg, kernel=kernel)
+    assert np.abs(f["X"][0, -1, :2] - b["x_ref"][0, -1, :2]).max() > 1e-3
