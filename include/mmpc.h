@@ -168,6 +168,14 @@ int mmpc_shift(MmpcHandle* h, int32_t B, const double* U, double* u_guess, void*
 int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const double* u0, double* x_next,
                     void* stream);
 
+/* Reference window on device: calcLocalRefTraj (interface_wholebody_qref.py:353-396).  For each instance the
+ * nearest row i* of its global reference x_glob ([M][9], or [B][M][9] when shared_ref == 0) by Euclidean
+ * distance over the state indices set in idx_mask (bit i = state i; the Interface uses {0,1} while moving :188
+ * and {6,7,8} while manipulating :226), then x_ref[b] = rows [i*, i*+N] with the last row repeated (:385-389);
+ * u_ref[b] = the same window of u_glob ([M-1][5] / [B][M-1][5]; NULL -> zeros, :266).  i_star may be NULL. */
+int mmpc_window(MmpcHandle* h, int32_t B, int32_t M, int32_t idx_mask, int32_t shared_ref, const double* x,
+                const double* x_glob, const double* u_glob, double* x_ref, double* u_ref, int32_t* i_star, void* stream);
+
 /* Phases of the staged solver (one kernel each per round; COMPACT runs twice per round). */
 enum { MMPC_PHASE_COMPACT = 0, MMPC_PHASE_EVAL = 1, MMPC_PHASE_SOLVE = 2, MMPC_PHASE_STEP = 3, MMPC_PHASE_CTRL_STEP = 4,
        MMPC_PHASE_TRIAL = 5, MMPC_PHASE_CTRL_TRIAL = 6, MMPC_PHASE_INIT = 7, MMPC_NPHASE = 8 };

@@ -54,6 +54,7 @@ def lib():
     L.mmpc_set_weights.argtypes = [vp, dp, dp, dp, dp, C.c_double]
     L.mmpc_set_kernel.argtypes = [vp, i32]
     L.mmpc_set_profile.argtypes = [vp, i32]
+    L.mmpc_window.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mmpc_workspace_bytes.argtypes = [vp, C.POINTER(C.c_int64)]
     L.mmpc_phase_times.argtypes = [vp, dp, C.POINTER(C.c_int64), C.POINTER(i32)]
     L.mmpc_solve.argtypes = [vp, i32, C.POINTER(_abi.MmpcBatchIn), C.POINTER(_abi.MmpcBatchOut), vp]
@@ -80,4 +81,4 @@ def check(rc):
 
 EXPORTS = ("mmpc_version", "mmpc_error_string", "mmpc_default_config", "mmpc_create", "mmpc_destroy",
            "mmpc_set_weights", "mmpc_set_kernel", "mmpc_set_profile", "mmpc_phase_times", "mmpc_workspace_bytes", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
-           "mmpc_plant_step", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")
+           "mmpc_plant_step", "mmpc_window", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")

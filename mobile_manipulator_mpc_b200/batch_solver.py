@@ -225,6 +225,21 @@ class BatchSolver:
         check(lib().mmpc_shift(self._h, int(U.shape[0]), C.c_void_p(U.data_ptr()), C.c_void_p(ug.data_ptr()), stream))
         return ug
 
+    def window(self, x, x_glob, u_glob=None, idx=(0, 1), want_index=False):
+        """calcLocalRefTraj on device: x [B,9], x_glob [M,9] (shared) or [B,M,9]; returns x_ref [B,N+1,9], u_ref [B,N,5]."""
+        import torch
+        B, N = int(x.shape[0]), self.cfg.N
+        shared = x_glob.dim() == 2
+        M = int(x_glob.shape[-2])
+        xr = torch.empty((B, N + 1, 9), dtype=torch.float64, device=x.device)
+        ur = torch.empty((B, N, 5), dtype=torch.float64, device=x.device)
+        ist = torch.empty(B, dtype=torch.int32, device=x.device) if want_index else None
+        mask = sum(1 << int(i) for i in idx)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        check(lib().mmpc_window(self._h, B, M, mask, int(shared), p(x), p(x_glob), p(u_glob), p(xr), p(ur), p(ist), stream))
+        return (xr, ur, ist) if want_index else (xr, ur)
+
     def plant_step(self, x, u0):
         import torch
         xn = torch.empty_like(x)

@@ -8,7 +8,8 @@ What the caller (interface_wholebody_qref.py) touches and what it gets here:
   angleDiff(a, b) -> float                                 :92-117
   .N .dt .f_dynamics .robot_model .obstacle_list .x_guess .u_latest .ulim .xlim .dulim .base_radius
   .opti.subject_to(.X[N, :2] == .X_ref[N, :2])             interface_wholebody_qref.py:167 (shim)
-Extra (keyword-only): batch, device, mode, and ``solve_batch`` for B instances at once.
+Extra (keyword-only): batch, device, mode ("reference" = bug-for-bug NLP, the default; "clean" = stage-separable),
+and ``solve_batch`` for B instances at once.
 """
 import numpy as np
 
@@ -75,7 +76,7 @@ class MPCWholeBody:
                  xlim=np.array([[-100, -100, -np.inf, -2, -2, -PI, -PI / 2, -PI, 0],
                                 [100, 100, np.inf, 2, 2, PI, PI / 2, 0, 3 * PI / 2]]),
                  dulim=np.array([[-np.inf, -np.inf, -0.5, -0.5, -0.5], [np.inf, np.inf, 0.5, 0.5, 0.5]]),
-                 *, batch=1, device=0, mode="clean", verbose=True):
+                 *, batch=1, device=0, mode="reference", verbose=True):
         self.N = N
         self.Q_value, self.R_value, self.P_value, self.S_value, self.W_value = Q, R, P, S, W
         self.dt = robot.dt

