@@ -152,10 +152,27 @@ def run_reference(args):
                                   sample=f"{sample} instances per step, oracle/mmpc_oracle.c over {cores} threads; "
                                          "CasADi/IPOPT not installable in this image"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL's version banner ...)
+    has been sent to stderr by _guard_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -365,7 +382,7 @@ def main():
             line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
                                         sample="first %d instances of rank 0's batch, oracle/mmpc_oracle.c on %d threads, %.1f s"
                                                % (args.cpu_sample, cores, cdt))
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
