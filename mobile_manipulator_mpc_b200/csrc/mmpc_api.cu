@@ -269,6 +269,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   CK(cudaGetLastError());
   h->launches += 1;
   const int LAG = 2, cap = h->sm_count * 16;
+  const bool ref = cfg.mode == MMPC_MODE_REFERENCE;
   long long ub = B;  // upper bound of the active instances (the lists only shrink)
   int r = 0;
   for (;; ++r) {
@@ -283,7 +284,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     staged_compact_kernel<<<1, 1024, 0, st>>>(P, 0, ST_ACTIVE);
     if (!P.fused || r == 0) {  // fused: the trial kernel has already evaluated the accepted point
       MARK(MMPC_PHASE_EVAL);
-      staged_eval_kernel<<<gs, 128, 0, st>>>(P);
+      if (ref) staged_eval_kernel<true><<<gs, 128, 0, st>>>(P); else staged_eval_kernel<false><<<gs, 128, 0, st>>>(P);
     }
     MARK(MMPC_PHASE_SOLVE);
     if (P.team) staged_solve_team_kernel<<<gt, 128, 0, st>>>(P);
@@ -291,14 +292,16 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     MARK(MMPC_PHASE_STEP);
     const bool thin = P.parts && (items + 31) / 32 <= (long long)h->sm_count;  // every tile gets its own SM
     if (thin) staged_parts_kernel<false><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
-    else staged_step_kernel<<<gs, 128, 0, st>>>(P);
+    else if (ref) staged_step_kernel<true><<<gs, 128, 0, st>>>(P);
+    else staged_step_kernel<false><<<gs, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_CTRL_STEP);
     staged_ctrl_step_kernel<<<gi_, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_COMPACT);
     staged_compact_kernel<<<1, 1024, 0, st>>>(P, 1, ST_TRIAL);
     MARK(MMPC_PHASE_TRIAL);
     if (thin) staged_parts_kernel<true><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
-    else staged_trial_kernel<<<gs, 128, 0, st>>>(P);
+    else if (ref) staged_trial_kernel<true><<<gs, 128, 0, st>>>(P);
+    else staged_trial_kernel<false><<<gs, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_CTRL_TRIAL);
     staged_ctrl_trial_kernel<<<gi_, 128, 0, st>>>(P);
     CK(cudaGetLastError());

@@ -133,6 +133,9 @@ struct Inst {
   }
   __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << 5]; }
   __device__ __forceinline__ double& W2(int k, int o) const { return w[(k * STG + B2 + o) << 5]; }
+  // base pointer of a block of fields of stage k (field f of the block is p[f << 5]): with it the field offsets
+  // of the hot kernels are compile-time immediates instead of an index computation per access
+  __device__ __forceinline__ double* stage_ptr(int k, int base) const { return w + ((k * STG + base) << 5); }
   __device__ __forceinline__ double& Qw(int k, int o) const { return P.qp[((long long)k * LS + b) * QS + o]; }
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
   __device__ __forceinline__ double& D(int o) const { return gd[o << 5]; }
@@ -447,6 +450,7 @@ struct Inst {
 
   // ------------------------------------------------------------------------------------------
   // eval (thread per instance and stage): full evaluation of stage k at the current iterate.
+  template <bool REF>
   __device__ void eval(int k) {
     load_npl();
     const int it = J(J_CUR) * ITSZ;
@@ -615,7 +619,7 @@ struct Inst {
       }
     }
     double bv[NP] = {0, 0, 0, 0, 0, 0};
-    if (cfg.mode == MMPC_MODE_REFERENCE) {
+    if (REF) {  // compiled out of the clean-mode kernels: taking &A would force the accumulators into local memory
       StaleIO io; io.A = &A; io.bv = bv; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp.init(); io.rd.init();
       stale_rows(k, 0, io);
     }
@@ -995,10 +999,12 @@ struct Inst {
   // ------------------------------------------------------------------------------------------
   // step (thread per instance and stage): slack / multiplier steps of every row and bound,
   // fraction to the boundary, merit ingredients of the current point.
+  template <bool REF>
   __device__ void step(int k) {
     load_npl();
     const int it = J(J_CUR) * ITSZ;
     prefetch_stage(k, it, false);
+    const double* ci = stage_ptr(k, it); double* c2 = stage_ptr(k, B2);
     const double os = D(D_OS), mu = D(D_MU);
     const double tau = fmax(0.99, 1 - mu);
     MinRatio rp, rd; rp.init(); rd.init();  // fraction to the boundary: primal, dual
@@ -1006,28 +1012,28 @@ struct Inst {
     LogProd lp; lp.init();
     double x[NX], dxv[NX], u[NU], duv[NU];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = W(k, it + I_X + i); dxv[i] = W2(k, S_DX + i); }
-    double s = W(k, it + I_S), dsv = W2(k, S_DS);
+    for (int i = 0; i < NX; ++i) { x[i] = ci[(I_X + i) << 5]; dxv[i] = c2[(S_DX + i) << 5]; }
+    double s = ci[(I_S) << 5], dsv = c2[(S_DS) << 5];
 #pragma unroll
-    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? W(k, it + I_U + a) : 0.0; duv[a] = (k < N) ? W2(k, S_DU + a) : 0.0; }
+    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? ci[(I_U + a) << 5] : 0.0; duv[a] = (k < N) ? c2[(S_DU + a) << 5] : 0.0; }
     double dp[NP];
 #pragma unroll
     for (int a = 0; a < NP; ++a) dp[a] = dxv[POSE2X[a]];
     // cost / boxes
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - W2(k, IN_XREF + i);
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - c2[(IN_XREF + i) << 5];
       fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, id = rcp(d), z = W(k, it + I_ZXL + i), dz = mu * id - z - z * id * dxv[i];
+          double d = x[i] - lo, id = rcp(d), z = ci[(I_ZXL + i) << 5], dz = mu * id - z - z * id * dxv[i];
           gphi -= mu * dxv[i] * id; lp.mul(d);
           if (dxv[i] < 0) rp.add(d, -dxv[i]);
           if (dz < 0) rd.add(z, -dz);
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], id = rcp(d), z = W(k, it + I_ZXU + i), dz = mu * id - z + z * id * dxv[i];
+          double d = hi - x[i], id = rcp(d), z = ci[(I_ZXU + i) << 5], dz = mu * id - z + z * id * dxv[i];
           gphi += mu * dxv[i] * id; lp.mul(d);
           if (dxv[i] > 0) rp.add(d, dxv[i]);
           if (dz < 0) rd.add(z, -dz);
@@ -1040,35 +1046,35 @@ struct Inst {
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - W2(k, IN_UREF + j), dl = u[j] - W2(k, IN_ULAST + j);
+        double e = u[j] - c2[(IN_UREF + j) << 5], dl = u[j] - c2[(IN_ULAST + j) << 5];
         fsum += Rj * e * e + Wj * dl * dl; gphi += (2 * Rj * e + 2 * Wj * dl) * duv[j];
-        double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
+        double lo = c2[(IN_ULO + j) << 5], hi = c2[(IN_UHI + j) << 5];
         if (is_fin(lo)) {
-          double d = u[j] - lo, id = rcp(d), z = W(k, it + I_ZUL + j), dz = mu * id - z - z * id * duv[j];
+          double d = u[j] - lo, id = rcp(d), z = ci[(I_ZUL + j) << 5], dz = mu * id - z - z * id * duv[j];
           gphi -= mu * duv[j] * id; lp.mul(d);
           if (duv[j] < 0) rp.add(d, -duv[j]);
           if (dz < 0) rd.add(z, -dz);
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], id = rcp(d), z = W(k, it + I_ZUU + j), dz = mu * id - z + z * id * duv[j];
+          double d = hi - u[j], id = rcp(d), z = ci[(I_ZUU + j) << 5], dz = mu * id - z + z * id * duv[j];
           gphi += mu * duv[j] * id; lp.mul(d);
           if (duv[j] > 0) rp.add(d, duv[j]);
           if (dz < 0) rd.add(z, -dz);
         }
       }
 #pragma unroll
-      for (int i = 0; i < NX; ++i) theta += fabs(W2(k, S_DFC + i));
+      for (int i = 0; i < NX; ++i) theta += fabs(c2[(S_DFC + i) << 5]);
     }
-    if (term_eq(k)) theta += fabs(x[0] - W2(k, IN_XREF + 0)) + fabs(x[1] - W2(k, IN_XREF + 1));
-    FK f; f.cp = W2(k, S_FK + 0); f.sp = W2(k, S_FK + 1);
+    if (term_eq(k)) theta += fabs(x[0] - c2[(IN_XREF + 0) << 5]) + fabs(x[1] - c2[(IN_XREF + 1) << 5]);
+    FK f; f.cp = c2[(S_FK + 0) << 5]; f.sp = c2[(S_FK + 1) << 5];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { f.vr[q] = W2(k, S_FK + 2 + q); f.vh[q] = W2(k, S_FK + 5 + q); }
+    for (int q = 0; q < 3; ++q) { f.vr[q] = c2[(S_FK + 2 + q) << 5]; f.vh[q] = c2[(S_FK + 5 + q) << 5]; }
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
     auto row_step = [&](int r, double h, double gd_) {
-      double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
+      double t = ci[(I_T + r) << 5], z = ci[(I_T + R + r) << 5];
       double res = h - s + t;
       double dtv = -res - (gd_ - dsv);
-      W2(k, S_DT + r) = dtv;
+      c2[(S_DT + r) << 5] = dtv;
       double itv = rcp(t), dz = (mu - z * (t + dtv)) * itv;
       theta += fabs(res); gphi -= mu * dtv * itv; lp.mul(t);
       if (dtv < 0) rp.add(t, -dtv);
@@ -1104,13 +1110,13 @@ struct Inst {
       }
     }
     double log_extra = 0;
-    if (cfg.mode == MMPC_MODE_REFERENCE) {
+    if (REF) {  // compiled out of the clean-mode kernels: taking &A would force the accumulators into local memory
       StaleIO io; io.A = nullptr; io.bv = nullptr; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp = rp; io.rd = rd;
       stale_rows(k, 2, io);
       theta += io.theta; gphi += io.gphi; log_extra = io.logsum; rp = io.rp; rd = io.rd;
     }
-    W2(k, S_PART + 0) = rp.value(tau); W2(k, S_PART + 1) = rd.value(tau); W2(k, S_PART + 2) = gphi; W2(k, S_PART + 3) = theta;
-    W2(k, S_PART + 4) = fsum; W2(k, S_PART + 5) = lp.value() + log_extra;
+    c2[(S_PART + 0) << 5] = rp.value(tau); c2[(S_PART + 1) << 5] = rd.value(tau); c2[(S_PART + 2) << 5] = gphi; c2[(S_PART + 3) << 5] = theta;
+    c2[(S_PART + 4) << 5] = fsum; c2[(S_PART + 5) << 5] = lp.value() + log_extra;
   }
 
   // Stage k of the results of an instance that left the solve in this round (state ST_FINISH):
@@ -1275,10 +1281,14 @@ struct Inst {
   // is exactly where the next iteration linearises -- the stage QP, defect, FK cache and KKT partials at
   // the candidate, all from registers.  A rejected candidate only wastes the derivative arithmetic: its
   // records are overwritten by the next trial before anything reads them.
+  template <bool REF>
   __device__ void trial_eval(int k) {
     load_npl();
     const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
     const double os = D(D_OS), mu = D(D_MU), alpha = D(D_ALPHA), ad = D(D_AD);
+    const double* ci = stage_ptr(k, it); double* cj = stage_ptr(k, jt); double* c2 = stage_ptr(k, B2);
+    const int k1 = k < N ? k + 1 : k;
+    const double* ni = stage_ptr(k1, it); const double* n2 = stage_ptr(k1, B2);
     prefetch_stage(k, it, true);
     double theta = 0, fsum = 0; bool ok = true;
     LogProd lp; lp.init();
@@ -1291,29 +1301,29 @@ struct Inst {
     double x[NX], u[NU], lam[NX], lam1[NX], xo[NX], dxo[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      xo[i] = W(k, it + I_X + i); dxo[i] = W2(k, S_DX + i);
+      xo[i] = ci[(I_X + i) << 5]; dxo[i] = c2[(S_DX + i) << 5];
       x[i] = fma(alpha, dxo[i], xo[i]);
-      W(k, jt + I_X + i) = x[i];
+      cj[(I_X + i) << 5] = x[i];
       lam[i] = 0;
       if (k >= 1) {
-        double l = W(k, it + I_LAM + i);
-        lam[i] = l + alpha * (W2(k, S_LAMN + i) - l);
-        W(k, jt + I_LAM + i) = lam[i];
+        double l = ci[(I_LAM + i) << 5];
+        lam[i] = l + alpha * (c2[(S_LAMN + i) << 5] - l);
+        cj[(I_LAM + i) << 5] = lam[i];
       }
     }
-    const double s = fma(alpha, W2(k, S_DS), W(k, it + I_S));
-    W(k, jt + I_S) = s;
+    const double s = fma(alpha, c2[(S_DS) << 5], ci[(I_S) << 5]);
+    cj[(I_S) << 5] = s;
     double uo[NU], duo[NU];
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
-      uo[j] = (k < N) ? W(k, it + I_U + j) : 0.0; duo[j] = (k < N) ? W2(k, S_DU + j) : 0.0;
+      uo[j] = (k < N) ? ci[(I_U + j) << 5] : 0.0; duo[j] = (k < N) ? c2[(S_DU + j) << 5] : 0.0;
       u[j] = fma(alpha, duo[j], uo[j]);
-      if (k < N) W(k, jt + I_U + j) = u[j];
+      if (k < N) cj[(I_U + j) << 5] = u[j];
     }
     FK f; fk_eval(x[2], x[6], x[7], x[8], f);
-    W2(k, S_FK + 0) = f.cp; W2(k, S_FK + 1) = f.sp;
+    c2[(S_FK + 0) << 5] = f.cp; c2[(S_FK + 1) << 5] = f.sp;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { W2(k, S_FK + 2 + q) = f.vr[q]; W2(k, S_FK + 5 + q) = f.vh[q]; }
+    for (int q = 0; q < 3; ++q) { c2[(S_FK + 2 + q) << 5] = f.vr[q]; c2[(S_FK + 5 + q) << 5] = f.vh[q]; }
     double es = 0, hpp = 0, sum_lam = 0;
     int n_eq = 0;
     // dynamics :180 at the candidate -- defect and costate terms (A^T lam_{k+1}, B^T lam_{k+1})
@@ -1327,11 +1337,11 @@ struct Inst {
       dyn_f(x, u, dt, f.cp, f.sp, xn);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double l1 = W(k + 1, it + I_LAM + i);
-        lam1[i] = l1 + alpha * (W2(k + 1, S_LAMN + i) - l1);
-        double x1 = fma(alpha, W2(k + 1, S_DX + i), W(k + 1, it + I_X + i));
+        double l1 = ni[(I_LAM + i) << 5];
+        lam1[i] = l1 + alpha * (n2[(S_LAMN + i) << 5] - l1);
+        double x1 = fma(alpha, n2[(S_DX + i) << 5], ni[(I_X + i) << 5]);
         double d = xn[i] - x1;
-        W2(k, S_DFC + i) = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
+        c2[(S_DFC + i) << 5] = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
         theta += fabs(d);
       }
       n_eq = NX;
@@ -1375,18 +1385,18 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-      double e = x[i] - W2(k, IN_XREF + i);
+      double e = x[i] - c2[(IN_XREF + i) << 5];
       fsum += Wx * e * e;
       double gr = 2 * Wx * e;
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, id, z = box(W(k, it + I_ZXL + i), xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
+          double d = x[i] - lo, id, z = box(ci[(I_ZXL + i) << 5], xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], id, z = box(W(k, it + I_ZXU + i), hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
+          double d = hi - x[i], id, z = box(ci[(I_ZXU + i) << 5], hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
           Hd += z * id; gB += id; st += z;
         }
       }
@@ -1408,18 +1418,18 @@ struct Inst {
       double Hd = 0, gA = 0, gB = 0;
       if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - W2(k, IN_UREF + j), dl = u[j] - W2(k, IN_ULAST + j);
+        double e = u[j] - c2[(IN_UREF + j) << 5], dl = u[j] - c2[(IN_ULAST + j) << 5];
         fsum += os * (cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl);
         double gr = 2 * Rj * e + 2 * Wj * dl;
         Hd = 2 * Rj + 2 * Wj; gA = gr;
         double st = gr + stu[j];
-        double lo = W2(k, IN_ULO + j), hi = W2(k, IN_UHI + j);
+        double lo = c2[(IN_ULO + j) << 5], hi = c2[(IN_UHI + j) << 5];
         if (is_fin(lo)) {
-          double d = u[j] - lo, id, z = box(W(k, it + I_ZUL + j), uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
+          double d = u[j] - lo, id, z = box(ci[(I_ZUL + j) << 5], uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], id, z = box(W(k, it + I_ZUU + j), hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
+          double d = hi - u[j], id, z = box(ci[(I_ZUU + j) << 5], hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
           Hd += z * id; gB += id; st += z;
         }
         es = fmax(es, fabs(st));
@@ -1428,13 +1438,13 @@ struct Inst {
     }
     // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
     auto row = [&](int r, double h, double& z, double& it_, double& res) {
-      double t = W(k, it + I_T + r), dtv = W2(k, S_DT + r);
-      z = W(k, it + I_T + R + r);
+      double t = ci[(I_T + r) << 5], dtv = c2[(S_DT + r) << 5];
+      z = ci[(I_T + R + r) << 5];
       double tt = fmax(fma(alpha, dtv, t), s - h);  // slack reset (Nocedal & Wright 19.30)
       double dz = (mu - z * (t + dtv)) * rcp(t);
       it_ = rcp(tt);
       z = zclamp(z + ad * dz, mu, it_);
-      W(k, jt + I_T + r) = tt; W(k, jt + I_T + R + r) = z;
+      cj[(I_T + r) << 5] = tt; cj[(I_T + R + r) << 5] = z;
       res = h - s + tt;
       theta += fabs(res);
       if (tt <= 0) ok = false; else lp.mul(tt);
@@ -1498,7 +1508,7 @@ struct Inst {
       }
     }
     double bv[NP] = {0, 0, 0, 0, 0, 0}, log_extra = 0;
-    if (cfg.mode == MMPC_MODE_REFERENCE) {
+    if (REF) {  // compiled out of the clean-mode kernels: taking &A would force the accumulators into local memory
       StaleIO io; io.A = &A; io.bv = bv; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp.init(); io.rd.init();
       stale_rows(k, 1, io);
       theta += io.theta; log_extra = io.logsum; ok = ok && io.ok;
@@ -1518,11 +1528,11 @@ struct Inst {
 #pragma unroll
     for (int e = 0; e < 21; ++e) Qw(k, Q_HP + e) = A.H[e];
     es = fmax(es, fabs(S2 * s - A.zrows));
-    W2(k, S_PART + 0) = es; W2(k, S_PART + 1) = A.prim; W2(k, S_PART + 2) = A.chi; W2(k, S_PART + 3) = A.clo;
-    W2(k, S_PART + 4) = sum_lam; W2(k, S_PART + 5) = A.sumz; W2(k, S_PART + 6) = (double)A.nz; W2(k, S_PART + 7) = (double)n_eq;
+    c2[(S_PART + 0) << 5] = es; c2[(S_PART + 1) << 5] = A.prim; c2[(S_PART + 2) << 5] = A.chi; c2[(S_PART + 3) << 5] = A.clo;
+    c2[(S_PART + 4) << 5] = sum_lam; c2[(S_PART + 5) << 5] = A.sumz; c2[(S_PART + 6) << 5] = (double)A.nz; c2[(S_PART + 7) << 5] = (double)n_eq;
     bool fin = ok && (fsum == fsum) && (theta == theta);
-    W2(k, S_PART + PT_MERIT + 0) = theta; W2(k, S_PART + PT_MERIT + 1) = fsum; W2(k, S_PART + PT_MERIT + 2) = fin ? lp.value() + log_extra : 0.0;
-    W2(k, S_PART + PT_MERIT + 3) = fin ? 1.0 : 0.0;
+    c2[(S_PART + PT_MERIT + 0) << 5] = theta; c2[(S_PART + PT_MERIT + 1) << 5] = fsum; c2[(S_PART + PT_MERIT + 2) << 5] = fin ? lp.value() + log_extra : 0.0;
+    c2[(S_PART + PT_MERIT + 3) << 5] = fin ? 1.0 : 0.0;
   }
 
   // ctrl_trial (thread per instance): filter acceptance test (Waechter & Biegler 2006, Alg. A
@@ -1584,18 +1594,21 @@ __device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.LS
 
 // ---- phase bodies on list items (shared by the kernels and by tests/emu) -----------------------------
 __device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init(); }
-__device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.eval(k); }
+template <bool REF>
+__device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.template eval<REF>(k); }
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
+template <bool REF>
 __device__ inline void body_step(const SParams& P, int j, int k) {
   Inst S(P, list_E(P)[j]);
   const int st = S.J(J_STATE);
   if (st == ST_FINISH) S.finish_stage(k);
-  else if (st == ST_ACTIVE) S.step(k);
+  else if (st == ST_ACTIVE) S.template step<REF>(k);
 }
 __device__ inline void body_ctrl_step(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.ctrl_step(); }
+template <bool REF>
 __device__ inline void body_trial(const SParams& P, int j, int k) {
   Inst S(P, list_T(P)[j]);
-  if (P.fused) S.trial_eval(k); else S.trial(k);
+  if (P.fused) S.template trial_eval<REF>(k); else S.trial(k);
 }
 __device__ inline void body_ctrl_trial(const SParams& P, int j) { Inst S(P, list_T(P)[j]); S.ctrl_trial(); }
 
@@ -1641,11 +1654,12 @@ __global__ void __launch_bounds__(128) staged_init_kernel(const __grid_constant_
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < P.B) body_init(P, b);
 }
+template <bool REF>
 __global__ void __launch_bounds__(128) staged_eval_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_eval(P, (int)(t % n), (int)(t / n));
+    body_eval<REF>(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
@@ -1658,21 +1672,23 @@ __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant_
 #ifndef MMPC_TRIAL_MINB
 #define MMPC_TRIAL_MINB 3
 #endif
+template <bool REF>
 __global__ void __launch_bounds__(128, MMPC_STEP_MINB) staged_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_step(P, (int)(t % n), (int)(t / n));
+    body_step<REF>(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_step(P, j);
 }
+template <bool REF>
 __global__ void __launch_bounds__(128, MMPC_TRIAL_MINB) staged_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[1];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_trial(P, (int)(t % n), (int)(t / n));
+    body_trial<REF>(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[1];

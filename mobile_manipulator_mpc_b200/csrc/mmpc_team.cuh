@@ -164,9 +164,24 @@ struct Team {
     team_sync();
     bw_issue(N - 2, it);
     int bad = 0;
+    // which neighbour columns this lane's column of P [A B] needs (fixed per lane; only the coefficients change)
+    int s1 = c, s2 = c, s3 = c;
+    switch (c) {
+      case 2: s1 = 3; s2 = 4; break;
+      case 3: s1 = 0; s2 = 4; break;
+      case 4: s1 = 1; s2 = 3; break;
+      case 5: s1 = 2; s2 = 3; s3 = 4; break;
+      case 9: s1 = 3; s2 = 4; break;
+      case 10: s1 = 5; break;
+      case 11: s1 = 6; break;
+      case 12: s1 = 7; break;
+      case 13: s1 = 8; break;
+      default: break;
+    }
     for (int k = N - 1; k >= 0; --k) {
       async_wait<1>(); team_sync();
       const double* q = sm + (k & 1) * BW_SZ;
+      double* rkk = &S.Rw(k, 0);
       const SACoef a = ac_from(q + BW_AC, S.dt);
       double d[9];
 #pragma unroll
@@ -179,19 +194,11 @@ struct Team {
 #pragma unroll
       for (int i = 0; i < 9; ++i) { double g = shfl16(zd, i); Y[i] = Pc[i] + (rhs ? g : 0.0); }  // u lanes: Pc = 0
       // Y += coef * Pxx[:, src]: the columns A and B couple (A = I + sparse, B sparse)
-      int s1 = c, s2 = c, s3 = c; double c1 = 0, c2 = 0, c3 = 0;
-      switch (c) {
-        case 2: s1 = 3; c1 = a.a32; s2 = 4; c2 = a.a42; break;
-        case 3: s1 = 0; c1 = a.dt;  s2 = 4; c2 = a.a43; break;
-        case 4: s1 = 1; c1 = a.dt;  s2 = 3; c2 = a.a34; break;
-        case 5: s1 = 2; c1 = a.dt;  s2 = 3; c2 = a.a35; s3 = 4; c3 = a.a45; break;
-        case 9: s1 = 3; c1 = a.dt * a.cp; s2 = 4; c2 = a.dt * a.sp; break;
-        case 10: s1 = 5; c1 = a.dt; break;
-        case 11: s1 = 6; c1 = a.dt; break;
-        case 12: s1 = 7; c1 = a.dt; break;
-        case 13: s1 = 8; c1 = a.dt; break;
-        default: break;
-      }
+      // coefficients of those columns: A = I + sparse, B sparse
+      const bool dtc = (c >= 3 && c <= 5) || (c >= 10 && c <= 13);
+      const double c1 = c == 2 ? a.a32 : c == 9 ? a.dt * a.cp : dtc ? a.dt : 0.0;
+      const double c2 = c == 2 ? a.a42 : c == 3 ? a.a43 : c == 4 ? a.a34 : c == 5 ? a.a35 : c == 9 ? a.dt * a.sp : 0.0;
+      const double c3 = c == 5 ? a.a45 : 0.0;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         double g1 = shfl16(Pc[i], s1), g2 = shfl16(Pc[i], s2), g3 = shfl16(Pc[i], s3);
@@ -226,7 +233,7 @@ struct Team {
       double l0 = gsn + q[Q_GA + SGY_V] + mu * q[Q_GB + SGY_V];
 #pragma unroll
       for (int p = 0; p < NP; ++p) l0 = fma(an[p], d[POSE2X[p]], l0);
-      const double cv = q[Q_HVV] + cn, icv = 1.0 / cv;
+      const double cv = q[Q_HVV] + cn, icv = rcp(cv);
       bad |= !(cv > 1e-13);
       double wc = 0;
 #pragma unroll
@@ -252,7 +259,7 @@ struct Team {
         for (int r = 0; r < 14; ++r) if (r < 9 || r >= pl) col[r] = shfl16(M[r], pl);
         const double piv = col[pl];
         bad |= !(piv > 1e-13);
-        const double ip = 1.0 / piv;
+        const double ip = rcp(piv);
         const double f = M[pl] * ip;
         yv[p] = f;
 #pragma unroll
@@ -272,17 +279,17 @@ struct Team {
       }
       if (c < 9) {
 #pragma unroll
-        for (int p = 0; p < NU; ++p) S.Rw(k, R_K + p * NX + c) = -kc[p];
+        for (int p = 0; p < NU; ++p) rkk[R_K + p * NX + c] = -kc[p];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) if (r <= c) S.Rw(k, R_P + ssidx(r, c)) = M[r];
+        for (int r = 0; r < 9; ++r) if (r <= c) rkk[R_P + ssidx(r, c)] = M[r];
       } else if (rhs) {
 #pragma unroll
-        for (int p = 0; p < NU; ++p) S.Rw(k, R_KFF + p) = -kc[p];
+        for (int p = 0; p < NU; ++p) rkk[R_KFF + p] = -kc[p];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) S.Rw(k, R_PV + r) = M[r];
-        S.Rw(k, R_CV) = cv; S.Rw(k, R_L0) = l0;
+        for (int r = 0; r < 9; ++r) rkk[R_PV + r] = M[r];
+        rkk[R_CV] = cv; rkk[R_L0] = l0;
       }
-      if (c < 14) S.Rw(k, R_W + c) = wc;
+      if (c < 14) rkk[R_W + c] = wc;
 #pragma unroll
       for (int r = 0; r < 9; ++r) Pc[r] = (c < 9 || rhs) ? M[r] : 0.0;
     }
@@ -307,12 +314,13 @@ struct Team {
       async_wait<2>(); team_sync();
       const double* r0 = sm + (k & 3) * RO_SZ;
       const double* r1 = sm + ((k + 1) & 3) * RO_SZ;
+      double* w2k = S.stage_ptr(k, S.B2); double* w2n = S.stage_ptr(k + 1, S.B2);
       double mine = 0;
       if (c < NU) {
         mine = r0[R_KFF + c];
 #pragma unroll
         for (int j = 0; j < NX; ++j) mine = fma(r0[R_K + c * NX + j], dxv[j], mine);
-        S.W2(k, S_DU + c) = mine;
+        w2k[(S_DU + c) << 5] = mine;
       }
       double duv[NU];
 #pragma unroll
@@ -322,7 +330,7 @@ struct Team {
       for (int i = 0; i < NX; ++i) l = fma(r0[R_W + i], dxv[i], l);
 #pragma unroll
       for (int a = 0; a < NU; ++a) l = fma(r0[R_W + NX + a], duv[a], l);
-      dsv = -l / r0[R_CV];
+      dsv = -l * rcp(r0[R_CV]);
       const SACoef a = ac_from(r0 + RO_AC, dt);
       double nx_[NX];
       nx_[0] = dxv[0] + dt * dxv[3]; nx_[1] = dxv[1] + dt * dxv[4]; nx_[2] = dxv[2] + dt * dxv[5];
@@ -336,15 +344,15 @@ struct Team {
         double mx = 0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) mx = (i == c) ? dxv[i] : mx;
-        S.W2(k + 1, S_DX + c) = mx;
+        w2n[(S_DX + c) << 5] = mx;
         double v = r1[R_PV + c];
 #pragma unroll
         for (int j = 0; j < NX; ++j) v = fma(r1[R_P + (c <= j ? c * 9 - c * (c - 1) / 2 + (j - c) : j * 9 - j * (j - 1) / 2 + (c - j))], dxv[j], v);
         if (c < 3) v = fma(r1[RO_A + c], dsv, v);
         if (c >= 6) v = fma(r1[RO_A + (c - 3)], dsv, v);
-        S.W2(k + 1, S_LAMN + c) = v;
+        w2n[(S_LAMN + c) << 5] = v;
       }
-      if (c == 14) S.W2(k + 1, S_DS) = dsv;
+      if (c == 14) w2n[S_DS << 5] = dsv;
       team_sync();  // slot k & 3 is free
       ro_issue(k + 4, it);
     }

@@ -54,15 +54,17 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   int cnt[2] = {0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
   for (int b = 0; b < B; ++b) body_init(P, b);
+  const bool ref = cfg->mode == MMPC_MODE_REFERENCE;
+  if (ref) parts = 0;  // the part kernels implement the clean NLP only
   int N = cfg->N, r = 0;
   for (;; ++r) {
     compact_list(P, 0, ST_ACTIVE);
     int nE = cnt[0];
     if (!fused || r == 0)  // fused: only the starting point needs the stand-alone evaluation
-      for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_eval(P, j, k);
+      for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) { if (ref) body_eval<true>(P, j, k); else body_eval<false>(P, j, k); }
     for (int j = 0; j < nE; ++j) { if (team) run_team(P, j, stacks); else body_solve(P, j); }
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) {
-      if (!parts) body_step(P, j, k);
+      if (!parts) { if (ref) body_step<true>(P, j, k); else body_step<false>(P, j, k); }
       else if (inst_state(P, list_E(P)[j]) == ST_ACTIVE) body_parts_item(P, list_E(P)[j], k, false);
       else if (inst_state(P, list_E(P)[j]) == ST_FINISH) { Inst F(P, list_E(P)[j]); F.finish_stage(k); }
     }
@@ -70,7 +72,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     compact_list(P, 1, ST_TRIAL);
     int nT = cnt[1];
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) {
-      if (!parts) body_trial(P, j, k);
+      if (!parts) { if (ref) body_trial<true>(P, j, k); else body_trial<false>(P, j, k); }
       else body_parts_item(P, list_T(P)[j], k, true);
     }
     for (int j = 0; j < nT; ++j) body_ctrl_trial(P, j);
