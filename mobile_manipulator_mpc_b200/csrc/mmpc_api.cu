@@ -234,9 +234,9 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     CK(cudaMalloc(&h->sg.rk, (size_t)(N + 1) * RS * LS * sizeof(double)));
     CK(cudaMalloc(&h->sg.gd, (size_t)staged_inst_doubles(cfg) * LS * sizeof(double)));
     CK(cudaMalloc(&h->sg.gi, (size_t)J_NFIELDS * LS * sizeof(int)));
-    CK(cudaMalloc(&h->sg.lists, (size_t)2 * LS * sizeof(int)));
-    CK(cudaMalloc(&h->sg.cnt, 2 * sizeof(int)));
-    CK(cudaMallocHost(&h->sg.pin, 8 * 2 * sizeof(int)));
+    CK(cudaMalloc(&h->sg.lists, (size_t)3 * LS * sizeof(int)));
+    CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
+    CK(cudaMallocHost(&h->sg.pin, 8 * 4 * sizeof(int)));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming));
     h->sg.ready = true;
   }
@@ -277,11 +277,15 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
     int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
     int gt = (int)((ub * 16 + 127) / 128);
+    int gw = (int)((ub * 32 + 127) / 128 < cap ? (ub * 32 + 127) / 128 : cap);  // one warp per instance
+    if (gw < 1) gw = 1;
     int gtile = (int)((items + 31) / 32 < 8 * cap ? (items + 31) / 32 : 8 * cap);
     if (gtile < 1) gtile = 1;
     if (gs < 1) gs = 1; if (gi_ < 1) gi_ = 1; if (g64 < 1) g64 = 1; if (gt < 1) gt = 1;
     MARK(MMPC_PHASE_COMPACT);
-    staged_compact_kernel<<<1, 1024, 0, st>>>(P, 0, ST_ACTIVE);
+    const int tcur = 1 + (r & 1), tnext = 1 + ((r + 1) & 1);
+    const int cthreads = ub > 16384 ? 1024 : ub > 2048 ? 256 : 64;
+    staged_compact_kernel<<<1, cthreads, 0, st>>>(P, 0, tcur, ST_ACTIVE);
     if (!P.fused || r == 0) {  // fused: the trial kernel has already evaluated the accepted point
       MARK(MMPC_PHASE_EVAL);
       if (ref) staged_eval_kernel<true><<<gs, 128, 0, st>>>(P); else staged_eval_kernel<false><<<gs, 128, 0, st>>>(P);
@@ -295,27 +299,28 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     else if (ref) staged_step_kernel<true><<<gs, 128, 0, st>>>(P);
     else staged_step_kernel<false><<<gs, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_CTRL_STEP);
-    staged_ctrl_step_kernel<<<gi_, 128, 0, st>>>(P);
+    staged_ctrl_step_kernel<<<gw, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_COMPACT);
-    staged_compact_kernel<<<1, 1024, 0, st>>>(P, 1, ST_TRIAL);
+    staged_compact_kernel<<<1, cthreads, 0, st>>>(P, tnext, tcur, ST_TRIAL);
+    P.tsel = tnext;
     MARK(MMPC_PHASE_TRIAL);
     if (thin) staged_parts_kernel<true><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
     else if (ref) staged_trial_kernel<true><<<gs, 128, 0, st>>>(P);
     else staged_trial_kernel<false><<<gs, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_CTRL_TRIAL);
-    staged_ctrl_trial_kernel<<<gi_, 128, 0, st>>>(P);
+    staged_ctrl_trial_kernel<<<gw, 128, 0, st>>>(P);
     CK(cudaGetLastError());
     h->launches += (!P.fused || r == 0) ? 8 : 7;
     // the list lengths of this round trail the launches by LAG rounds
     int slot = r & 7;
-    CK(cudaMemcpyAsync(h->sg.pin + 2 * slot, h->sg.cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->sg.pin + 4 * slot, h->sg.cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->sg.ev[slot], st));
     if (r >= LAG) {
       int qs = (r - LAG) & 7;
       CK(cudaEventSynchronize(h->sg.ev[qs]));
       // every instance still active after a round is in that round's trial list, and the
       // active set only shrinks: its length bounds every later list
-      long long nT = h->sg.pin[2 * qs + 1];
+      long long nT = h->sg.pin[4 * qs + 1 + ((r - LAG + 1) & 1)];
       if (nT == 0) break;
       if (nT < ub) ub = nT;
     }

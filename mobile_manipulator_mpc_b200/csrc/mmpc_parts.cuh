@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256, 1) staged_parts_kernel(const __grid_const
   __shared__ double qrec[32 * QREC_STRIDE];
   const PartPlan pl = part_plan(P.cfg);
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5, nthr = blockDim.x;
-  const int n = TRIAL ? P.cnt[1] : P.cnt[0];
+  const int n = TRIAL ? P.cnt[P.tsel] : P.cnt[0];
   const int* list = TRIAL ? list_T(P) : list_E(P);
   const long long tot = (long long)n * (P.cfg.N + 1);
   double* accp = acc + lane * ACC_STRIDE;

@@ -51,8 +51,9 @@ struct SParams {
   double* rk;      // Riccati records       rk[(k*LS + b)*RS + f]
   double* gd;      // per-instance doubles  gd[field * LS + b]
   int* gi;         // per-instance ints     gi[field * LS + b]
-  int* lists;      // 2 lists of LS ints: E (next phase eval), T (next phase trial)
+  int* lists;      // 3 lists of LS ints: E (next phase solve), T0 / T1 (next phase trial, ping-pong over rounds)
   int* cnt;        // their lengths
+  int tsel;        // which T list the trial kernels of this round read (1 or 2)
   long long LS;    // B_max rounded up to a multiple of 32 (whole tiles)
   int ND;          // per-instance doubles (staged_inst_doubles)
   int R, STG, ITSZ;
@@ -1145,27 +1146,38 @@ struct Inst {
 
   // ctrl_step (thread per instance): reduce the step partials, start the line search.
   // Returns true if the instance goes on to a trial.
-  __device__ bool ctrl_step() {
-    if (J(J_STATE) == ST_FINISH) {  // close an instance whose stages were written by finish_stage
+  // NL lanes share the reduction over the stages (NL = 32: one warp per instance on the GPU, butterfly sums in a
+  // fixed order; NL = 1: one lane does everything, the CPU emulation); lane 0 writes the instance state.
+  template <int NL>
+  __device__ bool ctrl_step(int lane) {
+    const int st = J(J_STATE);
+    if (st == ST_FINISH) {  // close an instance whose stages were written by finish_stage
       double fsum = 0;
-      for (int k = 0; k <= N; ++k) fsum += W2(k, S_PART + 0);
-      if (P.cost) P.cost[b] = fsum;
-      if (P.kkt) P.kkt[b] = D(D_E0);
-      if (P.iters) P.iters[b] = J(J_IT);
-      P.status[b] = J(J_STATUS);
-      J(J_STATE) = ST_DONE;
+      for (int k = lane; k <= N; k += NL) fsum += W2(k, S_PART + 0);
+      fsum = lanes_sum<NL>(fsum);
+      if (lane == 0) {
+        if (P.cost) P.cost[b] = fsum;
+        if (P.kkt) P.kkt[b] = D(D_E0);
+        if (P.iters) P.iters[b] = J(J_IT);
+        P.status[b] = J(J_STATUS);
+        J(J_STATE) = ST_DONE;
+      }
       return false;
     }
-    if (J(J_STATE) != ST_ACTIVE) return false;
+    if (st != ST_ACTIVE) return false;
     double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0, logsum = 0;
-    for (int k = 0; k <= N; ++k) {
+    for (int k = lane; k <= N; k += NL) {
       ap = fmin(ap, W2(k, S_PART + 0)); ad = fmin(ad, W2(k, S_PART + 1));
       gphi += W2(k, S_PART + 2); theta += W2(k, S_PART + 3); fsum += W2(k, S_PART + 4); logsum += W2(k, S_PART + 5);
     }
-    if (D(D_THMAX) < 0) { D(D_THMAX) = 1e4 * fmax(1.0, theta); D(D_THMIN) = 1e-4 * fmax(1.0, theta); }
-    D(D_ALPHA) = ap; D(D_AD) = ad; D(D_GPHI) = gphi; D(D_THETA) = theta; D(D_PHI0) = fsum - D(D_MU) * logsum;
-    J(J_LS) = 0;
-    J(J_STATE) = ST_TRIAL;
+    ap = lanes_min<NL>(ap); ad = lanes_min<NL>(ad);
+    gphi = lanes_sum<NL>(gphi); theta = lanes_sum<NL>(theta); fsum = lanes_sum<NL>(fsum); logsum = lanes_sum<NL>(logsum);
+    if (lane == 0) {
+      if (D(D_THMAX) < 0) { D(D_THMAX) = 1e4 * fmax(1.0, theta); D(D_THMIN) = 1e-4 * fmax(1.0, theta); }
+      D(D_ALPHA) = ap; D(D_AD) = ad; D(D_GPHI) = gphi; D(D_THETA) = theta; D(D_PHI0) = fsum - D(D_MU) * logsum;
+      J(J_LS) = 0;
+      J(J_STATE) = ST_TRIAL;
+    }
     return true;
   }
 
@@ -1538,19 +1550,27 @@ struct Inst {
   // ctrl_trial (thread per instance): filter acceptance test (Waechter & Biegler 2006, Alg. A
   // without second-order correction).  Returns 0 = accepted (next: eval), 1 = rejected (next: another
   // trial with alpha/2), 2 = finished (line search failed).
-  __device__ int ctrl_trial() {
-    double th1 = 0, f1 = 0, logsum = 0; bool ok = true;
-    for (int k = 0; k <= N; ++k) {
+  template <int NL>
+  __device__ int ctrl_trial(int lane) {
+    double th1 = 0, f1 = 0, logsum = 0, okv = 1.0;
+    for (int k = lane; k <= N; k += NL) {
       th1 += W2(k, S_PART + PT_MERIT + 0); f1 += W2(k, S_PART + PT_MERIT + 1); logsum += W2(k, S_PART + PT_MERIT + 2);
-      ok = ok && (W2(k, S_PART + PT_MERIT + 3) > 0.5);
+      okv = fmin(okv, W2(k, S_PART + PT_MERIT + 3));
     }
+    th1 = lanes_sum<NL>(th1); f1 = lanes_sum<NL>(f1); logsum = lanes_sum<NL>(logsum); okv = lanes_min<NL>(okv);
+    bool ok = okv > 0.5;
     const double mu = D(D_MU), theta_k = D(D_THETA), phi0 = D(D_PHI0), gphi = D(D_GPHI), alpha = D(D_ALPHA);
     double ph1 = f1 - mu * logsum;
     int nfilt = J(J_NFILT);
+    const int cur = J(J_CUR), itn = J(J_IT), lsn = J(J_LS);
     bool ftype = false;
     ok = ok && (th1 == th1) && (ph1 == ph1) && th1 < D(D_THMAX);
-    for (int q = 0; ok && q < nfilt; ++q)
-      if (th1 >= D(D_FILT + 2 * q) && ph1 >= D(D_FILT + 2 * q + 1)) ok = false;
+    // filter: an entry dominates the trial point if it is at least as good in both measures; entry q is checked by lane q mod NL
+    double dom = 0.0;
+    for (int q = lane; q < nfilt; q += NL)
+      if (th1 >= D(D_FILT + 2 * q) && ph1 >= D(D_FILT + 2 * q + 1)) dom = 1.0;
+    dom = lanes_max<NL>(dom);
+    ok = ok && !(dom > 0.5);
     if (ok) {
       bool sw = (gphi < 0) && (alpha * pow(-gphi, 2.3) > pow(theta_k, 1.1));
       if (theta_k <= D(D_THMIN) && sw) {
@@ -1559,23 +1579,25 @@ struct Inst {
         ok = (th1 <= (1 - 1e-5) * theta_k) || (ph1 <= phi0 - 1e-8 * theta_k); ftype = false;
       }
     }
+    lanes_sync<NL>();  // every lane has read the instance state before lane 0 rewrites it
     if (!ok) {
-      D(D_ALPHA) = alpha * 0.5;
-      int ls = J(J_LS) + 1; J(J_LS) = ls;
-      if (ls >= 50) { finish(MMPC_STATUS_LINESEARCH); return 2; }
+      if (lane == 0) { D(D_ALPHA) = alpha * 0.5; J(J_LS) = lsn + 1; }
+      if (lsn + 1 >= 50) { if (lane == 0) finish(MMPC_STATUS_LINESEARCH); return 2; }
       return 1;
     }
-    if (!ftype) {
-      if (nfilt == 16) {
-        for (int q = 0; q < 30; ++q) D(D_FILT + q) = D(D_FILT + q + 2);
-        nfilt--;
+    if (lane == 0) {
+      if (!ftype) {
+        if (nfilt == 16) {
+          for (int q = 0; q < 30; ++q) D(D_FILT + q) = D(D_FILT + q + 2);
+          nfilt--;
+        }
+        D(D_FILT + 2 * nfilt) = (1 - 1e-5) * theta_k; D(D_FILT + 2 * nfilt + 1) = phi0 - 1e-8 * theta_k; nfilt++;
+        J(J_NFILT) = nfilt;
       }
-      D(D_FILT + 2 * nfilt) = (1 - 1e-5) * theta_k; D(D_FILT + 2 * nfilt + 1) = phi0 - 1e-8 * theta_k; nfilt++;
-      J(J_NFILT) = nfilt;
+      J(J_CUR) = 1 - cur;
+      J(J_IT) = itn + 1;
+      J(J_STATE) = ST_ACTIVE;
     }
-    J(J_CUR) = 1 - J(J_CUR);
-    J(J_IT) = J(J_IT) + 1;
-    J(J_STATE) = ST_ACTIVE;
     return 0;
   }
 };
@@ -1590,7 +1612,8 @@ __device__ __forceinline__ int& inst_state(const SParams& P, int b) {
 // kernels stay as coalesced as the surviving instances allow) by an ordered compaction of the
 // per-instance state: E = instances whose next phase is eval, T = instances whose next phase is a trial.
 __device__ __forceinline__ int* list_E(const SParams& P) { return P.lists; }
-__device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.LS; }
+__device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.tsel * P.LS; }
+__device__ __forceinline__ int* list_n(const SParams& P, int which) { return P.lists + which * P.LS; }
 
 // ---- phase bodies on list items (shared by the kernels and by tests/emu) -----------------------------
 __device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init(); }
@@ -1604,55 +1627,62 @@ __device__ inline void body_step(const SParams& P, int j, int k) {
   if (st == ST_FINISH) S.finish_stage(k);
   else if (st == ST_ACTIVE) S.template step<REF>(k);
 }
-__device__ inline void body_ctrl_step(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.ctrl_step(); }
+template <int NL>
+__device__ inline void body_ctrl_step(const SParams& P, int j, int lane) { Inst S(P, list_E(P)[j]); S.template ctrl_step<NL>(lane); }
 template <bool REF>
 __device__ inline void body_trial(const SParams& P, int j, int k) {
   Inst S(P, list_T(P)[j]);
   if (P.fused) S.template trial_eval<REF>(k); else S.trial(k);
 }
-__device__ inline void body_ctrl_trial(const SParams& P, int j) { Inst S(P, list_T(P)[j]); S.ctrl_trial(); }
+template <int NL>
+__device__ inline void body_ctrl_trial(const SParams& P, int j, int lane) { Inst S(P, list_T(P)[j]); S.template ctrl_trial<NL>(lane); }
 
 #ifdef MMPC_EMULATE_LANE
-// ordered compaction of the instances in state `want` into list `which` (0 = E, 1 = T)
-inline void compact_list(const SParams& P, int which, int want) {
-  int n = 0; int* list = which ? list_T(P) : list_E(P);
-  for (int b = 0; b < P.B; ++b) if (inst_state(P, b) == want) list[n++] = b;
-  P.cnt[which] = n;
+// ordered compaction: list `dst` <- the entries of list `src` whose instance is in state `want`
+inline void compact_list(const SParams& P, int dst, int src, int want) {
+  int n = 0; int* out = list_n(P, dst); const int* in = list_n(P, src);
+  for (int i = 0; i < P.cnt[src]; ++i) if (inst_state(P, in[i]) == want) out[n++] = in[i];
+  P.cnt[dst] = n;
 }
 #else
-// One block of 1024 threads: warp w scans a contiguous chunk of the state array 32 entries at a
-// time (coalesced), counts with ballots, the warp totals are scanned through shared memory, and
-// the second pass writes the indices in ascending order.
-__global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_constant__ SParams P, int which, int want) {
+// Ordered compaction  list dst <- { b in list src : state(b) == want }  by one block of 1024 threads: warp w
+// scans a contiguous chunk of the source list 32 entries at a time (coalesced), counts with ballots, the warp
+// totals are scanned through shared memory, and the second pass writes the survivors in order.  Every
+// active instance is in the previous round's trial list, so the source shrinks with the active set.
+__global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_constant__ SParams P, int dst, int src, int want) {
   __shared__ int wtot[32];
-  int* list = which ? list_T(P) : list_E(P);
+  int* out = list_n(P, dst); const int* in = list_n(P, src);
+  const int n = P.cnt[src];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = ((P.B + 1023) / 1024) * 32;  // entries per warp, multiple of 32
-  const int lo = warp * chunk, hi = min(P.B, lo + chunk);
+  const int nw = blockDim.x >> 5;
+  const int chunk = ((n + blockDim.x - 1) / blockDim.x) * 32;  // entries per warp, multiple of 32
+  const int lo = warp * chunk, hi = min(n, lo + chunk);
   int c = 0;
-  for (int b0 = lo; b0 < hi; b0 += 32) {
-    int b = b0 + lane;
-    bool f = b < hi && inst_state(P, b) == want;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    int i = i0 + lane;
+    bool f = i < hi && inst_state(P, in[i]) == want;
     c += __popc(__ballot_sync(FULL, f));
   }
   if (lane == 0) wtot[warp] = c;
   __syncthreads();
   int off = 0, tot = 0;
-  for (int w2 = 0; w2 < 32; ++w2) { int v = wtot[w2]; if (w2 < warp) off += v; tot += v; }
-  for (int b0 = lo; b0 < hi; b0 += 32) {
-    int b = b0 + lane;
-    bool f = b < hi && inst_state(P, b) == want;
+  for (int w2 = 0; w2 < nw; ++w2) { int v = wtot[w2]; if (w2 < warp) off += v; tot += v; }
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    int i = i0 + lane;
+    int b = i < hi ? in[i] : 0;
+    bool f = i < hi && inst_state(P, b) == want;
     unsigned m = __ballot_sync(FULL, f);
-    if (f) list[off + __popc(m & ((1u << lane) - 1))] = b;
+    if (f) out[off + __popc(m & ((1u << lane) - 1))] = b;
     off += __popc(m);
   }
-  if (threadIdx.x == 0) P.cnt[which] = tot;
+  if (threadIdx.x == 0) P.cnt[dst] = tot;
 }
 
 // ---- kernels: grid-stride loops over the device-side list counts --------------------------------------
 __global__ void __launch_bounds__(128) staged_init_kernel(const __grid_constant__ SParams P) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < P.B) body_init(P, b);
+  if (b < P.B) { body_init(P, b); list_n(P, 1)[b] = b; }  // every instance starts in the first source list
+  if (b == 0) P.cnt[1] = P.B;
 }
 template <bool REF>
 __global__ void __launch_bounds__(128) staged_eval_kernel(const __grid_constant__ SParams P) {
@@ -1680,19 +1710,21 @@ __global__ void __launch_bounds__(128, MMPC_STEP_MINB) staged_step_kernel(const 
     body_step<REF>(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
-  const int n = P.cnt[0];
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_step(P, j);
+  const int n = P.cnt[0];  // one warp per instance
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5)
+    body_ctrl_step<32>(P, j, threadIdx.x & 31);
 }
 template <bool REF>
 __global__ void __launch_bounds__(128, MMPC_TRIAL_MINB) staged_trial_kernel(const __grid_constant__ SParams P) {
-  const int n = P.cnt[1];
+  const int n = P.cnt[P.tsel];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
     body_trial<REF>(P, (int)(t % n), (int)(t / n));
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
-  const int n = P.cnt[1];
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) body_ctrl_trial(P, j);
+  const int n = P.cnt[P.tsel];  // one warp per instance
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5)
+    body_ctrl_trial<32>(P, j, threadIdx.x & 31);
 }
 #endif
 

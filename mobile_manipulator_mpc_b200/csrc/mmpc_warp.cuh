@@ -62,6 +62,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
   return v;
 }
+// reductions over the NL lanes that share one instance in the control kernels (NL = 32: the warp, fixed
+// butterfly order; NL = 1: nothing to do)
+template <int NL> __device__ __forceinline__ double lanes_sum(double v) { return NL == 1 ? v : warp_sum(v); }
+template <int NL> __device__ __forceinline__ double lanes_min(double v) { return NL == 1 ? v : warp_min(v); }
+template <int NL> __device__ __forceinline__ double lanes_max(double v) { return NL == 1 ? v : warp_max(v); }
+template <int NL> __device__ __forceinline__ void lanes_sync() { if (NL > 1) sync_warp(); }
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);

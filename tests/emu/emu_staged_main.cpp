@@ -50,15 +50,17 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   EmuTeam* tw = new EmuTeam(); g_team = tw;
   std::vector<char*> stacks(16);
   for (int i = 0; i < 16; ++i) stacks[i] = (char*)malloc(1 << 18);
-  std::vector<int> gi((size_t)J_NFIELDS * P.LS, 0), lists((size_t)2 * P.LS, 0);
-  int cnt[2] = {0, 0};
+  std::vector<int> gi((size_t)J_NFIELDS * P.LS, 0), lists((size_t)3 * P.LS, 0);
+  int cnt[3] = {0, 0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
-  for (int b = 0; b < B; ++b) body_init(P, b);
+  for (int b = 0; b < B; ++b) { body_init(P, b); lists[P.LS + b] = b; }
+  cnt[1] = B;
   const bool ref = cfg->mode == MMPC_MODE_REFERENCE;
   if (ref) parts = 0;  // the part kernels implement the clean NLP only
   int N = cfg->N, r = 0;
   for (;; ++r) {
-    compact_list(P, 0, ST_ACTIVE);
+    const int tcur = 1 + (r & 1), tnext = 1 + ((r + 1) & 1);
+    compact_list(P, 0, tcur, ST_ACTIVE);
     int nE = cnt[0];
     if (!fused || r == 0)  // fused: only the starting point needs the stand-alone evaluation
       for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) { if (ref) body_eval<true>(P, j, k); else body_eval<false>(P, j, k); }
@@ -68,14 +70,15 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
       else if (inst_state(P, list_E(P)[j]) == ST_ACTIVE) body_parts_item(P, list_E(P)[j], k, false);
       else if (inst_state(P, list_E(P)[j]) == ST_FINISH) { Inst F(P, list_E(P)[j]); F.finish_stage(k); }
     }
-    for (int j = 0; j < nE; ++j) body_ctrl_step(P, j);
-    compact_list(P, 1, ST_TRIAL);
-    int nT = cnt[1];
+    for (int j = 0; j < nE; ++j) body_ctrl_step<1>(P, j, 0);
+    compact_list(P, tnext, tcur, ST_TRIAL);
+    P.tsel = tnext;
+    int nT = cnt[tnext];
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) {
       if (!parts) { if (ref) body_trial<true>(P, j, k); else body_trial<false>(P, j, k); }
       else body_parts_item(P, list_T(P)[j], k, true);
     }
-    for (int j = 0; j < nT; ++j) body_ctrl_trial(P, j);
+    for (int j = 0; j < nT; ++j) body_ctrl_trial<1>(P, j, 0);
     if (nT == 0) break;
     if (r > 200000) return 1;
   }
