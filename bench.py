@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--contexts", type=int, default=2, help="concurrent solver contexts (streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=3, help="concurrent solver contexts (streams) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -288,6 +288,20 @@ def main():
             phase_ms[k] = phase_ms.get(k, 0.0) + pm[k] / args.steps
             phase_ln[k] = pl[k]
     S.set_profile(False)
+    # p50 latency of ONE instance (B = 1, BASELINE config 1: demo scenario 1), device-resident
+    lat1 = None
+    if rank == 0:
+        from mobile_manipulator_mpc_b200 import scenarios
+        b1 = scenarios.make_batch(1, 1)
+        S1 = BatchSolver(N=b1["N"], dt=b1["dt"], n_obs=b1["n_obs"], n_pl=b1["n_pl"], B_max=1, device=local)
+        d1 = S1.to_device(b1); o1 = S1.solve_device(d1); torch.cuda.synchronize()
+        l1 = []
+        for _ in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); S1.solve_device(d1, out=o1); b.record(); torch.cuda.synchronize()
+            l1.append(a.elapsed_time(b))
+        lat1 = float(np.median(l1))
+        S1.close()
     barrier()
 
     # ---- end to end through the C ABI with host buffers (pinned staging, H2D, solve, D2H per step) ----
@@ -360,6 +374,7 @@ def main():
                                           % (S.workspace_bytes() / 1e9, (h2d + d2h) / 1e6),
                                 converged_fraction=conv_all / B_all, mean_iterations=iters_all / B_all,
                                 rounds=rounds, single_context_ms_per_step=step_ms,
+                                p50_batched_solve_latency_ms=float(np.median(lat_ms)), p50_single_instance_latency_ms=lat1,
                                 single_context_value=conv / (step_ms * 1e-3), wall_ms_timed_region=wall_ms),
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),

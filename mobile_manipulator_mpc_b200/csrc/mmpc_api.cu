@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -268,7 +269,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   staged_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(P);
   CK(cudaGetLastError());
   h->launches += 1;
-  const int LAG = 2, cap = h->sm_count * 16;
+  static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
+  const int LAG = 2, cap = h->sm_count * cap_mult;
   const bool ref = cfg.mode == MMPC_MODE_REFERENCE;
   long long ub = B;  // upper bound of the active instances (the lists only shrink)
   int r = 0;
@@ -294,7 +296,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     if (P.team) staged_solve_team_kernel<<<gt, 128, 0, st>>>(P);
     else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
     MARK(MMPC_PHASE_STEP);
-    const bool thin = P.parts && (items + 31) / 32 <= (long long)h->sm_count;  // every tile gets its own SM
+    static const long long parts_tiles = getenv("MMPC_PARTS_TILES") ? atoll(getenv("MMPC_PARTS_TILES")) : -1;  // A/B knob
+    const bool thin = P.parts && (items + 31) / 32 <= (parts_tiles >= 0 ? parts_tiles : (long long)h->sm_count);  // every tile gets its own SM
     if (thin) staged_parts_kernel<false><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
     else if (ref) staged_step_kernel<true><<<gs, 128, 0, st>>>(P);
     else staged_step_kernel<false><<<gs, 128, 0, st>>>(P);

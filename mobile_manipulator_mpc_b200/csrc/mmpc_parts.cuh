@@ -550,7 +550,10 @@ __device__ __forceinline__ void block_sync(int nthreads) { asm volatile("bar.syn
 // grid-stride over tiles of 32 items; blockDim = 32 * n_parts.  Each warp keeps only its own kind of
 // partial in registers; the partials are combined in part order, one barrier-separated phase per part.
 template <bool TRIAL>
-__global__ void __launch_bounds__(256, 1) staged_parts_kernel(const __grid_constant__ SParams P) {
+#ifndef MMPC_PARTS_MINB
+#define MMPC_PARTS_MINB 1
+#endif
+__global__ void __launch_bounds__(256, MMPC_PARTS_MINB) staged_parts_kernel(const __grid_constant__ SParams P) {
   __shared__ double acc[32 * ACC_STRIDE];
   __shared__ double qrec[32 * QREC_STRIDE];
   const PartPlan pl = part_plan(P.cfg);

@@ -141,8 +141,8 @@ struct Inst {
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
   __device__ __forceinline__ double& D(int o) const { return gd[o << 5]; }
   __device__ __forceinline__ int& J(int o) const { return gi[o << 5]; }
-  __device__ __forceinline__ double circ(int k, int i, int c) const {
-    return cfg.obs_per_stage ? W2(k, S_DT + R + 3 * i + c) : D(D_CIRC + 3 * i + c);
+  __device__ __forceinline__ double circ(int k, int i, int c) const {  // read-only after init: non-coherent load
+    return ldg(cfg.obs_per_stage ? &W2(k, S_DT + R + 3 * i + c) : &D(D_CIRC + 3 * i + c));
   }
   __device__ __forceinline__ void load_npl() { npl = J(J_NPL); }
   __device__ __forceinline__ bool term_eq(int k) const { return k == N && (J(J_FLAGS) & 1); }
@@ -1313,22 +1313,22 @@ struct Inst {
     double x[NX], u[NU], lam[NX], lam1[NX], xo[NX], dxo[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      xo[i] = ci[(I_X + i) << 5]; dxo[i] = c2[(S_DX + i) << 5];
+      xo[i] = ldg(&ci[(I_X + i) << 5]); dxo[i] = ldg(&c2[(S_DX + i) << 5]);
       x[i] = fma(alpha, dxo[i], xo[i]);
       cj[(I_X + i) << 5] = x[i];
       lam[i] = 0;
       if (k >= 1) {
-        double l = ci[(I_LAM + i) << 5];
-        lam[i] = l + alpha * (c2[(S_LAMN + i) << 5] - l);
+        double l = ldg(&ci[(I_LAM + i) << 5]);
+        lam[i] = l + alpha * (ldg(&c2[(S_LAMN + i) << 5]) - l);
         cj[(I_LAM + i) << 5] = lam[i];
       }
     }
-    const double s = fma(alpha, c2[(S_DS) << 5], ci[(I_S) << 5]);
+    const double s = fma(alpha, ldg(&c2[(S_DS) << 5]), ldg(&ci[(I_S) << 5]));
     cj[(I_S) << 5] = s;
     double uo[NU], duo[NU];
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
-      uo[j] = (k < N) ? ci[(I_U + j) << 5] : 0.0; duo[j] = (k < N) ? c2[(S_DU + j) << 5] : 0.0;
+      uo[j] = (k < N) ? ldg(&ci[(I_U + j) << 5]) : 0.0; duo[j] = (k < N) ? ldg(&c2[(S_DU + j) << 5]) : 0.0;
       u[j] = fma(alpha, duo[j], uo[j]);
       if (k < N) cj[(I_U + j) << 5] = u[j];
     }
@@ -1349,9 +1349,9 @@ struct Inst {
       dyn_f(x, u, dt, f.cp, f.sp, xn);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double l1 = ni[(I_LAM + i) << 5];
-        lam1[i] = l1 + alpha * (n2[(S_LAMN + i) << 5] - l1);
-        double x1 = fma(alpha, n2[(S_DX + i) << 5], ni[(I_X + i) << 5]);
+        double l1 = ldg(&ni[(I_LAM + i) << 5]);
+        lam1[i] = l1 + alpha * (ldg(&n2[(S_LAMN + i) << 5]) - l1);
+        double x1 = fma(alpha, ldg(&n2[(S_DX + i) << 5]), ldg(&ni[(I_X + i) << 5]));
         double d = xn[i] - x1;
         c2[(S_DFC + i) << 5] = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
         theta += fabs(d);
@@ -1397,18 +1397,18 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-      double e = x[i] - c2[(IN_XREF + i) << 5];
+      double e = x[i] - ldg(&c2[(IN_XREF + i) << 5]);
       fsum += Wx * e * e;
       double gr = 2 * Wx * e;
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, id, z = box(ci[(I_ZXL + i) << 5], xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
+          double d = x[i] - lo, id, z = box(ldg(&ci[(I_ZXL + i) << 5]), xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], id, z = box(ci[(I_ZXU + i) << 5], hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
+          double d = hi - x[i], id, z = box(ldg(&ci[(I_ZXU + i) << 5]), hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
           Hd += z * id; gB += id; st += z;
         }
       }
@@ -1430,18 +1430,18 @@ struct Inst {
       double Hd = 0, gA = 0, gB = 0;
       if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - c2[(IN_UREF + j) << 5], dl = u[j] - c2[(IN_ULAST + j) << 5];
+        double e = u[j] - ldg(&c2[(IN_UREF + j) << 5]), dl = u[j] - ldg(&c2[(IN_ULAST + j) << 5]);
         fsum += os * (cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl);
         double gr = 2 * Rj * e + 2 * Wj * dl;
         Hd = 2 * Rj + 2 * Wj; gA = gr;
         double st = gr + stu[j];
-        double lo = c2[(IN_ULO + j) << 5], hi = c2[(IN_UHI + j) << 5];
+        double lo = ldg(&c2[(IN_ULO + j) << 5]), hi = ldg(&c2[(IN_UHI + j) << 5]);
         if (is_fin(lo)) {
-          double d = u[j] - lo, id, z = box(ci[(I_ZUL + j) << 5], uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
+          double d = u[j] - lo, id, z = box(ldg(&ci[(I_ZUL + j) << 5]), uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], id, z = box(ci[(I_ZUU + j) << 5], hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
+          double d = hi - u[j], id, z = box(ldg(&ci[(I_ZUU + j) << 5]), hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
           Hd += z * id; gB += id; st += z;
         }
         es = fmax(es, fabs(st));
@@ -1450,8 +1450,8 @@ struct Inst {
     }
     // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
     auto row = [&](int r, double h, double& z, double& it_, double& res) {
-      double t = ci[(I_T + r) << 5], dtv = c2[(S_DT + r) << 5];
-      z = ci[(I_T + R + r) << 5];
+      double t = ldg(&ci[(I_T + r) << 5]), dtv = ldg(&c2[(S_DT + r) << 5]);
+      z = ldg(&ci[(I_T + R + r) << 5]);
       double tt = fmax(fma(alpha, dtv, t), s - h);  // slack reset (Nocedal & Wright 19.30)
       double dz = (mu - z * (t + dtv)) * rcp(t);
       it_ = rcp(tt);
