@@ -269,6 +269,14 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   staged_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(P);
   CK(cudaGetLastError());
   h->launches += 1;
+  // row ring of the step kernels: STAGED_RING_DOUBLES per thread (48 KB per block of 128)
+  const int ring_smem = 128 * STAGED_RING_DOUBLES * (int)sizeof(double);
+  static bool smem_attr_done = false;
+  if (!smem_attr_done) {
+    smem_attr_done = true;
+    CK(cudaFuncSetAttribute(staged_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
+    CK(cudaFuncSetAttribute(staged_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
+  }
   static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
   const int LAG = 2, cap = h->sm_count * cap_mult;
   const bool ref = cfg.mode == MMPC_MODE_REFERENCE;
@@ -299,8 +307,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     static const long long parts_tiles = getenv("MMPC_PARTS_TILES") ? atoll(getenv("MMPC_PARTS_TILES")) : -1;  // A/B knob
     const bool thin = P.parts && (items + 31) / 32 <= (parts_tiles >= 0 ? parts_tiles : (long long)h->sm_count);  // every tile gets its own SM
     if (thin) staged_parts_kernel<false><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
-    else if (ref) staged_step_kernel<true><<<gs, 128, 0, st>>>(P);
-    else staged_step_kernel<false><<<gs, 128, 0, st>>>(P);
+    else if (ref) staged_step_kernel<true><<<gs, 128, ring_smem, st>>>(P);
+    else staged_step_kernel<false><<<gs, 128, ring_smem, st>>>(P);
     MARK(MMPC_PHASE_CTRL_STEP);
     staged_ctrl_step_kernel<<<gw, 128, 0, st>>>(P);
     MARK(MMPC_PHASE_COMPACT);

@@ -118,6 +118,18 @@ struct Inst {
   long long LS;
   int N, R, STG, ITSZ, B2, nobs, npl, b;
   double dt;
+  // Row ring (step and trial kernels): the inputs of the "row-like" items of a stage -- circle rows with their circle,
+  // bound multipliers, self-collision and plane rows -- are streamed through a per-thread ring in shared memory
+  // with cp.async, RING_D items ahead of their use.  The items are consumed strictly in order; one commit group
+  // per item, so `wait_group RING_D - 1` is "the oldest item has landed".  (Register prefetching does not work
+  // here: ptxas puts the prefetch loads on the scoreboard their consumer waits on.)
+  static constexpr int RING_D = 8, RING_W = 6;
+  double* sm = nullptr;  // this thread's lane of the ring: item q, value c at sm[((q % RING_D) * RING_W + c) * bs]
+  int bs = 1;            // threads per block
+  __device__ __forceinline__ double* ring_slot(int q) const { return sm + ((q & (RING_D - 1)) * RING_W) * bs; }
+  __device__ __forceinline__ const double* circ_ptr(int k, int i, int c) const {
+    return cfg.obs_per_stage ? &W2(k, S_DT + R + 3 * i + c) : &D(D_CIRC + 3 * i + c);
+  }
 
   __device__ __forceinline__ Inst(const SParams& p, int b_) : P(p), cfg(p.cfg) {
     b = b_; LS = p.LS;
@@ -141,10 +153,16 @@ struct Inst {
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
   __device__ __forceinline__ double& D(int o) const { return gd[o << 5]; }
   __device__ __forceinline__ int& J(int o) const { return gi[o << 5]; }
+  template <bool NC = true>
   __device__ __forceinline__ double circ(int k, int i, int c) const {  // read-only after init: non-coherent load
-    return ldg(cfg.obs_per_stage ? &W2(k, S_DT + R + 3 * i + c) : &D(D_CIRC + 3 * i + c));
+    const double* p = cfg.obs_per_stage ? &W2(k, S_DT + R + 3 * i + c) : &D(D_CIRC + 3 * i + c);
+    return NC ? ldg(p) : *p;
   }
   __device__ __forceinline__ void load_npl() { npl = J(J_NPL); }
+  // plane data (point, normal) of this instance: written by init only, so the phase kernels read it non-coherently
+  // (init itself, which has just written it, passes NC = false)
+  template <bool NC = true>
+  __device__ __forceinline__ double PL(int o) const { return NC ? ldg(&gd[(D_PL + o) << 5]) : gd[(D_PL + o) << 5]; }
   __device__ __forceinline__ bool term_eq(int k) const { return k == N && (J(J_FLAGS) & 1); }
   // L2 prefetch of every field of stage k this thread is going to read (current iterate, step, references,
   // rows): the loads further down then find their lines in L2 instead of paying a full HBM round trip
@@ -164,12 +182,13 @@ struct Inst {
   }
 
   // -max_j c[i][j] for body point i (:76-87); returns the arg-max plane
+  template <bool NC = true>
   __device__ __forceinline__ double plane_row(const Point& p, int& jbest) const {
     double cb = 0; jbest = 0;
     for (int j = 0; j < npl; ++j) {
-      double n0 = D(D_PL + 6 * j + 3), n1 = D(D_PL + 6 * j + 4), n2 = D(D_PL + 6 * j + 5);
+      double n0 = PL<NC>(6 * j + 3), n1 = PL<NC>(6 * j + 4), n2 = PL<NC>(6 * j + 5);
       double e = cfg.obstacle_expand_dist;
-      double off = n0 * (D(D_PL + 6 * j + 0) - e * n0) + n1 * (D(D_PL + 6 * j + 1) - e * n1) + n2 * (D(D_PL + 6 * j + 2) - e * n2);
+      double off = n0 * (PL<NC>(6 * j + 0) - e * n0) + n1 * (PL<NC>(6 * j + 1) - e * n1) + n2 * (PL<NC>(6 * j + 2) - e * n2);
       double c = off - (n0 * p.P[0] + n1 * p.P[1] + n2 * p.P[2]);
       bool take = (j == 0) || (npl == 2 ? !(cb > c) : (c > cb));  // if_else(c0 > c1, c0, c1) :85 ; mmax :87
       if (take) { cb = c; jbest = j; }
@@ -224,8 +243,8 @@ struct Inst {
       FK f; fk_eval(x[2], x[6], x[7], x[8], f);
       double hmax = -1e300;
       for (int i = 0; i < nobs; ++i) {
-        double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
-        double h = (circ(k, i, 2) + cfg.base_radius) - sqrt(ddx * ddx + ddy * ddy);
+        double ddx = x[0] - circ<false>(k, i, 0), ddy = x[1] - circ<false>(k, i, 1);  // written above by this thread
+        double h = (circ<false>(k, i, 2) + cfg.base_radius) - sqrt(ddx * ddx + ddy * ddy);
         W(k, I_T + i) = h; hmax = fmax(hmax, h);
       }
 #pragma unroll 1
@@ -238,7 +257,7 @@ struct Inst {
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {
           Point p; point_eval(x[0], x[1], f, BODY[i], p);
-          int jb; double h = plane_row(p, jb);
+          int jb; double h = plane_row<false>(p, jb);
           W(k, I_T + nobs + 4 + i) = h; hmax = fmax(hmax, h);
         }
       }
@@ -355,7 +374,7 @@ struct Inst {
           const double (&pp)[NP] = here ? pk : pm;
           const FK& ff = here ? fk : fm;
           Point pt; point_eval(pp[0], pp[1], ff, BODY[i], pt);
-          const double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)};
+          const double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)};
           double g[NP]; point_grad(ff, pt, n, g);  // grad h = +g (at the arg-max stage)
           double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
           if (phase == 2) {
@@ -411,7 +430,7 @@ struct Inst {
           int jb; const double h = stale_max(cn, ck, i, j, jb);
           if (jb <= j) continue;  // belongs to stage k+1: its owner handles it
           Point pt; point_eval(pk[0], pk[1], fk, BODY[i], pt);
-          const double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)};
+          const double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)};
           double g[NP]; point_grad(fk, pt, n, g);
           double t = W(k + 1, it + I_T + r), z = W(k + 1, it + I_T + R + r), it_;
           if (cand) {  // the owner's candidate, recomputed with the same arithmetic
@@ -607,7 +626,7 @@ struct Inst {
         int jb; double h = plane_row(p, jb);
         double z, it_, res; row_state(it, nobs + 4 + i, k, h, s, z, it_, res, A);
         double sig = z * it_;
-        double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)}, g[NP];
+        double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)}, g[NP];
         point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g
 #pragma unroll
         for (int a = 0; a < NP; ++a)
@@ -1006,6 +1025,25 @@ struct Inst {
     const int it = J(J_CUR) * ITSZ;
     prefetch_stage(k, it, false);
     const double* ci = stage_ptr(k, it); double* c2 = stage_ptr(k, B2);
+    // ring items in consumption order: x bounds (zl, zu) x9, u bounds x5, circle rows (t, z, cx, cy, r), other rows (t, z)
+    const int q_circ = NX + NU, q_rows = q_circ + nobs, q_end = q_rows + 4 + (npl > 0 ? 6 : 0);
+    auto ring_issue = [&](int q) {  // one code path (selects, no per-kind branches): the body is inlined at 20 sites
+      double* d = ring_slot(q);
+      if (q < q_end) {
+        const bool isbox = q < q_circ;
+        const int r = q - q_circ;
+        const int oa = isbox ? (q < NX ? I_ZXL + q : I_ZXU + q) : I_T + r;          // I_ZUL + (q - NX) = I_ZXU + q
+        const int ob = isbox ? (q < NX ? I_ZXU + q : I_ZUU - NX + q) : I_T + R + r;
+        async_copy8(d, &ci[oa << 5]); async_copy8(d + bs, &ci[ob << 5]);
+        if (!isbox && q < q_rows) { async_copy8(d + 2 * bs, circ_ptr(k, r, 0)); async_copy8(d + 3 * bs, circ_ptr(k, r, 1)); async_copy8(d + 4 * bs, circ_ptr(k, r, 2)); }
+      }
+      async_commit();
+    };
+    int rq = 0;  // next ring item
+    auto ring_pop = [&]() -> const double* { async_wait<RING_D - 1>(); return ring_slot(rq); };
+    auto ring_next = [&]() { ring_issue(rq + RING_D); ++rq; };
+#pragma unroll
+    for (int q = 0; q < RING_D; ++q) ring_issue(q);
     const double os = D(D_OS), mu = D(D_MU);
     const double tau = fmax(0.99, 1 - mu);
     MinRatio rp, rd; rp.init(); rd.init();  // fraction to the boundary: primal, dual
@@ -1013,28 +1051,29 @@ struct Inst {
     LogProd lp; lp.init();
     double x[NX], dxv[NX], u[NU], duv[NU];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = ci[(I_X + i) << 5]; dxv[i] = c2[(S_DX + i) << 5]; }
-    double s = ci[(I_S) << 5], dsv = c2[(S_DS) << 5];
+    for (int i = 0; i < NX; ++i) { x[i] = ldg(&ci[(I_X + i) << 5]); dxv[i] = ldg(&c2[(S_DX + i) << 5]); }
+    double s = ldg(&ci[(I_S) << 5]), dsv = ldg(&c2[(S_DS) << 5]);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? ci[(I_U + a) << 5] : 0.0; duv[a] = (k < N) ? c2[(S_DU + a) << 5] : 0.0; }
+    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? ldg(&ci[(I_U + a) << 5]) : 0.0; duv[a] = (k < N) ? ldg(&c2[(S_DU + a) << 5]) : 0.0; }
     double dp[NP];
 #pragma unroll
     for (int a = 0; a < NP; ++a) dp[a] = dxv[POSE2X[a]];
     // cost / boxes
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - c2[(IN_XREF + i) << 5];
+      const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - ldg(&c2[(IN_XREF + i) << 5]);
       fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, id = rcp(d), z = ci[(I_ZXL + i) << 5], dz = mu * id - z - z * id * dxv[i];
+          double d = x[i] - lo, id = rcp(d), z = zl_c, dz = mu * id - z - z * id * dxv[i];
           gphi -= mu * dxv[i] * id; lp.mul(d);
           if (dxv[i] < 0) rp.add(d, -dxv[i]);
           if (dz < 0) rd.add(z, -dz);
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], id = rcp(d), z = ci[(I_ZXU + i) << 5], dz = mu * id - z + z * id * dxv[i];
+          double d = hi - x[i], id = rcp(d), z = zu_c, dz = mu * id - z + z * id * dxv[i];
           gphi += mu * dxv[i] * id; lp.mul(d);
           if (dxv[i] > 0) rp.add(d, dxv[i]);
           if (dz < 0) rd.add(z, -dz);
@@ -1043,36 +1082,38 @@ struct Inst {
     }
     double S1 = os * cfg.S;
     fsum += S1 * s * s; gphi += 2 * S1 * s * dsv;
-    if (k < N) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
+    for (int j = 0; j < NU; ++j) {
+      const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
+      if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - c2[(IN_UREF + j) << 5], dl = u[j] - c2[(IN_ULAST + j) << 5];
+        double e = u[j] - ldg(&c2[(IN_UREF + j) << 5]), dl = u[j] - ldg(&c2[(IN_ULAST + j) << 5]);
         fsum += Rj * e * e + Wj * dl * dl; gphi += (2 * Rj * e + 2 * Wj * dl) * duv[j];
-        double lo = c2[(IN_ULO + j) << 5], hi = c2[(IN_UHI + j) << 5];
+        double lo = ldg(&c2[(IN_ULO + j) << 5]), hi = ldg(&c2[(IN_UHI + j) << 5]);
         if (is_fin(lo)) {
-          double d = u[j] - lo, id = rcp(d), z = ci[(I_ZUL + j) << 5], dz = mu * id - z - z * id * duv[j];
+          double d = u[j] - lo, id = rcp(d), z = zl_c, dz = mu * id - z - z * id * duv[j];
           gphi -= mu * duv[j] * id; lp.mul(d);
           if (duv[j] < 0) rp.add(d, -duv[j]);
           if (dz < 0) rd.add(z, -dz);
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], id = rcp(d), z = ci[(I_ZUU + j) << 5], dz = mu * id - z + z * id * duv[j];
+          double d = hi - u[j], id = rcp(d), z = zu_c, dz = mu * id - z + z * id * duv[j];
           gphi += mu * duv[j] * id; lp.mul(d);
           if (duv[j] > 0) rp.add(d, duv[j]);
           if (dz < 0) rd.add(z, -dz);
         }
       }
-#pragma unroll
-      for (int i = 0; i < NX; ++i) theta += fabs(c2[(S_DFC + i) << 5]);
     }
-    if (term_eq(k)) theta += fabs(x[0] - c2[(IN_XREF + 0) << 5]) + fabs(x[1] - c2[(IN_XREF + 1) << 5]);
-    FK f; f.cp = c2[(S_FK + 0) << 5]; f.sp = c2[(S_FK + 1) << 5];
+    if (k < N) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { f.vr[q] = c2[(S_FK + 2 + q) << 5]; f.vh[q] = c2[(S_FK + 5 + q) << 5]; }
+      for (int i = 0; i < NX; ++i) theta += fabs(ldg(&c2[(S_DFC + i) << 5]));
+    }
+    if (term_eq(k)) theta += fabs(x[0] - ldg(&c2[(IN_XREF + 0) << 5])) + fabs(x[1] - ldg(&c2[(IN_XREF + 1) << 5]));
+    FK f; f.cp = ldg(&c2[(S_FK + 0) << 5]); f.sp = ldg(&c2[(S_FK + 1) << 5]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { f.vr[q] = ldg(&c2[(S_FK + 2 + q) << 5]); f.vh[q] = ldg(&c2[(S_FK + 5 + q) << 5]); }
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
-    auto row_step = [&](int r, double h, double gd_) {
-      double t = ci[(I_T + r) << 5], z = ci[(I_T + R + r) << 5];
+    auto row_step = [&](int r, double h, double gd_, double t, double z) {
       double res = h - s + t;
       double dtv = -res - (gd_ - dsv);
       c2[(S_DT + r) << 5] = dtv;
@@ -1082,9 +1123,11 @@ struct Inst {
       if (dz < 0) rd.add(z, -dz);
     };
     for (int i = 0; i < nobs; ++i) {
-      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+      const double* rb = ring_pop();
+      const double rt = rb[0], rz = rb[bs], ddx = x[0] - rb[2 * bs], ddy = x[1] - rb[3 * bs], rad = rb[4 * bs];
+      ring_next();
       double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
-      row_step(i, (circ(k, i, 2) + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv);
+      row_step(i, (rad + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv, rt, rz);
     }
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
@@ -1095,19 +1138,21 @@ struct Inst {
       double gd_ = 0;
 #pragma unroll
       for (int a = 0; a < NP; ++a) gd_ = fma(g[a], dp[a], gd_);
-      row_step(nobs + m, cfg.self_collision_radius - d, -gd_);
+      const double* rb = ring_pop(); const double rt = rb[0], rz = rb[bs]; ring_next();
+      row_step(nobs + m, cfg.self_collision_radius - d, -gd_, rt, rz);
     }
     if (npl > 0) {
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         Point p; point_eval(x[0], x[1], f, BODY[i], p);
         int jb; double h = plane_row(p, jb);
-        double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)}, g[NP];
+        double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)}, g[NP];
         point_grad(f, p, n, g);
         double gd_ = 0;
 #pragma unroll
         for (int a = 0; a < NP; ++a) gd_ = fma(g[a], dp[a], gd_);
-        row_step(nobs + 4 + i, h, gd_);
+        const double* rb = ring_pop(); const double rt = rb[0], rz = rb[bs]; ring_next();
+        row_step(nobs + 4 + i, h, gd_, rt, rz);
       }
     }
     double log_extra = 0;
@@ -1118,6 +1163,7 @@ struct Inst {
     }
     c2[(S_PART + 0) << 5] = rp.value(tau); c2[(S_PART + 1) << 5] = rd.value(tau); c2[(S_PART + 2) << 5] = gphi; c2[(S_PART + 3) << 5] = theta;
     c2[(S_PART + 4) << 5] = fsum; c2[(S_PART + 5) << 5] = lp.value() + log_extra;
+    async_wait<0>();  // nothing of this item's ring may still be in flight when the thread primes the next one
   }
 
   // Stage k of the results of an instance that left the solve in this round (state ST_FINISH):
@@ -1507,7 +1553,7 @@ struct Inst {
         int jb; double h = plane_row(p, jb);
         double z, it_, res; row(nobs + 4 + i, h, z, it_, res);
         double sig = z * it_;
-        double n[3] = {D(D_PL + 6 * jb + 3), D(D_PL + 6 * jb + 4), D(D_PL + 6 * jb + 5)}, g[NP];
+        double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)}, g[NP];
         point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g
 #pragma unroll
         for (int a = 0; a < NP; ++a)
@@ -1620,9 +1666,11 @@ __device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init
 template <bool REF>
 __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.template eval<REF>(k); }
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
+// doubles of shared memory one thread of the step / trial kernels needs for its row ring
+constexpr int STAGED_RING_DOUBLES = Inst::RING_D * Inst::RING_W;
 template <bool REF>
-__device__ inline void body_step(const SParams& P, int j, int k) {
-  Inst S(P, list_E(P)[j]);
+__device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {
+  Inst S(P, list_E(P)[j]); S.sm = sm; S.bs = bs;
   const int st = S.J(J_STATE);
   if (st == ST_FINISH) S.finish_stage(k);
   else if (st == ST_ACTIVE) S.template step<REF>(k);
@@ -1630,8 +1678,8 @@ __device__ inline void body_step(const SParams& P, int j, int k) {
 template <int NL>
 __device__ inline void body_ctrl_step(const SParams& P, int j, int lane) { Inst S(P, list_E(P)[j]); S.template ctrl_step<NL>(lane); }
 template <bool REF>
-__device__ inline void body_trial(const SParams& P, int j, int k) {
-  Inst S(P, list_T(P)[j]);
+__device__ inline void body_trial(const SParams& P, int j, int k, double* sm, int bs) {
+  Inst S(P, list_T(P)[j]); S.sm = sm; S.bs = bs;
   if (P.fused) S.template trial_eval<REF>(k); else S.trial(k);
 }
 template <int NL>
@@ -1704,10 +1752,11 @@ __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant_
 #endif
 template <bool REF>
 __global__ void __launch_bounds__(128, MMPC_STEP_MINB) staged_step_kernel(const __grid_constant__ SParams P) {
+  extern __shared__ double ring[];  // STAGED_RING_DOUBLES per thread, thread-interleaved
   const int n = P.cnt[0];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_step<REF>(P, (int)(t % n), (int)(t / n));
+    body_step<REF>(P, (int)(t % n), (int)(t / n), ring + threadIdx.x, blockDim.x);
 }
 __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];  // one warp per instance
@@ -1716,10 +1765,11 @@ __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_cons
 }
 template <bool REF>
 __global__ void __launch_bounds__(128, MMPC_TRIAL_MINB) staged_trial_kernel(const __grid_constant__ SParams P) {
+  extern __shared__ double ring[];  // STAGED_RING_DOUBLES per thread, thread-interleaved
   const int n = P.cnt[P.tsel];
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
-    body_trial<REF>(P, (int)(t % n), (int)(t / n));
+    body_trial<REF>(P, (int)(t % n), (int)(t / n), ring + threadIdx.x, blockDim.x);
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[P.tsel];  // one warp per instance

@@ -43,6 +43,8 @@ __device__ __forceinline__ void async_copy16(double* smem_dst, const double* src
 __device__ __forceinline__ void async_commit() { __pipeline_commit(); }
 template <int PENDING> __device__ __forceinline__ void async_wait() { __pipeline_wait_prior(PENDING); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// compiler-only fence: memory operations are not moved across it (no instruction is emitted)
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 }  // namespace mmpc
 #endif
 

@@ -15,3 +15,10 @@ for r in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); out = S.solve_device(d, out=out); e1.record(); torch.cuda.synchronize()
     print("rep", r, "ms", e0.elapsed_time(e1), "converged", int((out["status"] == 0).sum()), "iters sum", int(out["iters"].sum()))
+if os.environ.get("MMPC_PHASES"):
+    S.set_profile(True)
+    out = S.solve_device(d, out=out); torch.cuda.synchronize()
+    pm, pl, rounds = S.phase_times()
+    tot = sum(pm.values())
+    print("phases (ms, launches) over %d rounds, total %.1f ms:" % (rounds, tot),
+          " ".join("%s=%.1f/%d" % (k, pm[k], pl[k]) for k in pm if pl[k]))

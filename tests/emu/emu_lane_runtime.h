@@ -53,5 +53,6 @@ inline void async_copy16(double* dst, const double* src) { dst[0] = src[0]; dst[
 inline void async_commit() {}
 template <int PENDING> inline void async_wait() {}
 inline void prefetch_l2(const void*) {}
+inline void compiler_fence() {}
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 }  // namespace mmpc

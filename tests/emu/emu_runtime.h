@@ -53,6 +53,7 @@ inline unsigned next_instance(unsigned* counter) {
 }
 inline double ldg(const double* p) { return *p; }
 inline int ldg(const int* p) { return *p; }
+inline void compiler_fence() {}
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 }  // namespace mmpc

@@ -39,6 +39,7 @@ static void run_team(const SParams& P, int j, std::vector<char*>& stacks) {
 extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out,
                                      int32_t* rounds_out, int32_t team, int32_t fused, int32_t parts) {
   SParams P; memset(&P, 0, sizeof P);
+  static double row_ring[STAGED_RING_DOUBLES];  // the step / trial row ring of the one emulated thread
   P.cfg = *cfg; P.B = B;
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
   P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
@@ -66,7 +67,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
       for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) { if (ref) body_eval<true>(P, j, k); else body_eval<false>(P, j, k); }
     for (int j = 0; j < nE; ++j) { if (team) run_team(P, j, stacks); else body_solve(P, j); }
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) {
-      if (!parts) { if (ref) body_step<true>(P, j, k); else body_step<false>(P, j, k); }
+      if (!parts) { if (ref) body_step<true>(P, j, k, row_ring, 1); else body_step<false>(P, j, k, row_ring, 1); }
       else if (inst_state(P, list_E(P)[j]) == ST_ACTIVE) body_parts_item(P, list_E(P)[j], k, false);
       else if (inst_state(P, list_E(P)[j]) == ST_FINISH) { Inst F(P, list_E(P)[j]); F.finish_stage(k); }
     }
@@ -75,7 +76,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     P.tsel = tnext;
     int nT = cnt[tnext];
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) {
-      if (!parts) { if (ref) body_trial<true>(P, j, k); else body_trial<false>(P, j, k); }
+      if (!parts) { if (ref) body_trial<true>(P, j, k, row_ring, 1); else body_trial<false>(P, j, k, row_ring, 1); }
       else body_parts_item(P, list_T(P)[j], k, true);
     }
     for (int j = 0; j < nT; ++j) body_ctrl_trial<1>(P, j, 0);
