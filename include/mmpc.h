@@ -84,7 +84,10 @@ typedef struct MmpcConfig {
   int32_t mode;          /* MMPC_MODE_*                                                          */
   int32_t obs_per_stage; /* 0: circles[B][n_obs][3]; 1: circles[B][N+1][n_obs][3] (moving)       */
   int32_t max_iter;      /* 'ipopt.max_iter': 2000 (:280)                                        */
-  int32_t reserved0, reserved1;
+  int32_t terminal_rows_on_sN; /* MMPC_MODE_REFERENCE: 0 = the four terminal self-collision rows are bounded by s[N-1], the
+                                  reference's leaked loop variable (:263-265); 1 = by s[N].  The CPU
+                                  oracle implements both; the GPU solver implements 1 only and reports it in its config. */
+  int32_t reserved1;
   double dt;             /* robot.dt, demo_wholebody_qref.py:10                                  */
   double Qd[9], Pd[9], Rd[5], Wd[5], S; /* diagonals of Q,P,R,W and S (:12-16); setWeight :119   */
   double ulim[2][5];     /* (:17)  rows: lower, upper                                            */
@@ -175,6 +178,42 @@ int mmpc_plant_step(MmpcHandle* h, int32_t B, const double* x, const double* u0,
  * u_ref[b] = the same window of u_glob ([M-1][5] / [B][M-1][5]; NULL -> zeros, :266).  i_star may be NULL. */
 int mmpc_window(MmpcHandle* h, int32_t B, int32_t M, int32_t idx_mask, int32_t shared_ref, const double* x,
                 const double* x_glob, const double* u_glob, double* x_ref, double* u_ref, int32_t* i_star, void* stream);
+
+/* ---- the callers either side of the solve, batched -------------------------- */
+
+/* Batched inverse kinematics: ManipulatorPanda3DoF.inverse_transformation (robot_models/manipulator_3DoF.py:79-133),
+ *     min (x(q) - xt)^2 + (z(q) - zt)^2   s.t.  q1 in [-pi/2, pi/2], q2 in [-3pi/4, 0], q3 in [0, 3pi/2]   (:123)
+ * q_guess [B][3], target [B][3] = (x, y, z) in the arm frame with y == 0 (:99), q_out [B][3]; status[b] (may be
+ * NULL) = 0, or 1 when no q reaches the target (the reference raises ValueError :124-125).  Device pointers. */
+int mmpc_ik(MmpcHandle* h, int32_t B, const double* q_guess, const double* target, double* q_out, int32_t* status,
+            void* stream);
+
+/* Task flag of an episode: Interface.task_flag (interface_wholebody_qref.py:81, :146-228). */
+enum { MMPC_TASK_MOVE = 0, MMPC_TASK_APPROACH = 1, MMPC_TASK_ROTATE = 2, MMPC_TASK_MOVE_FINISH = 3, MMPC_TASK_MANIPULATE = 4,
+       MMPC_TASK_FINISHED = 5 /* 'manipulate finish', robot_status False :223 */, MMPC_TASK_IK_FAILED = 6 };
+
+/* Per-episode arrays of mmpc_episode_update (device pointers, one leading batch axis). */
+typedef struct MmpcEpisodeIO {
+  const double* x;            /* [B][9]    current_state                                                (:134) */
+  const double* pose_target;  /* [B][4]    global_pose_target x y z psi                                 (:20)  */
+  double* traj;               /* [B][M][9] traj_ref of the current phase; rewritten by globalPlanManipulator (:277-297) */
+  int32_t* traj_len;          /* [B]       rows of traj in use                                                  */
+  int32_t* task;              /* [B]       MMPC_TASK_* (in/out)                                                 */
+  uint8_t* flags;             /* [B]       solver flags; bit 0 is set when the episode enters 'approach' (:167) */
+  int32_t* wset;              /* [B] out   weights of this step's solve: 0 = constructor defaults, 1 = 'rotate' set (:176-178),
+                                           2 = 'manipulate' set (:212-215)                                      */
+  int32_t* active;            /* [B] out   1 = solve and step this episode, 0 = finished / IK failed            */
+  double* x_ref;              /* [B][N+1][9] out  local_traj_ref (calcLocalRefTraj :353-396 / calcLocalRefPose :398-410) */
+  double* u_ref;              /* [B][N][5]   out  local_u_ref (identically zero in the reference :266, :296)    */
+  double* local_pose_target;  /* [B][3] out at the manipulate hand-off (:206-210), may be NULL                   */
+  int32_t* ik_status;         /* [B]    out at the manipulate hand-off, may be NULL                              */
+} MmpcEpisodeIO;
+
+/* Interface.stateMachineUpdate (interface_wholebody_qref.py:146-228) for B episodes: phase transitions, the local
+ * reference of the step, the terminal-equality flag, the weight set, and at the move -> manipulate hand-off the
+ * inverse kinematics and the joint-space plan with n_manip = t_manipulate / dt intervals.  M = rows allocated per
+ * episode in io->traj (>= n_manip + 1). */
+int mmpc_episode_update(MmpcHandle* h, int32_t B, int32_t M, int32_t n_manip, const MmpcEpisodeIO* io, void* stream);
 
 /* Phases of the staged solver (one kernel each per round; COMPACT runs twice per round). */
 enum { MMPC_PHASE_COMPACT = 0, MMPC_PHASE_EVAL = 1, MMPC_PHASE_SOLVE = 2, MMPC_PHASE_STEP = 3, MMPC_PHASE_CTRL_STEP = 4,

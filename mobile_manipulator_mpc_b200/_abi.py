@@ -22,7 +22,7 @@ _d = C.c_double
 class MmpcConfig(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("n_obs", C.c_int32), ("n_pl", C.c_int32), ("mode", C.c_int32),
-        ("obs_per_stage", C.c_int32), ("max_iter", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("obs_per_stage", C.c_int32), ("max_iter", C.c_int32), ("terminal_rows_on_sN", C.c_int32), ("reserved1", C.c_int32),
         ("dt", _d),
         ("Qd", _d * 9), ("Pd", _d * 9), ("Rd", _d * 5), ("Wd", _d * 5), ("S", _d),
         ("ulim", (_d * 5) * 2), ("xlim", (_d * 9) * 2), ("dulim", (_d * 5) * 2),
@@ -38,6 +38,16 @@ class MmpcBatchIn(C.Structure):
 
 class MmpcBatchOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("U", "X", "s", "cost", "kkt", "iters", "status")]
+
+
+TASK_MOVE, TASK_APPROACH, TASK_ROTATE, TASK_MOVE_FINISH, TASK_MANIPULATE, TASK_FINISHED, TASK_IK_FAILED = range(7)
+TASK_NAMES = ("move", "approach", "rotate", "move finish", "manipulate", "manipulate finish", "ik failed")
+
+
+class MmpcEpisodeIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("x", "pose_target", "traj", "traj_len", "task", "flags", "wset", "active", "x_ref", "u_ref",
+                 "local_pose_target", "ik_status")]
 
 
 def default_config(N=20, dt=0.1, n_obs=3, n_pl=3, mode=MODE_REFERENCE):

@@ -12,7 +12,7 @@ from . import _abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMPC_LIB") or os.path.join(_PKG, "libmmpc_b200.so")  # MMPC_LIB: A/B builds of the same sources
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_solver.cuh", "mmpc_lane.cuh", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_parts.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_solver.cuh", "mmpc_lane.cuh", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_parts.cuh", "mmpc_episode.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -62,6 +62,8 @@ def lib():
     L.mmpc_eval_model.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, vp]
     L.mmpc_shift.argtypes = [vp, i32, dp, dp, vp]
     L.mmpc_plant_step.argtypes = [vp, i32, dp, dp, dp, vp]
+    L.mmpc_ik.argtypes = [vp, i32, dp, dp, dp, vp, vp]
+    L.mmpc_episode_update.argtypes = [vp, i32, i32, i32, C.POINTER(_abi.MmpcEpisodeIO), vp]
     L.mmpc_launch_count.argtypes = [vp]
     L.mmpc_launch_count.restype = i64
     L.mmpc_occupancy.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
@@ -81,4 +83,4 @@ def check(rc):
 
 EXPORTS = ("mmpc_version", "mmpc_error_string", "mmpc_default_config", "mmpc_create", "mmpc_destroy",
            "mmpc_set_weights", "mmpc_set_kernel", "mmpc_set_profile", "mmpc_phase_times", "mmpc_workspace_bytes", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
-           "mmpc_plant_step", "mmpc_window", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")
+           "mmpc_plant_step", "mmpc_window", "mmpc_ik", "mmpc_episode_update", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")

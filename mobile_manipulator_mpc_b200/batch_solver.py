@@ -40,6 +40,7 @@ class BatchSolver:
             cfg.obs_per_stage = int(bool(obs_per_stage))
         for k, v in overrides.items():
             setattr(cfg, k, v)
+        cfg.terminal_rows_on_sN = 1   # the variant the kernels implement (include/mmpc.h)
         self.cfg = cfg
         self.B_max = int(B_max)
         self.device = int(device)
@@ -247,3 +248,26 @@ class BatchSolver:
         check(lib().mmpc_plant_step(self._h, int(x.shape[0]), C.c_void_p(x.data_ptr()), C.c_void_p(u0.data_ptr()),
                                     C.c_void_p(xn.data_ptr()), stream))
         return xn
+
+    def ik(self, q_guess, target):
+        """Batched inverse_transformation (robot_models/manipulator_3DoF.py:79-133) on device: q_guess [B,3],
+        target [B,3] = (x, 0, z) in the arm frame; returns (q [B,3], status [B] int32: 0 reached, 1 unreachable)."""
+        import torch
+        B = int(q_guess.shape[0])
+        q = torch.empty((B, 3), dtype=torch.float64, device=q_guess.device)
+        st = torch.empty(B, dtype=torch.int32, device=q_guess.device)
+        stream = C.c_void_p(torch.cuda.current_stream(q_guess.device).cuda_stream)
+        check(lib().mmpc_ik(self._h, B, C.c_void_p(q_guess.contiguous().data_ptr()), C.c_void_p(target.contiguous().data_ptr()),
+                            C.c_void_p(q.data_ptr()), C.c_void_p(st.data_ptr()), stream))
+        return q, st
+
+    def episode_update(self, io, B, M, n_manip):
+        """Interface.stateMachineUpdate for B episodes (mmpc_episode_update); ``io``: dict of device tensors named like
+        the fields of MmpcEpisodeIO (missing optional ones -> NULL)."""
+        import torch
+        e = _abi.MmpcEpisodeIO()
+        for name, _ in _abi.MmpcEpisodeIO._fields_:
+            t = io.get(name)
+            setattr(e, name, None if t is None else t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(io["x"].device).cuda_stream)
+        check(lib().mmpc_episode_update(self._h, int(B), int(M), int(n_manip), C.byref(e), stream))

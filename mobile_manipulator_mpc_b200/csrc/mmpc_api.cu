@@ -15,6 +15,7 @@
 #include "mmpc_staged.cuh"
 #include "mmpc_team.cuh"
 #include "mmpc_parts.cuh"
+#include "mmpc_episode.cuh"
 
 using namespace mmpc;
 
@@ -115,6 +116,7 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   if (!h) return MMPC_ERR_ARG;
   memset(h, 0, sizeof *h);
   h->cfg = *cfg; h->device = device; h->B_max = B_max; h->sm_count = prop.multiProcessorCount;
+  h->cfg.terminal_rows_on_sN = 1;  // the only variant the kernels implement (include/mmpc.h)
   int N = cfg->N;
   h->SP = N + 1; h->KP = ((N + 1 + 3) / 4) * 4; h->R = cfg->n_obs + 4 + (cfg->n_pl > 0 ? 6 : 0);
   h->smem_bytes = (size_t)smem_doubles(N) * sizeof(double);
@@ -286,7 +288,9 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     long long items = ub * (N + 1);
     int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
     int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
+    static const int team_cap = getenv("MMPC_TEAM_GRID") ? atoi(getenv("MMPC_TEAM_GRID")) : 0;  // A/B: blocks per SM of the team kernel (0: one block per 8 instances)
     int gt = (int)((ub * 16 + 127) / 128);
+    if (team_cap > 0 && gt > team_cap * h->sm_count) gt = team_cap * h->sm_count;
     int gw = (int)((ub * 32 + 127) / 128 < cap ? (ub * 32 + 127) / 128 : cap);  // one warp per instance
     if (gw < 1) gw = 1;
     int gtile = (int)((items + 31) / 32 < 8 * cap ? (items + 31) / 32 : 8 * cap);
@@ -589,6 +593,31 @@ extern "C" int mmpc_window(MmpcHandle* h, int32_t B, int32_t M, int32_t idx_mask
   CK(cudaSetDevice(h->device));
   window_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, h->cfg.N, M, idx_mask, shared_ref, x, x_glob, u_glob,
                                                                     x_ref, u_ref, i_star);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_ik(MmpcHandle* h, int32_t B, const double* q_guess, const double* target, double* q_out, int32_t* status,
+                       void* stream) {
+  if (!h || !q_guess || !target || !q_out || B < 0) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  ik_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, q_guess, target, q_out, status);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MMPC_OK;
+}
+
+extern "C" int mmpc_episode_update(MmpcHandle* h, int32_t B, int32_t M, int32_t n_manip, const MmpcEpisodeIO* io, void* stream) {
+  if (!h || !io || B < 0 || n_manip < 1 || M < n_manip + 1) return MMPC_ERR_ARG;
+  if (!io->x || !io->pose_target || !io->traj || !io->traj_len || !io->task || !io->flags || !io->wset || !io->active ||
+      !io->x_ref || !io->u_ref)
+    return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;
+  CK(cudaSetDevice(h->device));
+  EpisodeArgs A; A.B = B; A.N = h->cfg.N; A.M = M; A.n_manip = n_manip; A.io = *io;
+  episode_update_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A);
   CK(cudaGetLastError());
   h->launches += 1;
   return MMPC_OK;

@@ -189,3 +189,26 @@ def approach_instance(N=20, dt=0.1):
     return dict(N=N, dt=dt, n_obs=3, n_pl=3, obs_per_stage=0, x_init=x[None], x_ref=xr[None], u_ref=ur[None],
                 u_last=np.zeros((1, N, 5)), circles=DEMO_CIRCLES[None].copy(), planes=planes[None].copy(),
                 n_pl_inst=np.full(1, 3, np.int32), flags=np.ones(1, np.uint8))
+
+
+def episode_batch(B, seed=7):
+    """Starts and targets of B "push the button" episodes: episode 0 is demo scenario 1 and
+    episode 1 demo scenario 2 exactly (demo_wholebody_qref.py:17-44); the others perturb the start pose and joint
+    angles of those two.  Returns x_start [B,9], global_pose_target [B,4], circles [B,3,3], planes [B,3,6] (scenario 2
+    padded by repeating its last plane, which leaves the max over the planes unchanged), n_pl_inst [B]."""
+    rng = np.random.default_rng(seed)
+    xs = np.empty((B, 9)); gps = np.empty((B, 4)); planes = np.zeros((B, 3, 6)); npl = np.empty(B, np.int32)
+    for b in range(B):
+        x_start, tgt, pl = demo_scenario(1 + (b % 2))
+        x = x_start.copy()
+        if b >= 2:
+            x[0:2] += rng.uniform(-0.5, 0.5, 2)
+            x[2] += rng.uniform(-0.5, 0.5)
+            x[6] += rng.uniform(0.0, 0.3)
+            x[7] = min(0.0, x[7] + rng.uniform(0.0, 0.4))
+            x[8] = max(0.0, x[8] - rng.uniform(0.0, 0.4))
+        xs[b], gps[b] = x, tgt
+        planes[b, :pl.shape[0]] = pl
+        planes[b, pl.shape[0]:] = pl[-1]
+        npl[b] = pl.shape[0]
+    return xs, gps, np.tile(DEMO_CIRCLES, (B, 1, 1)), planes, npl

@@ -227,6 +227,7 @@ static void build_rows(Work* w) {
     RowDesc* r = w->rows + (size_t)m * w->rmax; int n = 0;
     for (int i = 0; i < w->nobs; ++i) r[n++] = (RowDesc){ROW_CIRCLE, i, 0};
     int term_on_prev = (w->mode == MMPC_MODE_REFERENCE); /* quirk 3, :263-265 */
+    if (w->cfg->terminal_rows_on_sN) term_on_prev = 0; /* rows on s_N: the variant the GPU's reference mode solves */
     if (m < N || !term_on_prev)
       for (int i = 0; i < 4; ++i) r[n++] = (RowDesc){ROW_SELF, i, 0};
     if (m == N - 1 && term_on_prev)

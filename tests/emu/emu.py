@@ -22,7 +22,27 @@ def lib():
         _LIB.lane.mmpc_emu_lane_solve.argtypes = _LIB.mmpc_emu_solve.argtypes
         _LIB.staged = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_staged.so"))
         _LIB.staged.mmpc_emu_staged_solve.argtypes = _LIB.mmpc_emu_solve.argtypes + [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]
+        _LIB.staged.mmpc_emu_ik.argtypes = [C.c_int32] + [C.c_void_p] * 4
+        _LIB.staged.mmpc_emu_episode_update.argtypes = [C.c_int32] * 4 + [C.POINTER(_abi.MmpcEpisodeIO)]
     return _LIB
+
+
+def ik(q_guess, target):
+    """csrc/mmpc_episode.cuh::ik_solve on the CPU; q_guess [B,3], target [B,3] -> (q [B,3], status [B])."""
+    q_guess = np.ascontiguousarray(q_guess, dtype=np.float64); target = np.ascontiguousarray(target, dtype=np.float64)
+    B = q_guess.shape[0]
+    q = np.zeros((B, 3)); st = np.zeros(B, np.int32)
+    assert lib().staged.mmpc_emu_ik(B, _abi.ptr(q_guess), _abi.ptr(target), _abi.ptr(q), _abi.ptr(st)) == 0
+    return q, st
+
+
+def episode_update(N, M, n_manip, io):
+    """csrc/mmpc_episode.cuh::episode_update on the CPU; ``io``: dict of NumPy arrays named like MmpcEpisodeIO (in place)."""
+    e = _abi.MmpcEpisodeIO()
+    for name, _ in _abi.MmpcEpisodeIO._fields_:
+        a = io.get(name)
+        setattr(e, name, None if a is None else a.ctypes.data)
+    assert lib().staged.mmpc_emu_episode_update(N, io["x"].shape[0], M, n_manip, C.byref(e)) == 0
 
 
 def solve(batch, cfg, kernel="warp"):

@@ -7,6 +7,7 @@
 #include "emu_lane_runtime.h"
 #include "../../mobile_manipulator_mpc_b200/csrc/mmpc_team.cuh"
 #include "../../mobile_manipulator_mpc_b200/csrc/mmpc_parts.cuh"
+#include "../../mobile_manipulator_mpc_b200/csrc/mmpc_episode.cuh"
 
 namespace mmpc { EmuTeam* g_team = nullptr; }
 using namespace mmpc;
@@ -86,5 +87,19 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   for (int i = 0; i < 16; ++i) free(stacks[i]);
   delete tw; g_team = nullptr;
   if (rounds_out) *rounds_out = r + 1;
+  return 0;
+}
+
+// csrc/mmpc_episode.cuh on the CPU: the bodies of ik_kernel and episode_update_kernel, one episode at a time (host pointers)
+extern "C" int mmpc_emu_ik(int32_t B, const double* q_guess, const double* target, double* q_out, int32_t* status) {
+  for (int b = 0; b < B; ++b) {
+    int rc = ik_solve(q_guess + (size_t)b * 3, target[(size_t)b * 3 + 0], target[(size_t)b * 3 + 2], q_out + (size_t)b * 3);
+    if (status) status[b] = rc;
+  }
+  return 0;
+}
+extern "C" int mmpc_emu_episode_update(int32_t N, int32_t B, int32_t M, int32_t n_manip, const MmpcEpisodeIO* io) {
+  EpisodeArgs A; A.B = B; A.N = N; A.M = M; A.n_manip = n_manip; A.io = *io;
+  for (int b = 0; b < B; ++b) episode_update(A, b);
   return 0;
 }
