@@ -65,3 +65,32 @@ def test_terminal_xy_equality_flag(kernel):
     free = dict(b); free["flags"] = None                                            # and it binds: without it x_N differs
     f = emu.solve(free, cfg, kernel=kernel)
     assert np.abs(f["X"][0, -1, :2] - b["x_ref"][0, -1, :2]).max() > 1e-3
+
+
+def _terminal_rows_instance():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_terminal_rows_instance.npz"))
+    Q = np.array([25.0, 25, 0, 0, 0, 5, 5, 5, 5])
+    return dict(N=20, dt=0.1, n_obs=3, n_pl=3, obs_per_stage=0, x_init=g["x_init"][None], x_ref=g["x_ref"][None], u_ref=np.zeros((1, 20, 5)),
+                u_last=g["u_last"][None], circles=g["circles"][None], planes=g["planes"][None], n_pl_inst=np.array([int(g["n_pl"])], np.int32),
+                flags=np.zeros(1, np.uint8), Qd=Q, Pd=Q)
+
+
+def test_reference_mode_terminal_rows_variant_is_what_the_kernels_solve():
+    """SURVEY.md 8(a) row 9 on a path-sensitive instance (found in a closed loop next to demo scenario 2's aerial obstacle):
+    the reference-mode NLP with the terminal self-collision rows bounded by s[N-1] (the reference to the letter) and by s[N]
+    (what the kernels implement, cfg.terminal_rows_on_sN = 1) are both solved by the oracle; none of those rows is active,
+    yet the two barrier paths end in different local optima of the non-smooth NLP.  The kernel source must reproduce the
+    s[N] variant iterate for iterate, and both optima must be stationary points of the dense restated NLP."""
+    from oracle import nlp
+    b = _terminal_rows_instance()
+    lit = solver.solve(b, cfg=solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=0))
+    var = solver.solve(b, cfg=solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=1))
+    ker = emu.solve(b, solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=1), kernel="staged")
+    assert lit["status"][0] == 0 and var["status"][0] == 0 and ker["status"][0] == 0
+    assert abs(lit["cost"][0] - 457.41613461) < 1e-5 and abs(var["cost"][0] - 475.98075895) < 1e-5   # two optima
+    assert abs(ker["cost"][0] - var["cost"][0]) < 1e-5 * var["cost"][0]
+    assert np.abs(ker["U"][0, 0] - var["U"][0, 0]).max() < 1e-4 and abs(int(ker["iters"][0]) - int(var["iters"][0])) <= 2
+    P = nlp.from_batch(b, 0, "reference")   # the dense restatement has the rows on s[N-1]; both points are feasible for it
+    for sol in (lit, var):
+        assert P.violation(P.pack(sol["X"][0], sol["U"][0], sol["s"][0])) < 1e-6
