@@ -84,9 +84,9 @@ typedef struct MmpcConfig {
   int32_t mode;          /* MMPC_MODE_*                                                          */
   int32_t obs_per_stage; /* 0: circles[B][n_obs][3]; 1: circles[B][N+1][n_obs][3] (moving)       */
   int32_t max_iter;      /* 'ipopt.max_iter': 2000 (:280)                                        */
-  int32_t terminal_rows_on_sN; /* MMPC_MODE_REFERENCE: 0 = the four terminal self-collision rows are bounded by s[N-1], the
-                                  reference's leaked loop variable (:263-265); 1 = by s[N].  The CPU
-                                  oracle implements both; the GPU solver implements 1 only and reports it in its config. */
+  int32_t terminal_rows_on_sN; /* MMPC_MODE_REFERENCE: 0 (default) = the four terminal self-collision rows are bounded by s[N-1],
+                                  the reference's leaked loop variable (:263-265); 1 = by s[N] (what a
+                                  reader of the reference would expect).  Same optimum unless the barrier path forks. */
   int32_t reserved1;
   double dt;             /* robot.dt, demo_wholebody_qref.py:10                                  */
   double Qd[9], Pd[9], Rd[5], Wd[5], S; /* diagonals of Q,P,R,W and S (:12-16); setWeight :119   */

@@ -40,7 +40,6 @@ class BatchSolver:
             cfg.obs_per_stage = int(bool(obs_per_stage))
         for k, v in overrides.items():
             setattr(cfg, k, v)
-        cfg.terminal_rows_on_sN = 1   # the variant the kernels implement (include/mmpc.h)
         self.cfg = cfg
         self.B_max = int(B_max)
         self.device = int(device)

@@ -116,7 +116,6 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   if (!h) return MMPC_ERR_ARG;
   memset(h, 0, sizeof *h);
   h->cfg = *cfg; h->device = device; h->B_max = B_max; h->sm_count = prop.multiProcessorCount;
-  h->cfg.terminal_rows_on_sN = 1;  // the only variant the kernels implement (include/mmpc.h)
   int N = cfg->N;
   h->SP = N + 1; h->KP = ((N + 1 + 3) / 4) * 4; h->R = cfg->n_obs + 4 + (cfg->n_pl > 0 ? 6 : 0);
   h->smem_bytes = (size_t)smem_doubles(N) * sizeof(double);
@@ -282,6 +281,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
   const int LAG = 2, cap = h->sm_count * cap_mult;
   const bool ref = cfg.mode == MMPC_MODE_REFERENCE;
+  const bool q3 = ref && cfg.terminal_rows_on_sN == 0;  // terminal self-collision rows on s[N-1]
   long long ub = B;  // upper bound of the active instances (the lists only shrink)
   int r = 0;
   for (;; ++r) {
@@ -305,7 +305,9 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
       if (ref) staged_eval_kernel<true><<<gs, 128, 0, st>>>(P); else staged_eval_kernel<false><<<gs, 128, 0, st>>>(P);
     }
     MARK(MMPC_PHASE_SOLVE);
-    if (P.team) staged_solve_team_kernel<<<gt, 128, 0, st>>>(P);
+    if (P.team) {
+      if (q3) staged_solve_team_kernel<true><<<gt, 128, 0, st>>>(P); else staged_solve_team_kernel<false><<<gt, 128, 0, st>>>(P);
+    }
     else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
     MARK(MMPC_PHASE_STEP);
     static const long long parts_tiles = getenv("MMPC_PARTS_TILES") ? atoll(getenv("MMPC_PARTS_TILES")) : -1;  // A/B knob

@@ -159,6 +159,14 @@ struct Inst {
     return NC ? ldg(p) : *p;
   }
   __device__ __forceinline__ void load_npl() { npl = J(J_NPL); }
+  // MMPC_MODE_REFERENCE to the letter (controllers/mpc_wholebody_qref.py:263-265): the four terminal
+  // self-collision rows  h_m(x_N) <= s[N-1]  (the reference's leaked loop variable), not s[N].  Thread (instance, N) still
+  // evaluates them (their pose terms belong to x_N), but with the slack of stage N-1, and their slack-column sums
+  //     abar = H[pose(x_N)][s_{N-1}],  cbar = sum sigma,  gbar = -(sum sigma res) - mu sum 1/t
+  // go to the v-slots of stage N's record (Q_BV, Q_HVV, Q_GA/GB[SGY_V]: stage N has no v), from where the Riccati sweep
+  // folds them into the slack column of stage N-1 (mmpc_team.cuh).  The stationarity residual of s[N-1] is the sum of two
+  // threads' terms; they are exchanged through the unused defect slots of stage N (S_DFC + 0 / + 1).
+  __device__ __forceinline__ bool q3() const { return cfg.mode == MMPC_MODE_REFERENCE && cfg.terminal_rows_on_sN == 0; }
   // plane data (point, normal) of this instance: written by init only, so the phase kernels read it non-coherently
   // (init itself, which has just written it, passes NC = false)
   template <bool NC = true>
@@ -251,7 +259,8 @@ struct Inst {
       for (int m = 0; m < 4; ++m) {
         Point p; point_eval(x[0], x[1], f, SELFD[m], p);
         double h = cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]);
-        W(k, I_T + nobs + m) = h; hmax = fmax(hmax, h);
+        W(k, I_T + nobs + m) = h;
+        if (!(k == N && q3())) hmax = fmax(hmax, h);  // the terminal rows of the literal reference NLP are bounded by s[N-1]: they do not lift s[N]
       }
       if (npl > 0) {
 #pragma unroll 1
@@ -279,7 +288,11 @@ struct Inst {
       double s = fmax(0.0, hmax + 1e-2);
       W(k, I_S) = s;
       gmax = fmax(gmax, fabs(2 * cfg.S * s));
-      for (int r = 0; r < R; ++r) { W(k, I_T + r) = s - W(k, I_T + r); W(k, I_T + R + r) = 1.0; }
+      for (int r = 0; r < R; ++r) {
+        // (x_N = x_{N-1} in the starting point, so s[N-1] already clears the terminal rows by the same 1e-2)
+        const double sr = (k == N && q3() && r >= nobs && r < nobs + 4) ? W(k - 1, I_S) : s;
+        W(k, I_T + r) = sr - W(k, I_T + r); W(k, I_T + R + r) = 1.0;
+      }
     }
     D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
     D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
@@ -303,11 +316,7 @@ struct Inst {
   // couple x_k with v_k = s_{k+1} (Q_BV) in the augmented Riccati form.  Kept out of line: it only
   // runs in reference mode and needs forward kinematics at three stages.
   //   phase 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step
-  // NOT reproduced here: quirk 3, the terminal self-collision rows bounded by s_{N-1}
-  // instead of s_N -- they stay on s_N.  The two NLPs have the same optimum unless one of those four rows is
-  // active at stage N (the end point within 5 cm of a check point, which only happens for check point 1 =
-  // half of joint 2's WORLD position, i.e. within about a metre of the world origin); the CPU restatement
-  // implements the literal form and the reference-mode parity tests compare against it.
+  // (Quirk 3, the terminal self-collision rows bounded by s_{N-1}, is handled where those rows are evaluated: see q3().)
   struct StaleIO {
     RowAcc* A; double* bv;                   // phase 0/1: accumulators of stage k; bv[6] = H[pose][v]
     double theta, logsum; bool ok;           // merit ingredients (phase 1, 2)
@@ -599,12 +608,20 @@ struct Inst {
       A.a[0] += sig * nx; A.a[1] += sig * ny; A.gA[0] -= cb * nx; A.gA[1] -= cb * ny;
       A.gB[0] -= it_ * nx; A.gB[1] -= it_ * ny; A.st[0] -= z * nx; A.st[1] -= z * ny;
     }
+    const bool q3n = REF && k == N && q3();  // terminal self-collision rows on s[N-1]
+    double s_self = s, sv_c = 0, sv_b0 = 0, sv_b1 = 0, sv_z = 0, sv_a[NP] = {0, 0, 0, 0, 0, 0};
+    if (q3n) {
+      s_self = W(N - 1, it + I_S);
+      sv_c = A.csum; sv_b0 = A.be0; sv_b1 = A.be1; sv_z = A.zrows; A.csum = A.be0 = A.be1 = A.zrows = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { sv_a[a] = A.a[a]; A.a[a] = 0; }
+    }
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {  // self collision :219-222
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
       double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2);
       double h = cfg.self_collision_radius - d2 * inv;
-      double z, it_, res; row_state(it, nobs + m, k, h, s, z, it_, res, A);
+      double z, it_, res; row_state(it, nobs + m, k, h, s_self, z, it_, res, A);
       double sig = z * it_, zd = z * inv;
       double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
       point_grad(f, p, n, g);  // grad h = -g
@@ -618,6 +635,12 @@ struct Inst {
       double cb = sig * res;
 #pragma unroll
       for (int a = 0; a < NP; ++a) { A.a[a] += sig * g[a]; A.gA[a] -= cb * g[a]; A.gB[a] -= it_ * g[a]; A.st[a] -= z * g[a]; }
+    }
+    double q3_c = 0, q3_b0 = 0, q3_b1 = 0, q3_z = 0, q3_a[NP] = {0, 0, 0, 0, 0, 0};
+    if (q3n) {  // the sums of the four rows are the slack column they add to stage N-1; stage N's own column goes on without them
+      q3_c = A.csum; q3_b0 = A.be0; q3_b1 = A.be1; q3_z = A.zrows; A.csum = sv_c; A.be0 = sv_b0; A.be1 = sv_b1; A.zrows = sv_z;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { q3_a[a] = A.a[a]; A.a[a] = sv_a[a]; }
     }
     if (npl > 0) {
 #pragma unroll 1
@@ -648,16 +671,19 @@ struct Inst {
     Qw(k, Q_C) = S2 + A.csum;
     Qw(k, Q_GA + SGY_S) = S2 * s - A.be0;
     Qw(k, Q_GB + SGY_S) = -A.be1;
-    Qw(k, Q_HVV) = 0; Qw(k, Q_GA + SGY_V) = 0; Qw(k, Q_GB + SGY_V) = 0;
+    Qw(k, Q_HVV) = q3_c; Qw(k, Q_GA + SGY_V) = -q3_b0; Qw(k, Q_GB + SGY_V) = -q3_b1;
 #pragma unroll
     for (int a = 0; a < NP; ++a) {
-      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = bv[a];
+      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = q3n ? q3_a[a] : bv[a];
       Qw(k, Q_GA + POSE2X[a]) = A.gA[a]; Qw(k, Q_GB + POSE2X[a]) = A.gB[a];
       if (k >= 1) es = fmax(es, fabs(A.st[a]));
     }
 #pragma unroll
     for (int e = 0; e < 21; ++e) Qw(k, Q_HP + e) = A.H[e];
-    es = fmax(es, fabs(S2 * s - A.zrows));
+    if (REF && q3() && k >= N - 1) {  // d/ds[N-1] of the Lagrangian: this thread's share, summed in the solve kernel
+      if (k == N) { W2(N, S_DFC + 0) = q3_z; es = fmax(es, fabs(S2 * s - A.zrows)); }
+      else W2(N, S_DFC + 1) = S2 * s - A.zrows;
+    } else es = fmax(es, fabs(S2 * s - A.zrows));
     W2(k, S_PART + 0) = es; W2(k, S_PART + 1) = A.prim; W2(k, S_PART + 2) = A.chi; W2(k, S_PART + 3) = A.clo;
     W2(k, S_PART + 4) = sum_lam; W2(k, S_PART + 5) = A.sumz; W2(k, S_PART + 6) = (double)A.nz; W2(k, S_PART + 7) = (double)n_eq;
   }
@@ -1113,9 +1139,10 @@ struct Inst {
 #pragma unroll
     for (int q = 0; q < 3; ++q) { f.vr[q] = ldg(&c2[(S_FK + 2 + q) << 5]); f.vh[q] = ldg(&c2[(S_FK + 5 + q) << 5]); }
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
+    double s_cur = s, ds_cur = dsv;  // slack (and its step) the rows are bounded by
     auto row_step = [&](int r, double h, double gd_, double t, double z) {
-      double res = h - s + t;
-      double dtv = -res - (gd_ - dsv);
+      double res = h - s_cur + t;
+      double dtv = -res - (gd_ - ds_cur);
       c2[(S_DT + r) << 5] = dtv;
       double itv = rcp(t), dz = (mu - z * (t + dtv)) * itv;
       theta += fabs(res); gphi -= mu * dtv * itv; lp.mul(t);
@@ -1129,6 +1156,7 @@ struct Inst {
       double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
       row_step(i, (rad + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv, rt, rz);
     }
+    if (REF && k == N && q3()) { s_cur = W(N - 1, it + I_S); ds_cur = W2(N - 1, S_DS); }  // terminal rows on s[N-1]
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
@@ -1141,6 +1169,7 @@ struct Inst {
       const double* rb = ring_pop(); const double rt = rb[0], rz = rb[bs]; ring_next();
       row_step(nobs + m, cfg.self_collision_radius - d, -gd_, rt, rz);
     }
+    s_cur = s; ds_cur = dsv;
     if (npl > 0) {
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
@@ -1495,15 +1524,16 @@ struct Inst {
       Qw(k, Q_HUU + j) = Hd; Qw(k, Q_GA + SGY_U + j) = gA; Qw(k, Q_GB + SGY_U + j) = gB;
     }
     // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
+    double s_cur = s;  // slack the rows are bounded by (s[N-1] for the terminal self-collision rows of the literal reference NLP)
     auto row = [&](int r, double h, double& z, double& it_, double& res) {
       double t = ldg(&ci[(I_T + r) << 5]), dtv = ldg(&c2[(S_DT + r) << 5]);
       z = ldg(&ci[(I_T + R + r) << 5]);
-      double tt = fmax(fma(alpha, dtv, t), s - h);  // slack reset (Nocedal & Wright 19.30)
+      double tt = fmax(fma(alpha, dtv, t), s_cur - h);  // slack reset (Nocedal & Wright 19.30)
       double dz = (mu - z * (t + dtv)) * rcp(t);
       it_ = rcp(tt);
       z = zclamp(z + ad * dz, mu, it_);
       cj[(I_T + r) << 5] = tt; cj[(I_T + R + r) << 5] = z;
-      res = h - s + tt;
+      res = h - s_cur + tt;
       theta += fabs(res);
       if (tt <= 0) ok = false; else lp.mul(tt);
       A.prim = fmax(A.prim, fabs(res));
@@ -1526,6 +1556,14 @@ struct Inst {
       A.a[0] += sig * nx; A.a[1] += sig * ny; A.gA[0] -= cb * nx; A.gA[1] -= cb * ny;
       A.gB[0] -= it_ * nx; A.gB[1] -= it_ * ny; A.st[0] -= z * nx; A.st[1] -= z * ny;
     }
+    const bool q3n = REF && k == N && q3();  // terminal self-collision rows on s[N-1]
+    double sv_c = 0, sv_b0 = 0, sv_b1 = 0, sv_z = 0, sv_a[NP] = {0, 0, 0, 0, 0, 0};
+    if (q3n) {
+      s_cur = fma(alpha, W2(N - 1, S_DS), W(N - 1, it + I_S));  // candidate s[N-1], as thread N-1 forms it
+      sv_c = A.csum; sv_b0 = A.be0; sv_b1 = A.be1; sv_z = A.zrows; A.csum = A.be0 = A.be1 = A.zrows = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { sv_a[a] = A.a[a]; A.a[a] = 0; }
+    }
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {  // self collision :219-222
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
@@ -1545,6 +1583,13 @@ struct Inst {
       double cb = sig * res;
 #pragma unroll
       for (int a = 0; a < NP; ++a) { A.a[a] += sig * g[a]; A.gA[a] -= cb * g[a]; A.gB[a] -= it_ * g[a]; A.st[a] -= z * g[a]; }
+    }
+    double q3_c = 0, q3_b0 = 0, q3_b1 = 0, q3_z = 0, q3_a[NP] = {0, 0, 0, 0, 0, 0};
+    if (q3n) {
+      s_cur = s;
+      q3_c = A.csum; q3_b0 = A.be0; q3_b1 = A.be1; q3_z = A.zrows; A.csum = sv_c; A.be0 = sv_b0; A.be1 = sv_b1; A.zrows = sv_z;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { q3_a[a] = A.a[a]; A.a[a] = sv_a[a]; }
     }
     if (npl > 0) {
 #pragma unroll 1
@@ -1576,16 +1621,19 @@ struct Inst {
     Qw(k, Q_C) = S2 + A.csum;
     Qw(k, Q_GA + SGY_S) = S2 * s - A.be0;
     Qw(k, Q_GB + SGY_S) = -A.be1;
-    Qw(k, Q_HVV) = 0; Qw(k, Q_GA + SGY_V) = 0; Qw(k, Q_GB + SGY_V) = 0;
+    Qw(k, Q_HVV) = q3_c; Qw(k, Q_GA + SGY_V) = -q3_b0; Qw(k, Q_GB + SGY_V) = -q3_b1;
 #pragma unroll
     for (int a = 0; a < NP; ++a) {
-      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = bv[a];
+      Qw(k, Q_A + a) = A.a[a]; Qw(k, Q_BV + a) = q3n ? q3_a[a] : bv[a];
       Qw(k, Q_GA + POSE2X[a]) = A.gA[a]; Qw(k, Q_GB + POSE2X[a]) = A.gB[a];
       if (k >= 1) es = fmax(es, fabs(A.st[a]));
     }
 #pragma unroll
     for (int e = 0; e < 21; ++e) Qw(k, Q_HP + e) = A.H[e];
-    es = fmax(es, fabs(S2 * s - A.zrows));
+    if (REF && q3() && k >= N - 1) {  // d/ds[N-1] of the Lagrangian: this thread's share, summed in the solve kernel
+      if (k == N) { W2(N, S_DFC + 0) = q3_z; es = fmax(es, fabs(S2 * s - A.zrows)); }
+      else W2(N, S_DFC + 1) = S2 * s - A.zrows;
+    } else es = fmax(es, fabs(S2 * s - A.zrows));
     c2[(S_PART + 0) << 5] = es; c2[(S_PART + 1) << 5] = A.prim; c2[(S_PART + 2) << 5] = A.chi; c2[(S_PART + 3) << 5] = A.clo;
     c2[(S_PART + 4) << 5] = sum_lam; c2[(S_PART + 5) << 5] = A.sumz; c2[(S_PART + 6) << 5] = (double)A.nz; c2[(S_PART + 7) << 5] = (double)n_eq;
     bool fin = ok && (fsum == fsum) && (theta == theta);

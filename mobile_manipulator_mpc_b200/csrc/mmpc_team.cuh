@@ -133,11 +133,18 @@ struct Team {
   }
 
   // Backward sweep.  Returns 0, or 1 on a non-positive pivot (wrong inertia).
+  template <bool Q3>
   __device__ int riccati(double reg, double mu, int it) {
     const int N = S.N;
     const bool rhs = (c == 14);
     double Pc[9];            // lanes 0..8: column c of Pxx(k+1); lane 14: pxx(k+1)
-    double an[NP], cn, gsn;  // slack column of stage k+1 (replicated)
+    double an[9], cn, gsn;   // slack column of stage k+1 (replicated): H[x][s] (pose entries, except after the terminal-row stage), H[s][s], g_s
+    // MMPC_MODE_REFERENCE to the letter (Inst::q3): the terminal self-collision rows couple x_N with s[N-1].  Their column
+    // (abar, cbar, gbar; v-slots of stage N's record) enters stage N-1 as [A B]^T abar, i.e. s[N-1] is coupled with u[N-1]
+    // and has to take part in that stage's control elimination: lane 15 carries the slack column through the LDL^T
+    // like the x lanes carry theirs, `ss` is the s-row of lanes 15 (H[s][s]) and 14 (g_s).
+    constexpr bool q3 = Q3;  // compile-time: the clean / rows-on-s[N] kernels carry none of this
+    double ab[NP], cb = 0, gb = 0;
     team_sync();             // the ring may still be read by a slower lane of the previous phase
     bw_issue(N, it); bw_issue(N - 1, it);
     async_wait<1>(); team_sync();
@@ -151,8 +158,11 @@ struct Team {
         Pc[r] = v;
       }
 #pragma unroll
-      for (int a = 0; a < NP; ++a) an[a] = q[Q_A + a];
+      for (int i = 0; i < 9; ++i) an[i] = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { an[POSE2X[a]] = q[Q_A + a]; ab[a] = q3 ? q[Q_BV + a] : 0.0; }
       cn = q[Q_C]; gsn = q[Q_GA + SGY_S] + mu * q[Q_GB + SGY_S];
+      if (q3) { cb = q[Q_HVV]; gb = q[Q_GA + SGY_V] + mu * q[Q_GB + SGY_V]; }
       if (c < 9) {
 #pragma unroll
         for (int r = 0; r < 9; ++r) if (r <= c) S.Rw(N, R_P + ssidx(r, c)) = Pc[r];
@@ -220,19 +230,12 @@ struct Team {
       }
       // eliminate v_k = s_{k+1}:  w = [A B]^T a(k+1) + bv(k),  cv = hvv(k) + c(k+1),  l0 = g_s(k+1) + a.d + g_v(k)
       double wv[14];
-      {
-        double ae[9];
+      abt_mul(an, a, wv);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) ae[i] = 0;
-#pragma unroll
-        for (int p = 0; p < NP; ++p) ae[POSE2X[p]] = an[p];
-        abt_mul(ae, a, wv);
-#pragma unroll
-        for (int p = 0; p < NP; ++p) wv[POSE2X[p]] += q[Q_BV + p];
-      }
+      for (int p = 0; p < NP; ++p) wv[POSE2X[p]] += q[Q_BV + p];
       double l0 = gsn + q[Q_GA + SGY_V] + mu * q[Q_GB + SGY_V];
 #pragma unroll
-      for (int p = 0; p < NP; ++p) l0 = fma(an[p], d[POSE2X[p]], l0);
+      for (int i = 0; i < 9; ++i) l0 = fma(an[i], d[i], l0);
       const double cv = q[Q_HVV] + cn, icv = rcp(cv);
       bad |= !(cv > 1e-13);
       double wc = 0;
@@ -243,9 +246,30 @@ struct Team {
 #pragma unroll
         for (int r = 0; r < 14; ++r) M[r] = fma(-wv[r], fac, M[r]);
       }
+      // terminal-row stage (q3, k = N-1): lane 15 takes the slack column  H[(x,u)][s] = a(k) + [A B]^T abar,  ss = its s-row
+      const bool q3k = q3 && k == N - 1;
+      double ss = 0;
+      if (q3k) {
+        double abe[9], wb[14];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) abe[i] = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) abe[POSE2X[p]] = ab[p];
+        abt_mul(abe, a, wb);
+        double abd = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { wb[POSE2X[p]] += q[Q_A + p]; abd = fma(ab[p], d[POSE2X[p]], abd); }
+        if (c == 15) {
+#pragma unroll
+          for (int r = 0; r < 14; ++r) M[r] = wb[r];
+          ss = q[Q_C] + cb;
+        } else if (rhs) ss = q[Q_GA + SGY_S] + mu * q[Q_GB + SGY_S] + gb + abd;
+      }
       // this stage's slack column is the next iteration's a(k+1); the ring slot is then free
 #pragma unroll
-      for (int p = 0; p < NP; ++p) an[p] = q[Q_A + p];
+      for (int i = 0; i < 9; ++i) an[i] = 0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) an[POSE2X[p]] = q[Q_A + p];
       cn = q[Q_C]; gsn = q[Q_GA + SGY_S] + mu * q[Q_GB + SGY_S];
       team_sync();
       bw_issue(k - 2, it);
@@ -262,6 +286,7 @@ struct Team {
         const double ip = rcp(piv);
         const double f = M[pl] * ip;
         yv[p] = f;
+        if (q3k) ss = fma(-shfl16(M[pl], 15), f, ss);  // s-row of this lane's column (by symmetry the pivot column's s entry is lane 15's)
 #pragma unroll
         for (int r = 0; r < 14; ++r) if (r < 9 || r > pl) M[r] = fma(-col[r], f, M[r]);
 #pragma unroll
@@ -290,6 +315,19 @@ struct Team {
         rkk[R_CV] = cv; rkk[R_L0] = l0;
       }
       if (c < 14) rkk[R_W + c] = wc;
+      if (q3k) {  // the slack column after the control elimination: what stage N-2 eliminates v = s[N-1] with
+#pragma unroll
+        for (int r = 0; r < 9; ++r) an[r] = shfl16(M[r], 15);
+        cn = shfl16(ss, 15); gsn = shfl16(ss, 14);
+        bad |= !(cn > 1e-13);
+        if (c == 15) {  // gain of u[N-1] on ds[N-1] and the column itself, for the roll-out (free slots of stage N's record)
+          double* rkn = &S.Rw(N, 0);
+#pragma unroll
+          for (int p = 0; p < NU; ++p) rkn[R_K + p] = -kc[p];
+#pragma unroll
+          for (int r = 0; r < 9; ++r) rkn[R_K + 8 + r] = M[r];
+        }
+      }
 #pragma unroll
       for (int r = 0; r < 9; ++r) Pc[r] = (c < 9 || rhs) ? M[r] : 0.0;
     }
@@ -300,6 +338,7 @@ struct Team {
 
   // roll-out of the Newton step: dx, du, ds and the new costates lam+ = P [dx; ds] + p.
   // dx is replicated in the team; lane a < 5 forms du[a], lane i < 9 forms lam+[i].
+  template <bool Q3>
   __device__ void rollout(double mu, int it) {
     const int N = S.N; const double dt = S.dt;
     team_sync();
@@ -310,16 +349,19 @@ struct Team {
     if (c < 9) S.W2(0, S_DX + c) = 0;
     double dsv = -(S.Qw(0, Q_GA + SGY_S) + mu * S.Qw(0, Q_GB + SGY_S)) / S.Qw(0, Q_C);
     if (c == 14) S.W2(0, S_DS) = dsv;
+    constexpr bool q3 = Q3;
     for (int k = 0; k < N; ++k) {
       async_wait<2>(); team_sync();
       const double* r0 = sm + (k & 3) * RO_SZ;
       const double* r1 = sm + ((k + 1) & 3) * RO_SZ;
       double* w2k = S.stage_ptr(k, S.B2); double* w2n = S.stage_ptr(k + 1, S.B2);
+      const double ds_in = dsv;  // ds[k]
       double mine = 0;
       if (c < NU) {
         mine = r0[R_KFF + c];
 #pragma unroll
         for (int j = 0; j < NX; ++j) mine = fma(r0[R_K + c * NX + j], dxv[j], mine);
+        if (q3 && k == N - 1) mine = fma(S.Rw(N, R_K + c), ds_in, mine);  // u[N-1] also answers to ds[N-1] (terminal rows)
         w2k[(S_DU + c) << 5] = mine;
       }
       double duv[NU];
@@ -348,8 +390,12 @@ struct Team {
         double v = r1[R_PV + c];
 #pragma unroll
         for (int j = 0; j < NX; ++j) v = fma(r1[R_P + (c <= j ? c * 9 - c * (c - 1) / 2 + (j - c) : j * 9 - j * (j - 1) / 2 + (c - j))], dxv[j], v);
-        if (c < 3) v = fma(r1[RO_A + c], dsv, v);
-        if (c >= 6) v = fma(r1[RO_A + (c - 3)], dsv, v);
+        if (q3 && k + 1 == N - 1) v = fma(S.Rw(N, R_K + 8 + c), dsv, v);  // the column left by stage N-1's control elimination
+        else {
+          if (c < 3) v = fma(r1[RO_A + c], dsv, v);
+          if (c >= 6) v = fma(r1[RO_A + (c - 3)], dsv, v);
+        }
+        if (q3 && k + 1 == N && (c < 3 || c >= 6)) v = fma(S.Qw(N, Q_BV + (c < 3 ? c : c - 3)), ds_in, v);  // abar ds[N-1]
         w2n[(S_LAMN + c) << 5] = v;
       }
       if (c == 14) w2n[S_DS << 5] = dsv;
@@ -369,6 +415,7 @@ struct Team {
   // instance needs no (further) factorisation simply repeats its last one, which rewrites the same values.
   // An instance that leaves here is only marked (state ST_FINISH + status); its results are written by
   // the stage-parallel step kernel of the same round.
+  template <bool Q3>
   __device__ void solve() {
     const MmpcConfig& cfg = S.cfg;
     const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5;
@@ -386,6 +433,7 @@ struct Team {
     kp.e_stat = tmax(kp.e_stat); kp.e_prim = tmax(kp.e_prim); kp.c_hi = tmax(kp.c_hi); kp.c_lo = tmin(kp.c_lo);
     kp.sum_lam = tsum(kp.sum_lam); kp.sum_z = tsum(kp.sum_z); nz = tsum(nz); neq = tsum(neq);
     kp.n_z = (int)nz; kp.n_eq = (int)neq;
+    if (Q3) kp.e_stat = fmax(kp.e_stat, fabs(S.W2(N, S_DFC + 1) - S.W2(N, S_DFC + 0)));  // d/ds[N-1]: two threads' shares
     const double E0 = kkt_error(kp, 0.0);
     // every lane reads the scalar state before lane 0 rewrites any of it
     const int iter = S.J(J_IT);
@@ -408,7 +456,7 @@ struct Team {
     double reg = 0;
     int tries = 0;
     for (;;) {
-      const int fail = riccati(reg, mu, it);
+      const int fail = riccati<Q3>(reg, mu, it);
       if (need) {
         if (!fail) { need = false; if (reg > 0 && c == 0) S.D(D_REGLAST) = reg; }
         else {
@@ -420,17 +468,20 @@ struct Team {
       if (!warp_any(need)) break;
     }
     team_sync();  // the Riccati records written by the other lanes are read back in the roll-out
-    rollout(mu, it);
+    rollout<Q3>(mu, it);
     if (fin >= 0 && c == 0) { S.J(J_STATUS) = fin; S.J(J_STATE) = ST_FINISH; }
   }
 };
 
+// Q3: the literal reference NLP (Inst::q3) -- the host picks the instantiation from the configuration
+template <bool Q3>
 __device__ inline void body_solve_team(const SParams& P, int j, int c, const signed char* ht, double* sm) {
   Team T(P, list_E(P)[j], c, ht, sm);
-  T.solve();
+  T.template solve<Q3>();
 }
 
 #if !defined(MMPC_EMULATE) && !defined(MMPC_EMULATE_LANE)
+template <bool Q3>
 __global__ void __launch_bounds__(128, 4) staged_solve_team_kernel(const __grid_constant__ SParams P) {
   __shared__ signed char ht[14 * 16];
   __shared__ __align__(16) double ring[8 * Team::SMEM_DOUBLES];  // 8 teams per block
@@ -443,7 +494,7 @@ __global__ void __launch_bounds__(128, 4) staged_solve_team_kernel(const __grid_
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; j0 < n; j0 += 2 * warps) {
     const int j = min(j0 + ((threadIdx.x >> 4) & 1), n - 1);
-    body_solve_team(P, j, c, ht, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
+    body_solve_team<Q3>(P, j, c, ht, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
   }
 }
 #endif

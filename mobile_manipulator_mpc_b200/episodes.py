@@ -29,7 +29,7 @@ WORKING_RADIUS = 0.6  # interface_wholebody_qref.py:22
 
 class BatchedInterface:
     def __init__(self, dt, t_move, t_manipulate, x_start, global_pose_target, circles, planes, n_pl_inst=None, N=20,
-                 mode=_abi.MODE_REFERENCE, device=0, max_iter=2000):
+                 mode=_abi.MODE_REFERENCE, device=0, max_iter=2000, terminal_rows_on_sN=0):
         """x_start [B,9], global_pose_target [B,4] (x y z psi), circles [B,n_obs,3], planes [B,n_pl,6] (NumPy).
         max_iter: 'ipopt.max_iter' (2000 in the reference, controllers/mpc_wholebody_qref.py:280).  One instance that runs
         into the cap holds up its whole group for that many rounds, so throughput runs lower it."""
@@ -42,7 +42,7 @@ class BatchedInterface:
         dev = torch.device("cuda", device)
         self.dev = dev
         kw = dict(N=N, dt=dt, n_obs=int(circles.shape[1]), n_pl=int(planes.shape[1]), B_max=B, device=device, mode=mode,
-                  max_iter=int(max_iter))
+                  max_iter=int(max_iter), terminal_rows_on_sN=int(terminal_rows_on_sN))
         self.solvers = []
         for w in WEIGHT_SETS:
             s = BatchSolver(**kw)

@@ -1,5 +1,7 @@
 """Batched episodes on the GPU against the CPU restatement (oracle/episode.py), step by step.
-usage: python scripts/episode_check.py [B] [reference|clean] [n_checked] [free|forced] [literal]"""
+usage: python scripts/episode_check.py [B] [reference|clean] [n_checked] [free|forced] [on_sN]
+The oracle and the GPU solve the same variant of the terminal self-collision rows: the reference to the
+letter (rows on s[N-1]) unless "on_sN" is given."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,10 +12,10 @@ from oracle.episode import Episode
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 mode = _abi.MODE_CLEAN if (len(sys.argv) > 2 and sys.argv[2] == "clean") else _abi.MODE_REFERENCE
 ncheck = int(sys.argv[3]) if len(sys.argv) > 3 else min(B, 4)
-forced = len(sys.argv) > 4 and sys.argv[4] == "forced"
-literal = len(sys.argv) > 5 and sys.argv[5] == "literal"  # oracle with the terminal self-collision rows on s[N-1]   # re-seed the oracle with the GPU's state and U* after every step
+forced = len(sys.argv) > 4 and sys.argv[4] == "forced"   # re-seed the oracle with the GPU's state and U* after every step
+literal = not (len(sys.argv) > 5 and sys.argv[5] == "on_sN")  # terminal self-collision rows on s[N-1] (the reference to the letter) or on s[N]
 xs, gps, circ, pls, npl = scenarios.episode_batch(B)
-T = BatchedInterface(0.1, 5, 2, xs, gps, circ, pls, npl, N=20, mode=mode)
+T = BatchedInterface(0.1, 5, 2, xs, gps, circ, pls, npl, N=20, mode=mode, terminal_rows_on_sN=0 if literal else 1)
 eps = [Episode(0.1, 5, 2, xs[b], gps[b], circ[b], pls[b][:npl[b]], N=20, mode=mode, terminal_rows_on_sN=0 if literal else 1) for b in range(ncheck)]
 t0 = time.time(); worst = 0.0; mism = 0
 while T.steps < 600:

@@ -63,7 +63,7 @@ def solve(batch, cfg, kernel="warp"):
         # staged: product default (team Riccati, fused trial+evaluation, warp-specialised parts);
         # staged_thread: one-thread Riccati; staged_fat: one thread per item; staged_unfused: separate eval
         rounds = C.c_int32(0)
-        team = 1 if kernel == "staged" else 0
+        team = 1 if kernel in ("staged", "staged_noparts") else 0
         fused = 0 if kernel == "staged_unfused" else 1
         parts = 1 if kernel in ("staged", "staged_thread") else 0
         assert lib().staged.mmpc_emu_staged_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo), C.byref(rounds), team, fused, parts) == 0

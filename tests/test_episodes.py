@@ -107,7 +107,7 @@ def test_device_state_machine_source_follows_restatement():
     names = {v: k for k, v in enumerate(_abi.TASK_NAMES)}
     for scen in (1, 2):
         x_start, tgt, planes = scenarios.demo_scenario(scen)
-        ep = Episode(0.1, 5, 2, x_start, tgt, scenarios.DEMO_CIRCLES, planes, N=20, terminal_rows_on_sN=1)
+        ep = Episode(0.1, 5, 2, x_start, tgt, scenarios.DEMO_CIRCLES, planes, N=20)
         io, Mrows = _emu_machine(x_start[None], tgt[None], 50, 20, 20)
         seen = set()
         while ep.active and ep.steps < 400:
@@ -166,12 +166,12 @@ def test_gpu_ik_matches_restatement():
 def test_gpu_episodes_free_running_against_restatement():
     """B = 6 whole episodes on the device (demo scenarios 1 and 2 and perturbed starts); episodes 0 and 1 are followed by the
     CPU restatement free-running (no re-seeding): same task flag at every step, states within 1e-4 after ~200 closed-loop
-    steps.  The restatement solves the NLP variant the GPU's reference mode solves (terminal_rows_on_sN = 1)."""
+    steps.  Both solve the reference's NLP to the letter (terminal self-collision rows on s[N-1])."""
     from mobile_manipulator_mpc_b200.episodes import BatchedInterface
     B = 6
     xs, gps, circ, pls, npl = scenarios.episode_batch(B)
     T = BatchedInterface(0.1, 5, 2, xs, gps, circ, pls, npl, N=20, mode=_abi.MODE_REFERENCE)
-    eps = [Episode(0.1, 5, 2, xs[b], gps[b], circ[b], pls[b][:npl[b]], N=20, terminal_rows_on_sN=1) for b in range(2)]
+    eps = [Episode(0.1, 5, 2, xs[b], gps[b], circ[b], pls[b][:npl[b]], N=20) for b in range(2)]
     worst = 0.0
     while T.steps < 600:
         n = T.step()

@@ -76,21 +76,39 @@ def _terminal_rows_instance():
                 flags=np.zeros(1, np.uint8), Qd=Q, Pd=Q)
 
 
-def test_reference_mode_terminal_rows_variant_is_what_the_kernels_solve():
+def test_reference_mode_terminal_rows_both_variants():
     """SURVEY.md 8(a) row 9 on a path-sensitive instance (found in a closed loop next to demo scenario 2's aerial obstacle):
-    the reference-mode NLP with the terminal self-collision rows bounded by s[N-1] (the reference to the letter) and by s[N]
-    (what the kernels implement, cfg.terminal_rows_on_sN = 1) are both solved by the oracle; none of those rows is active,
-    yet the two barrier paths end in different local optima of the non-smooth NLP.  The kernel source must reproduce the
-    s[N] variant iterate for iterate, and both optima must be stationary points of the dense restated NLP."""
+    the reference-mode NLP with the terminal self-collision rows bounded by s[N-1] (the reference to the letter,
+    cfg.terminal_rows_on_sN = 0) and by s[N] (= 1) end in different local optima of the non-smooth NLP although none of those
+    rows is active.  The kernel source implements both and must land where the oracle lands in each; both optima must be
+    feasible points of the dense restated NLP."""
     from oracle import nlp
     b = _terminal_rows_instance()
-    lit = solver.solve(b, cfg=solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=0))
-    var = solver.solve(b, cfg=solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=1))
-    ker = emu.solve(b, solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=1), kernel="staged")
-    assert lit["status"][0] == 0 and var["status"][0] == 0 and ker["status"][0] == 0
-    assert abs(lit["cost"][0] - 457.41613461) < 1e-5 and abs(var["cost"][0] - 475.98075895) < 1e-5   # two optima
-    assert abs(ker["cost"][0] - var["cost"][0]) < 1e-5 * var["cost"][0]
-    assert np.abs(ker["U"][0, 0] - var["U"][0, 0]).max() < 1e-4 and abs(int(ker["iters"][0]) - int(var["iters"][0])) <= 2
-    P = nlp.from_batch(b, 0, "reference")   # the dense restatement has the rows on s[N-1]; both points are feasible for it
-    for sol in (lit, var):
-        assert P.violation(P.pack(sol["X"][0], sol["U"][0], sol["s"][0])) < 1e-6
+    cost = {0: 457.41613461, 1: 475.98075895}
+    for v in (0, 1):
+        cfg = solver.config_from_batch(b, _abi.MODE_REFERENCE, terminal_rows_on_sN=v)
+        ora = solver.solve(b, cfg=cfg)
+        ker = emu.solve(b, cfg, kernel="staged")
+        assert ora["status"][0] == 0 and ker["status"][0] == 0
+        assert abs(ora["cost"][0] - cost[v]) < 1e-5
+        assert abs(ker["cost"][0] - ora["cost"][0]) < 1e-5 * ora["cost"][0]
+        assert np.abs(ker["U"][0, 0] - ora["U"][0, 0]).max() < 1e-4
+        assert abs(int(ker["iters"][0]) - int(ora["iters"][0])) <= 4
+        P = nlp.from_batch(b, 0, "reference")   # the dense restatement has the rows on s[N-1]; both points are feasible for it
+        assert P.violation(P.pack(ora["X"][0], ora["U"][0], ora["s"][0])) < 1e-6
+
+
+def test_reference_mode_literal_terminal_rows_kernel_vs_oracle():
+    """The literal reference NLP (terminal rows on s[N-1], the default) in the kernel source against the oracle on seeded
+    batches of configs 2, 3 and 5: same optimum within the north-star tolerances."""
+    for cid, B in ((2, 12), (3, 16), (5, 4)):
+        b = scenarios.make_batch(cid, B)
+        cfg = solver.config_from_batch(b, _abi.MODE_REFERENCE)
+        assert cfg.terminal_rows_on_sN == 0
+        ora = solver.solve(b, cfg=cfg, threads=4)
+        ker = emu.solve(b, cfg, kernel="staged")
+        both = (ora["status"] == 0) & (ker["status"] == 0)
+        assert both.sum() >= B - 1
+        rel = np.abs(ora["cost"] - ker["cost"])[both] / np.abs(ora["cost"][both])
+        du0 = np.abs(ora["U"][:, 0] - ker["U"][:, 0]).max(axis=1)[both]
+        assert (rel < 1e-5).all() and (du0 < 1e-4).all(), (cid, rel.max(), du0.max())
