@@ -289,7 +289,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
     int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
     static const int team_cap = getenv("MMPC_TEAM_GRID") ? atoi(getenv("MMPC_TEAM_GRID")) : 0;  // A/B: blocks per SM of the team kernel (0: one block per 8 instances)
-    int gt = (int)((ub * 16 + 127) / 128);
+    int gt = (int)((ub * 16 + MMPC_TEAM_BLOCK - 1) / MMPC_TEAM_BLOCK);
     if (team_cap > 0 && gt > team_cap * h->sm_count) gt = team_cap * h->sm_count;
     int gw = (int)((ub * 32 + 127) / 128 < cap ? (ub * 32 + 127) / 128 : cap);  // one warp per instance
     if (gw < 1) gw = 1;
@@ -306,7 +306,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     }
     MARK(MMPC_PHASE_SOLVE);
     if (P.team) {
-      if (q3) staged_solve_team_kernel<true><<<gt, 128, 0, st>>>(P); else staged_solve_team_kernel<false><<<gt, 128, 0, st>>>(P);
+      if (q3) staged_solve_team_kernel<true><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P); else staged_solve_team_kernel<false><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
     }
     else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
     MARK(MMPC_PHASE_STEP);

@@ -481,10 +481,16 @@ __device__ inline void body_solve_team(const SParams& P, int j, int c, const sig
 }
 
 #if !defined(MMPC_EMULATE) && !defined(MMPC_EMULATE_LANE)
+// threads per block of the team kernel, 16 lanes per instance.  A/B on B200 (solve phase of a 65,536 batch): 128 -> 162.5 ms,
+// 64 -> 155.5 ms, 32 -> 153.3 ms: a block leaves when its slowest warp (most delta_w retries) does, smaller blocks free their
+// registers sooner
+#ifndef MMPC_TEAM_BLOCK
+#define MMPC_TEAM_BLOCK 32
+#endif
 template <bool Q3>
-__global__ void __launch_bounds__(128, 4) staged_solve_team_kernel(const __grid_constant__ SParams P) {
+__global__ void __launch_bounds__(MMPC_TEAM_BLOCK, 512 / MMPC_TEAM_BLOCK) staged_solve_team_kernel(const __grid_constant__ SParams P) {
   __shared__ signed char ht[14 * 16];
-  __shared__ __align__(16) double ring[8 * Team::SMEM_DOUBLES];  // 8 teams per block
+  __shared__ __align__(16) double ring[(MMPC_TEAM_BLOCK / 16) * Team::SMEM_DOUBLES];  // one ring per team
   for (int i = threadIdx.x; i < 14 * 16; i += blockDim.x) ht[i] = TEAM_TABLE.v[i / 16][i % 16];
   __syncthreads();
   const int n = P.cnt[0];
