@@ -101,7 +101,7 @@ def test_reference_mode_terminal_rows_both_variants():
 def test_reference_mode_literal_terminal_rows_kernel_vs_oracle():
     """The literal reference NLP (terminal rows on s[N-1], the default) in the kernel source against the oracle on seeded
     batches of configs 2, 3 and 5: same optimum within the north-star tolerances."""
-    for cid, B in ((2, 12), (3, 16), (5, 4)):
+    for cid, B in ((2, 4), (3, 6), (5, 2)):
         b = scenarios.make_batch(cid, B)
         cfg = solver.config_from_batch(b, _abi.MODE_REFERENCE)
         assert cfg.terminal_rows_on_sN == 0
