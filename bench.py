@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--contexts", type=int, default=3, help="concurrent solver contexts (streams) per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -394,9 +394,11 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, cconv, cdt, _ = cpu_baseline(batch, args.cpu_sample, cores)
+            v1, _, cdt1, _ = cpu_baseline(batch, min(256, args.cpu_sample), 1)   # serial leg
             line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port",
                                         sample="first %d instances of rank 0's batch, oracle/mmpc_oracle.c on %d threads, %.1f s"
-                                               % (args.cpu_sample, cores, cdt))
+                                               % (args.cpu_sample, cores, cdt),
+                                        serial_value=v1, serial_sample="first %d instances on 1 thread, %.1f s" % (min(256, args.cpu_sample), cdt1))
         _emit(line)
     if dist is not None:
         dist.barrier()

@@ -33,3 +33,38 @@ def reduce_stats(dist, converged, seconds, device="cpu"):
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return dict(converged_total=int(c.item()), seconds_max=float(t.item()))
+
+
+def run_interleaved(shards, step, steps):
+    """Drive K independent sub-batches of one GPU concurrently: one host thread and one CUDA stream per shard, so that the
+    thin tail of one shard's solve (a few slow instances, launch-latency bound) overlaps the bulk of another's.  ``shards``:
+    objects with their own solver handles (handles are per host thread); ``step(shard)`` advances one of them by one MPC step
+    and may return a value; returns the list of per-shard lists of those values.  Used by the closed-loop and episode
+    benches; a single solve call cannot hide its own tail, independent batches can."""
+    import threading
+    import torch
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in shards]
+    for s in streams:
+        s.wait_stream(main)
+    out = [[] for _ in shards]
+    err = []
+
+    def work(i):
+        try:
+            with torch.cuda.stream(streams[i]):
+                for _ in range(steps):
+                    out[i].append(step(shards[i]))
+        except BaseException as e:  # surfaced by the caller
+            err.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(shards))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for s in streams:
+        main.wait_stream(s)
+    if err:
+        raise err[0]
+    return out

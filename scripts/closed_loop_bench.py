@@ -21,3 +21,22 @@ for shift in (True, False):
           "mean iterations %.1f, mean distance to goal %.2f m" % (shift, B, steps, dt, conv / dt, np.median(lat), conv / (B * steps),
                                                                  iters / (B * steps), float(d.mean())), flush=True)
     L.solver.close()
+
+# ---- K interleaved shards of the same total batch: the tail of one shard's solve overlaps the bulk of another's ----
+from mobile_manipulator_mpc_b200.sharding import run_interleaved
+for K in (2, 4):
+    subs = []
+    for i in range(K):
+        sl = slice(i * B // K, (i + 1) * B // K)
+        bi = {k: (v[sl] if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+        subs.append(closed_loop.ClosedLoop(bi, x_glob[sl], shift_guess=True))
+    run_interleaved(subs, lambda L: L.step(), 2); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = run_interleaved(subs, lambda L: int((L.step()[1] == 0).sum()), steps)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1); conv = sum(sum(r) for r in res)
+    print("%d interleaved shards of %d: %d closed-loop steps in %.2f s (device) -> %.0f instance-steps/s, %.1f ms per step of the whole batch, "
+          "converged %.4f" % (K, B // K, steps, ms * 1e-3, conv / (ms * 1e-3), ms / steps, conv / (B * steps)), flush=True)
+    for L in subs:
+        L.solver.close()
