@@ -272,11 +272,14 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   h->launches += 1;
   // row ring of the step kernels: STAGED_RING_DOUBLES per thread (48 KB per block of 128)
   const int ring_smem = 128 * STAGED_RING_DOUBLES * (int)sizeof(double);
+  const int trial_ring_smem = 128 * STAGED_TRIAL_RING_DOUBLES * (int)sizeof(double);  // row ring of the trial kernels (24 KB)
   static bool smem_attr_done = false;
   if (!smem_attr_done) {
     smem_attr_done = true;
     CK(cudaFuncSetAttribute(staged_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
     CK(cudaFuncSetAttribute(staged_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
+    CK(cudaFuncSetAttribute(staged_trial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
+    CK(cudaFuncSetAttribute(staged_trial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
   }
   static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
   const int LAG = 2, cap = h->sm_count * cap_mult;
@@ -322,8 +325,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     P.tsel = tnext;
     MARK(MMPC_PHASE_TRIAL);
     if (thin) staged_parts_kernel<true><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
-    else if (ref) staged_trial_kernel<true><<<gs, 128, 0, st>>>(P);
-    else staged_trial_kernel<false><<<gs, 128, 0, st>>>(P);
+    else if (ref) staged_trial_kernel<true><<<gs, 128, trial_ring_smem, st>>>(P);
+    else staged_trial_kernel<false><<<gs, 128, trial_ring_smem, st>>>(P);
     MARK(MMPC_PHASE_CTRL_TRIAL);
     staged_ctrl_trial_kernel<<<gw, 128, 0, st>>>(P);
     CK(cudaGetLastError());

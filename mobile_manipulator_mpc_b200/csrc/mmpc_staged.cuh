@@ -124,6 +124,7 @@ struct Inst {
   // per item, so `wait_group RING_D - 1` is "the oldest item has landed".  (Register prefetching does not work
   // here: ptxas puts the prefetch loads on the scoreboard their consumer waits on.)
   static constexpr int RING_D = 8, RING_W = 6;
+  static constexpr int RING_DT = 4;  // depth of the trial kernel's circle-row ring
   double* sm = nullptr;  // this thread's lane of the ring: item q, value c at sm[((q % RING_D) * RING_W + c) * bs]
   int bs = 1;            // threads per block
   __device__ __forceinline__ double* ring_slot(int q) const { return sm + ((q & (RING_D - 1)) * RING_W) * bs; }
@@ -1377,6 +1378,20 @@ struct Inst {
     const int k1 = k < N ? k + 1 : k;
     const double* ni = stage_ptr(k1, it); const double* n2 = stage_ptr(k1, B2);
     prefetch_stage(k, it, true);
+    // The rows (t, z, dt; circle rows also their circle) stream through a small cp.async ring, RING_DT rows ahead: primed
+    // here, consumed after the cost / bound section in three rolled loops.  Not the bound multipliers: neither ringed (14 unrolled
+    // issue sites: instruction-cache misses) nor parked in shared memory up front (L1, where the spills live, shrinks) paid.
+    const int q_end = nobs + 4 + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
+    auto ring_issue = [&](int q) {
+      if (q < q_end) {
+        double* d = sm + ((q & (RING_DT - 1)) * RING_W) * bs;
+        async_copy8(d, &ci[(I_T + q) << 5]); async_copy8(d + bs, &ci[(I_T + R + q) << 5]); async_copy8(d + 2 * bs, &c2[(S_DT + q) << 5]);
+        if (q < nobs) { async_copy8(d + 3 * bs, circ_ptr(k, q, 0)); async_copy8(d + 4 * bs, circ_ptr(k, q, 1)); async_copy8(d + 5 * bs, circ_ptr(k, q, 2)); }
+      }
+      async_commit();
+    };
+#pragma unroll 1
+    for (int q = 0; q < RING_DT; ++q) ring_issue(q);
     double theta = 0, fsum = 0; bool ok = true;
     LogProd lp; lp.init();
     RowAcc A;
@@ -1525,9 +1540,7 @@ struct Inst {
     }
     // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
     double s_cur = s;  // slack the rows are bounded by (s[N-1] for the terminal self-collision rows of the literal reference NLP)
-    auto row = [&](int r, double h, double& z, double& it_, double& res) {
-      double t = ldg(&ci[(I_T + r) << 5]), dtv = ldg(&c2[(S_DT + r) << 5]);
-      z = ldg(&ci[(I_T + R + r) << 5]);
+    auto row_core = [&](int r, double h, double t, double dtv, double& z, double& it_, double& res) {  // z: in = current multiplier
       double tt = fmax(fma(alpha, dtv, t), s_cur - h);  // slack reset (Nocedal & Wright 19.30)
       double dz = (mu - z * (t + dtv)) * rcp(t);
       it_ = rcp(tt);
@@ -1543,11 +1556,16 @@ struct Inst {
       double sig = z * it_;
       A.csum += sig; A.be0 += sig * res; A.be1 += it_;
     };
+#pragma unroll 1
     for (int i = 0; i < nobs; ++i) {  // obsAvoid :49-54
-      double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
+      async_wait<RING_DT - 1>();
+      const double* rb = sm + ((i & (RING_DT - 1)) * RING_W) * bs;
+      const double rt = rb[0], rdt = rb[2 * bs], ddx = x[0] - rb[3 * bs], ddy = x[1] - rb[4 * bs], rad = rb[5 * bs];
+      double z = rb[bs], it_, res;
+      ring_issue(i + RING_DT);
       double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
-      double h = (circ(k, i, 2) + cfg.base_radius) - d;
-      double z, it_, res; row(i, h, z, it_, res);
+      double h = (rad + cfg.base_radius) - d;
+      row_core(i, h, rt, rdt, z, it_, res);
       double sig = z * it_, nx = ddx * inv, ny = ddy * inv, zd = z * inv;
       A.H[pidx(0, 0)] += sig * nx * nx - zd * (1 - nx * nx);
       A.H[pidx(0, 1)] += (sig + zd) * nx * ny;
@@ -1569,7 +1587,12 @@ struct Inst {
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
       double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2);
       double h = cfg.self_collision_radius - d2 * inv;
-      double z, it_, res; row(nobs + m, h, z, it_, res);
+      async_wait<RING_DT - 1>();
+      const double* rb = sm + (((nobs + m) & (RING_DT - 1)) * RING_W) * bs;
+      const double rt = rb[0], rdt = rb[2 * bs];
+      double z = rb[bs], it_, res;
+      ring_issue(nobs + m + RING_DT);
+      row_core(nobs + m, h, rt, rdt, z, it_, res);
       double sig = z * it_, zd = z * inv;
       double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
       point_grad(f, p, n, g);  // grad h = -g
@@ -1596,7 +1619,12 @@ struct Inst {
       for (int i = 0; i < 6; ++i) {  // obsAvoidConvex :57-89 (proper row)
         Point p; point_eval(x[0], x[1], f, BODY[i], p);
         int jb; double h = plane_row(p, jb);
-        double z, it_, res; row(nobs + 4 + i, h, z, it_, res);
+        async_wait<RING_DT - 1>();
+        const double* rb = sm + (((nobs + 4 + i) & (RING_DT - 1)) * RING_W) * bs;
+        const double rt = rb[0], rdt = rb[2 * bs];
+        double z = rb[bs], it_, res;
+        ring_issue(nobs + 4 + i + RING_DT);
+        row_core(nobs + 4 + i, h, rt, rdt, z, it_, res);
         double sig = z * it_;
         double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)}, g[NP];
         point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g
@@ -1639,6 +1667,7 @@ struct Inst {
     bool fin = ok && (fsum == fsum) && (theta == theta);
     c2[(S_PART + PT_MERIT + 0) << 5] = theta; c2[(S_PART + PT_MERIT + 1) << 5] = fsum; c2[(S_PART + PT_MERIT + 2) << 5] = fin ? lp.value() + log_extra : 0.0;
     c2[(S_PART + PT_MERIT + 3) << 5] = fin ? 1.0 : 0.0;
+    async_wait<0>();  // nothing of this item's ring may still be in flight when the thread primes the next one
   }
 
   // ctrl_trial (thread per instance): filter acceptance test (Waechter & Biegler 2006, Alg. A
@@ -1716,6 +1745,7 @@ __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, lis
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
 // doubles of shared memory one thread of the step / trial kernels needs for its row ring
 constexpr int STAGED_RING_DOUBLES = Inst::RING_D * Inst::RING_W;
+constexpr int STAGED_TRIAL_RING_DOUBLES = Inst::RING_DT * Inst::RING_W;
 template <bool REF>
 __device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {
   Inst S(P, list_E(P)[j]); S.sm = sm; S.bs = bs;

@@ -42,7 +42,7 @@ static void run_team(const SParams& P, int j, std::vector<char*>& stacks) {
 extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out,
                                      int32_t* rounds_out, int32_t team, int32_t fused, int32_t parts) {
   SParams P; memset(&P, 0, sizeof P);
-  static double row_ring[STAGED_RING_DOUBLES];  // the step / trial row ring of the one emulated thread
+  static double row_ring[STAGED_RING_DOUBLES > STAGED_TRIAL_RING_DOUBLES ? STAGED_RING_DOUBLES : STAGED_TRIAL_RING_DOUBLES];  // the step / trial row ring of the one emulated thread
   P.cfg = *cfg; P.B = B;
   P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
   P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
