@@ -175,11 +175,11 @@ def main():
     _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--contexts", type=int, default=3, help="concurrent solver contexts (streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=6, help="concurrent solver contexts (streams) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -228,12 +228,18 @@ def main():
     def run_steps(nsteps, contexts, host=False):
         """nsteps solves of the batch spread round-robin over `contexts` concurrent solver contexts."""
         outs = [None] * contexts
+        nxt = [0]
+        lock = threading.Lock()
 
         def work(t):
             c = ctx[t]
             torch.cuda.set_device(local)
             with torch.cuda.stream(c["stream"]):
-                for _ in range(t, nsteps, contexts):
+                while True:
+                    with lock:   # a context takes the next step when it is free: exactly nsteps solves, balanced
+                        if nxt[0] >= nsteps:
+                            break
+                        nxt[0] += 1
                     outs[t] = c["S"].solve_host(batch) if host else c["S"].solve_device(c["dev_in"], out=c["out"])
         if contexts == 1:
             work(0)
@@ -311,7 +317,7 @@ def main():
     outs_h = run_steps(args.steps, T, host=True)
     barrier()
     e2e_s = time.perf_counter() - t0
-    out_h = outs_h[0]
+    out_h = next(o for o in outs_h if o is not None)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     ce = torch.tensor([float((out_h["status"] == 0).sum())], dtype=torch.float64, device="cuda")
     if dist is not None:
