@@ -239,7 +239,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     CK(cudaMalloc(&h->sg.lists, (size_t)3 * LS * sizeof(int)));
     CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
     CK(cudaMallocHost(&h->sg.pin, 8 * 4 * sizeof(int)));
-    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming | cudaEventBlockingSync));  // the host thread sleeps, it does not spin: several contexts per GPU and ranks per box share the cores
     h->sg.ready = true;
   }
   SParams P; memset(&P, 0, sizeof P);
