@@ -361,9 +361,9 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
 
 extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, void* stream) {
   if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;  // the empty batch needs no arrays
   if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
   if ((h->cfg.n_obs > 0 && !in->circles) || (h->cfg.n_pl > 0 && !in->planes)) return MMPC_ERR_ARG;
-  if (B == 0) return MMPC_OK;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
@@ -402,8 +402,8 @@ static int ensure_staging(MmpcHandle* h) {
 
 extern "C" int mmpc_solve_host(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out) {
   if (!h || !in || !out || B < 0 || B > h->B_max) return MMPC_ERR_ARG;
+  if (B == 0) return MMPC_OK;  // the empty batch needs no arrays
   if (!in->x_init || !in->x_ref || !in->u_ref || !in->u_last || !out->U || !out->status) return MMPC_ERR_ARG;
-  if (B == 0) return MMPC_OK;
   CK(cudaSetDevice(h->device));
   int rc = ensure_staging(h);
   if (rc != MMPC_OK) return rc;

@@ -346,3 +346,38 @@ def test_reference_mode_terminal_rows_both_variants_on_gpu():
         assert abs(o["cost"][0] - ref["cost"][0]) < 1e-5 * ref["cost"][0]
         assert np.abs(o["U"][0, 0] - ref["U"][0, 0]).max() < 1e-4
         S.close()
+
+
+def test_ragged_and_extreme_sizes():
+    """Batches that are not whole tiles of 32, the empty batch, the smallest and the largest horizon the ABI accepts
+    (mmpc_create: 1 <= N <= 63), and a batch larger than the handle was created for."""
+    import ctypes as C
+    from mobile_manipulator_mpc_b200._lib import lib, MmpcError
+    full = scenarios.make_batch(3, 70)
+    S = _solver(full)
+    ref = solver.solve(full, mode=_abi.MODE_CLEAN, threads=4)
+    for B in (1, 31, 33, 70):
+        b = {k: (v[:B] if isinstance(v, np.ndarray) else v) for k, v in full.items()}
+        o = S.solve_host(b)
+        both = (o["status"] == 0) & (ref["status"][:B] == 0)
+        assert both.sum() >= B - 1
+        assert (np.abs(o["cost"] - ref["cost"][:B])[both] <= 1e-5 * np.abs(ref["cost"][:B][both])).all()
+        assert (np.abs(o["U"][:, 0] - ref["U"][:B, 0]).max(axis=1)[both] <= 1e-4).all()
+    # B = 0 is a no-op, B > B_max is refused by the host class and by the ABI
+    bi, bo = _abi.MmpcBatchIn(), _abi.MmpcBatchOut()
+    assert lib().mmpc_solve_host(S._h, 0, C.byref(bi), C.byref(bo)) == _abi.OK
+    with pytest.raises(ValueError):
+        S.solve_host(scenarios.make_batch(3, 71))
+    assert lib().mmpc_solve_host(S._h, 71, C.byref(bi), C.byref(bo)) == _abi.ERR_ARG
+    S.close()
+    for N in (2, 63):
+        b = scenarios.make_batch(1, 3, N=N)
+        SN = _solver(b)
+        o = SN.solve_host(b)
+        r = solver.solve(b, mode=_abi.MODE_CLEAN)
+        assert (o["status"] == 0).all() and (r["status"] == 0).all(), (N, o["status"], r["status"])
+        assert (np.abs(o["cost"] - r["cost"]) <= 1e-5 * np.abs(r["cost"])).all()
+        SN.close()
+    from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    with pytest.raises(MmpcError):
+        BatchSolver(N=64)
