@@ -102,6 +102,9 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   if (!cfg || !out || B_max < 1) return MMPC_ERR_ARG;
   if (cfg->N < 1 || cfg->N > 63 || cfg->n_obs < 0 || cfg->n_pl < 0 || cfg->n_pl > MMPC_MAX_PLANES) return MMPC_ERR_ARG;
   if (cfg->mode != MMPC_MODE_CLEAN && cfg->mode != MMPC_MODE_REFERENCE) return MMPC_ERR_ARG;
+  // the literal reference NLP bounds the terminal self-collision rows by s[N-1]: the starting point relies on x_N = x_{N-1},
+  // which needs a stage N-1 >= 1 (stage 0 is the un-pushed initial state)
+  if (cfg->mode == MMPC_MODE_REFERENCE && cfg->terminal_rows_on_sN == 0 && cfg->N < 2) return MMPC_ERR_UNSUPPORTED;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MMPC_ERR_NO_DEVICE; }
   if (device < 0 || device >= ndev) return MMPC_ERR_ARG;

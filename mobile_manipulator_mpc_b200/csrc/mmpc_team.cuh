@@ -39,20 +39,36 @@ __host__ __device__ constexpr int team_hidx(int r, int c) {
   if (r >= 9) return r == c ? Q_HUU + (r - 9) : -1;
   return (r == 2 && c == 9) ? Q_HPU : -1;
 }
-struct TeamTable {
-  signed char v[14][16];
-  constexpr TeamTable() : v() {
-    for (int r = 0; r < 14; ++r)
-      for (int c = 0; c < 16; ++c) v[r][c] = (signed char)(c < 14 ? team_hidx(r, c) : -1);
+// Slot of the stage-QP record (in the shared-memory ring) that lane c adds to row r of its column: the Hessian entry for
+// the x and u lanes, the gradient entry for the right-hand-side lane, BW_ZERO (a slot that holds 0.0) where the entry is
+// structurally zero.  Packed one byte per row into four words per lane, which the lane keeps in registers: the hot loop
+// then is  M[r] += q[slot(r)]  without a table look-up, a branch on the sign of the index, or a diverging right-hand side.
+constexpr int TEAM_BW_ZERO = 95;
+__host__ __device__ constexpr int team_slot(int r, int c) {
+  if (c < 14) { const int i = team_hidx(r, c); return i >= 0 ? i : TEAM_BW_ZERO; }
+  if (c == 14) return Q_GA + (r < 9 ? r : r + 1);
+  return TEAM_BW_ZERO;
+}
+struct TeamPack {
+  unsigned v[16][4];
+  constexpr TeamPack() : v() {
+    for (int c = 0; c < 16; ++c)
+      for (int r = 0; r < 14; ++r) v[c][r >> 2] |= (unsigned)team_slot(r, c) << (8 * (r & 3));
   }
 };
-__device__ constexpr TeamTable TEAM_TABLE = TeamTable();
+__device__ constexpr TeamPack TEAM_PACK = TeamPack();
 
 struct Team {
   Inst S;
-  const signed char* ht;  // [14][16] table (shared memory on the GPU)
+  unsigned hp[4];         // TEAM_PACK.v[c]: the record slots of this lane's column
   int c;                  // lane of the team
-  __device__ __forceinline__ Team(const SParams& p, int b, int c_, const signed char* ht_, double* sm_) : S(p, b), ht(ht_), c(c_), sm(sm_) {}
+  int sd;                 // slot of the diagonal entry of this lane's column (x and u lanes)
+  __device__ __forceinline__ Team(const SParams& p, int b, int c_, double* sm_) : S(p, b), c(c_), sm(sm_) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) hp[w] = TEAM_PACK.v[c_][w];
+    sd = c_ < 14 ? (int)((TEAM_PACK.v[c_][c_ >> 2] >> (8 * (c_ & 3))) & 0xffu) : TEAM_BW_ZERO;
+  }
+  __device__ __forceinline__ int slot(int r) const { return (int)((hp[r >> 2] >> (8 * (r & 3))) & 0xffu); }  // r: compile-time
 
   __device__ __forceinline__ static double tsum(double v) {
 #pragma unroll
@@ -85,7 +101,7 @@ struct Team {
   // ---- shared-memory prefetch ring (cp.async) ---------------------------------------------------------
   // backward sweep, one record per stage:  QP[80] | dfc[9] | u0 x3 x4 x5 cos sin | pad   (2 slots)
   // roll-out, one record per stage:        RK[120] | a[6] | dfc[9] | u0 x3 x4 x5 cos sin | pad   (4 slots)
-  static constexpr int BW_DFC = 80, BW_AC = 89, BW_SZ = 96, BW_SLOTS = 2;
+  static constexpr int BW_DFC = 80, BW_AC = 89, BW_SZ = 96, BW_SLOTS = 2;  // [95] = TEAM_BW_ZERO, never written by the copies
   static constexpr int RO_A = 120, RO_DFC = 126, RO_AC = 135, RO_SZ = 144, RO_SLOTS = 4;
   static constexpr int SMEM_DOUBLES = RO_SZ * RO_SLOTS;  // per team (>= BW_SZ * BW_SLOTS)
   double* sm;  // this team's ring
@@ -146,16 +162,17 @@ struct Team {
     constexpr bool q3 = Q3;  // compile-time: the clean / rows-on-s[N] kernels carry none of this
     double ab[NP], cb = 0, gb = 0;
     team_sync();             // the ring may still be read by a slower lane of the previous phase
+    if (c == 0) { sm[TEAM_BW_ZERO] = 0.0; sm[BW_SZ + TEAM_BW_ZERO] = 0.0; }  // (the roll-out reuses the ring with another layout)
     bw_issue(N, it); bw_issue(N - 1, it);
     async_wait<1>(); team_sync();
     {
-      const double* q = sm + (N & 1) * BW_SZ;
+      double* q = sm + (N & 1) * BW_SZ;
+      if (c < 9) q[sd] += reg;  // the diagonal entry of a column is read by its own lane only
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
-        double v = 0;
-        if (rhs) v = q[Q_GA + r] + mu * q[Q_GB + r];
-        else if (c < 9) { int idx = ht[r * 16 + c]; if (idx >= 0) v = q[idx]; if (r == c) v += reg; }
-        Pc[r] = v;
+        const int i1 = slot(r), i2 = rhs ? i1 + (Q_GB - Q_GA) : TEAM_BW_ZERO;
+        const double v = fma(mu, q[i2], q[i1]);
+        Pc[r] = (c < 9 || rhs) ? v : 0.0;
       }
 #pragma unroll
       for (int i = 0; i < 9; ++i) an[i] = 0;
@@ -190,7 +207,8 @@ struct Team {
     }
     for (int k = N - 1; k >= 0; --k) {
       async_wait<1>(); team_sync();
-      const double* q = sm + (k & 1) * BW_SZ;
+      double* qm = sm + (k & 1) * BW_SZ;
+      const double* q = qm;
       double* rkk = &S.Rw(k, 0);
       const SACoef a = ac_from(q + BW_AC, S.dt);
       double d[9];
@@ -216,17 +234,12 @@ struct Team {
       }
       double M[14];
       abt_mul(Y, a, M);
-      // + H(:, c) + reg on the diagonal; right-hand side: + g
-      if (rhs) {
+      // + H(:, c) + reg on the diagonal; right-hand side: + g_A + mu g_B -- one code path for all lanes (slot(), BW_ZERO)
+      if (c < 14) qm[sd] += reg;  // the diagonal entry of a column is read by its own lane only
 #pragma unroll
-        for (int r = 0; r < 14; ++r) { const int y = r < 9 ? r : r + 1; M[r] += q[Q_GA + y] + mu * q[Q_GB + y]; }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 14; ++r) {
-          int idx = ht[r * 16 + c];
-          if (idx >= 0) M[r] += q[idx];
-          if (r == c) M[r] += reg;
-        }
+      for (int r = 0; r < 14; ++r) {
+        const int i1 = slot(r), i2 = rhs ? i1 + (Q_GB - Q_GA) : TEAM_BW_ZERO;
+        M[r] += fma(mu, q[i2], q[i1]);
       }
       // eliminate v_k = s_{k+1}:  w = [A B]^T a(k+1) + bv(k),  cv = hvv(k) + c(k+1),  l0 = g_s(k+1) + a.d + g_v(k)
       double wv[14];
@@ -475,8 +488,8 @@ struct Team {
 
 // Q3: the literal reference NLP (Inst::q3) -- the host picks the instantiation from the configuration
 template <bool Q3>
-__device__ inline void body_solve_team(const SParams& P, int j, int c, const signed char* ht, double* sm) {
-  Team T(P, list_E(P)[j], c, ht, sm);
+__device__ inline void body_solve_team(const SParams& P, int j, int c, double* sm) {
+  Team T(P, list_E(P)[j], c, sm);
   T.template solve<Q3>();
 }
 
@@ -489,10 +502,7 @@ __device__ inline void body_solve_team(const SParams& P, int j, int c, const sig
 #endif
 template <bool Q3>
 __global__ void __launch_bounds__(MMPC_TEAM_BLOCK, 512 / MMPC_TEAM_BLOCK) staged_solve_team_kernel(const __grid_constant__ SParams P) {
-  __shared__ signed char ht[14 * 16];
   __shared__ __align__(16) double ring[(MMPC_TEAM_BLOCK / 16) * Team::SMEM_DOUBLES];  // one ring per team
-  for (int i = threadIdx.x; i < 14 * 16; i += blockDim.x) ht[i] = TEAM_TABLE.v[i / 16][i % 16];
-  __syncthreads();
   const int n = P.cnt[0];
   const int c = threadIdx.x & 15;
   // a warp strides over pairs of list entries; with an odd count the last warp's second team repeats the
@@ -500,7 +510,7 @@ __global__ void __launch_bounds__(MMPC_TEAM_BLOCK, 512 / MMPC_TEAM_BLOCK) staged
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; j0 < n; j0 += 2 * warps) {
     const int j = min(j0 + ((threadIdx.x >> 4) & 1), n - 1);
-    body_solve_team<Q3>(P, j, c, ht, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
+    body_solve_team<Q3>(P, j, c, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
   }
 }
 #endif

@@ -20,8 +20,8 @@ static void team_entry() {
   int me = w->cur;
   static double ring[Team::SMEM_DOUBLES];
   const SParams& TP = *g_targ.P;
-  if (TP.cfg.mode == MMPC_MODE_REFERENCE && TP.cfg.terminal_rows_on_sN == 0) body_solve_team<true>(TP, g_targ.j, me, &TEAM_TABLE.v[0][0], ring);
-  else body_solve_team<false>(TP, g_targ.j, me, &TEAM_TABLE.v[0][0], ring);
+  if (TP.cfg.mode == MMPC_MODE_REFERENCE && TP.cfg.terminal_rows_on_sN == 0) body_solve_team<true>(TP, g_targ.j, me, ring);
+  else body_solve_team<false>(TP, g_targ.j, me, ring);
   w->done++;
   if (w->done < 16) { int nx = (me + 1) & 15; w->cur = nx; swapcontext(&w->ctx[me], &w->ctx[nx]); }
   else swapcontext(&w->ctx[me], &w->main_ctx);

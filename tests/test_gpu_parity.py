@@ -381,3 +381,6 @@ def test_ragged_and_extreme_sizes():
     from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
     with pytest.raises(MmpcError):
         BatchSolver(N=64)
+    with pytest.raises(MmpcError):   # literal reference NLP: the terminal rows need a stage N-1 >= 1
+        BatchSolver(N=1, mode=_abi.MODE_REFERENCE)
+    BatchSolver(N=1, mode=_abi.MODE_REFERENCE, terminal_rows_on_sN=1).close()
