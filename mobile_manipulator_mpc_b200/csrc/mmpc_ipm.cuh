@@ -36,7 +36,34 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi) {
 #if defined(MMPC_EMULATE) || defined(MMPC_EMULATE_LANE)
 __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 #else
+#ifdef MMPC_RCP_RN
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+#else
+// MUFU.RCP64H seed (relative error 2^-23) and two Newton steps: 1 + 4 instructions, no slow-path branch; within an ulp or two
+// of 1/x for the normal, finite arguments the solver divides by (slacks, pivots, distances).  A zero, subnormal or non-finite
+// argument gives a non-finite result, which is what those call sites test for anyway (pivot > 0, t > 0).
+__device__ __forceinline__ double rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(y, fma(-x, y, 1.0), y);
+  y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+}
+#endif
+#endif
+// 1/sqrt(x) for the squared distances of the circle and self-collision rows (x > 0, normal): MUFU.RSQ64H seed (relative
+// error 2^-22) and two Newton steps, no special-case path.
+#if defined(MMPC_EMULATE) || defined(MMPC_EMULATE_LANE) || defined(MMPC_RCP_RN)
+__device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
+#else
+__device__ __forceinline__ double rsq(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  return y;
+}
 #endif
 // IPOPT's multiplier safeguard  z <- max(min(z, kappa mu/d), mu/(kappa d)),  kappa = 1e10, id = 1/d
 __device__ __forceinline__ double zclamp(double z, double mu, double id) { double r = mu * id; return fmax(fmin(z, 1e10 * r), 1e-10 * r); }

@@ -147,7 +147,7 @@ struct Parts {
       int i = i0 + q;
       if (i < i1) {
         double ddx = p.x[0] - cx[q], ddy = p.x[1] - cy[q];
-        double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+        double d2 = ddx * ddx + ddy * ddy, inv = rsq(d2), d = d2 * inv;
         double h = (cr[q] + S.cfg.base_radius) - d;
         if (!trial) { row_step(i, io[q], h, -(ddx * p.dp[0] + ddy * p.dp[1]) * inv, p, A.c); continue; }
         RowOut o = row_trial(i, io[q], h, p, A.c, A.csum, A.be0, A.be1, A.zrows);
@@ -201,7 +201,7 @@ struct Parts {
       if (m >= m1) continue;
       const RowIO& r = io[q];
       Point pt; point_eval(p.x[0], p.x[1], f, SELFD[m], pt);
-      double d2 = pt.P[0] * pt.P[0] + pt.P[1] * pt.P[1] + pt.P[2] * pt.P[2], inv = rsqrt(d2);
+      double d2 = pt.P[0] * pt.P[0] + pt.P[1] * pt.P[1] + pt.P[2] * pt.P[2], inv = rsq(d2);
       double h = S.cfg.self_collision_radius - d2 * inv;
       double n[3] = {pt.P[0] * inv, pt.P[1] * inv, pt.P[2] * inv}, g[NP];
       point_grad(f, pt, n, g);  // grad h = -g

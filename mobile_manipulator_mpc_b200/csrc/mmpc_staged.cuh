@@ -598,7 +598,7 @@ struct Inst {
     // inequality rows with slack:  h(x_k) - s_k + t = 0
     for (int i = 0; i < nobs; ++i) {  // obsAvoid :49-54
       double ddx = x[0] - circ(k, i, 0), ddy = x[1] - circ(k, i, 1);
-      double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+      double d2 = ddx * ddx + ddy * ddy, inv = rsq(d2), d = d2 * inv;
       double h = (circ(k, i, 2) + cfg.base_radius) - d;
       double z, it_, res; row_state(it, i, k, h, s, z, it_, res, A);
       double sig = z * it_, nx = ddx * inv, ny = ddy * inv, zd = z * inv;
@@ -620,7 +620,7 @@ struct Inst {
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {  // self collision :219-222
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
-      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2);
+      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsq(d2);
       double h = cfg.self_collision_radius - d2 * inv;
       double z, it_, res; row_state(it, nobs + m, k, h, s_self, z, it_, res, A);
       double sig = z * it_, zd = z * inv;
@@ -1154,14 +1154,14 @@ struct Inst {
       const double* rb = ring_pop();
       const double rt = rb[0], rz = rb[bs], ddx = x[0] - rb[2 * bs], ddy = x[1] - rb[3 * bs], rad = rb[4 * bs];
       ring_next();
-      double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+      double d2 = ddx * ddx + ddy * ddy, inv = rsq(d2), d = d2 * inv;
       row_step(i, (rad + cfg.base_radius) - d, -(ddx * dp[0] + ddy * dp[1]) * inv, rt, rz);
     }
     if (REF && k == N && q3()) { s_cur = W(N - 1, it + I_S); ds_cur = W2(N - 1, S_DS); }  // terminal rows on s[N-1]
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
-      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2), d = d2 * inv;
+      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsq(d2), d = d2 * inv;
       double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
       point_grad(f, p, n, g);
       double gd_ = 0;
@@ -1563,7 +1563,7 @@ struct Inst {
       const double rt = rb[0], rdt = rb[2 * bs], ddx = x[0] - rb[3 * bs], ddy = x[1] - rb[4 * bs], rad = rb[5 * bs];
       double z = rb[bs], it_, res;
       ring_issue(i + RING_DT);
-      double d2 = ddx * ddx + ddy * ddy, inv = rsqrt(d2), d = d2 * inv;
+      double d2 = ddx * ddx + ddy * ddy, inv = rsq(d2), d = d2 * inv;
       double h = (rad + cfg.base_radius) - d;
       row_core(i, h, rt, rdt, z, it_, res);
       double sig = z * it_, nx = ddx * inv, ny = ddy * inv, zd = z * inv;
@@ -1585,7 +1585,7 @@ struct Inst {
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {  // self collision :219-222
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
-      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsqrt(d2);
+      double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsq(d2);
       double h = cfg.self_collision_radius - d2 * inv;
       async_wait<RING_DT - 1>();
       const double* rb = sm + (((nobs + m) & (RING_DT - 1)) * RING_W) * bs;
