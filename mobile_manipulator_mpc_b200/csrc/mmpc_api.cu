@@ -312,7 +312,15 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     }
     MARK(MMPC_PHASE_SOLVE);
     if (P.team) {
-      if (q3) staged_solve_team_kernel<true><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P); else staged_solve_team_kernel<false><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
+      // thin round: every instance gets its own half warp at TEAM_WARPS_THIN warps per SM -> the spill-free instantiation
+      const bool thin_team = ub * 16 <= (long long)h->sm_count * TEAM_WARPS_THIN * 32;
+      if (q3) {
+        if (thin_team) staged_solve_team_kernel<true, TEAM_WARPS_THIN><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
+        else staged_solve_team_kernel<true, TEAM_WARPS_BULK><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
+      } else {
+        if (thin_team) staged_solve_team_kernel<false, TEAM_WARPS_THIN><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
+        else staged_solve_team_kernel<false, TEAM_WARPS_BULK><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
+      }
     }
     else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
     MARK(MMPC_PHASE_STEP);
