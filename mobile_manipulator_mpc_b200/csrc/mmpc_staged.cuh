@@ -1823,10 +1823,10 @@ __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant_
 }
 // resident blocks per SM the step / trial kernels are compiled for (A/B on B200: 3 beats 1 and 4)
 #ifndef MMPC_STEP_MINB
-#define MMPC_STEP_MINB 3
+#define MMPC_STEP_MINB 4
 #endif
 #ifndef MMPC_TRIAL_MINB
-#define MMPC_TRIAL_MINB 3
+#define MMPC_TRIAL_MINB 2
 #endif
 template <bool REF>
 __global__ void __launch_bounds__(128, MMPC_STEP_MINB) staged_step_kernel(const __grid_constant__ SParams P) {
