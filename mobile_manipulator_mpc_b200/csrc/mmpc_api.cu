@@ -283,6 +283,8 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     CK(cudaFuncSetAttribute(staged_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
     CK(cudaFuncSetAttribute(staged_trial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
     CK(cudaFuncSetAttribute(staged_trial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
+    CK(cudaFuncSetAttribute(staged_trial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
+    CK(cudaFuncSetAttribute(staged_trial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
   }
   static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
   const int LAG = 2, cap = h->sm_count * cap_mult;

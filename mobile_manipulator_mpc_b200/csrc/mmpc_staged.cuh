@@ -1381,6 +1381,12 @@ struct Inst {
     // The rows (t, z, dt; circle rows also their circle) stream through a small cp.async ring, RING_DT rows ahead: primed
     // here, consumed after the cost / bound section in three rolled loops.  Not the bound multipliers: neither ringed (14 unrolled
     // issue sites: instruction-cache misses) nor parked in shared memory up front (L1, where the spills live, shrinks) paid.
+    // the 28 bound multipliers (fields I_ZXL .. I_T) are parked in shared memory by one group of copies and read back as plain
+    // LDS at the sites that use them: each of those sites exposed a full HBM round trip (the compiler does not hoist them)
+    double* zb = sm + (RING_DT * RING_W) * bs;
+#pragma unroll 1
+    for (int f = 0; f < I_T - I_ZXL; ++f) async_copy8(zb + f * bs, &ci[(I_ZXL + f) << 5]);
+    async_commit();
     const int q_end = nobs + 4 + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
     auto ring_issue = [&](int q) {
       if (q < q_end) {
@@ -1484,6 +1490,7 @@ struct Inst {
       }
     }
     // cost and boxes -- :192-205, :240-245
+    async_wait<RING_DT>();  // the bound multipliers have landed (the row ring's RING_DT groups were committed after them)
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
@@ -1494,11 +1501,11 @@ struct Inst {
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, id, z = box(ldg(&ci[(I_ZXL + i) << 5]), xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
+          double d = x[i] - lo, id, z = box(zb[i * bs], xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], id, z = box(ldg(&ci[(I_ZXU + i) << 5]), hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
+          double d = hi - x[i], id, z = box(zb[(I_ZXU - I_ZXL + i) * bs], hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
           Hd += z * id; gB += id; st += z;
         }
       }
@@ -1527,11 +1534,11 @@ struct Inst {
         double st = gr + stu[j];
         double lo = ldg(&c2[(IN_ULO + j) << 5]), hi = ldg(&c2[(IN_UHI + j) << 5]);
         if (is_fin(lo)) {
-          double d = u[j] - lo, id, z = box(ldg(&ci[(I_ZUL + j) << 5]), uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
+          double d = u[j] - lo, id, z = box(zb[(I_ZUL - I_ZXL + j) * bs], uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], id, z = box(ldg(&ci[(I_ZUU + j) << 5]), hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
+          double d = hi - u[j], id, z = box(zb[(I_ZUU - I_ZXL + j) * bs], hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
           Hd += z * id; gB += id; st += z;
         }
         es = fmax(es, fabs(st));
@@ -1745,7 +1752,7 @@ __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, lis
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
 // doubles of shared memory one thread of the step / trial kernels needs for its row ring
 constexpr int STAGED_RING_DOUBLES = Inst::RING_D * Inst::RING_W;
-constexpr int STAGED_TRIAL_RING_DOUBLES = Inst::RING_DT * Inst::RING_W;
+constexpr int STAGED_TRIAL_RING_DOUBLES = Inst::RING_DT * Inst::RING_W + (I_T - I_ZXL);  // row ring + the 28 bound multipliers
 template <bool REF>
 __device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {
   Inst S(P, list_E(P)[j]); S.sm = sm; S.bs = bs;
