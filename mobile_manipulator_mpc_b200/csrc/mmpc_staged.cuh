@@ -1386,6 +1386,10 @@ struct Inst {
     double* zb = sm + (RING_DT * RING_W) * bs;
 #pragma unroll 1
     for (int f = 0; f < I_T - I_ZXL; ++f) async_copy8(zb + f * bs, &ci[(I_ZXL + f) << 5]);
+    // ... and so are the 29 reference / bound inputs of the stage (fields IN_XREF .. S_DT of the second block)
+    double* rb_in = zb + (I_T - I_ZXL) * bs;
+#pragma unroll 1
+    for (int f = 0; f < S_DT - IN_XREF; ++f) async_copy8(rb_in + f * bs, &c2[(IN_XREF + f) << 5]);
     async_commit();
     const int q_end = nobs + 4 + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
     auto ring_issue = [&](int q) {
@@ -1494,7 +1498,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-      double e = x[i] - ldg(&c2[(IN_XREF + i) << 5]);
+      double e = x[i] - rb_in[(IN_XREF - IN_XREF + i) * bs];
       fsum += Wx * e * e;
       double gr = 2 * Wx * e;
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
@@ -1527,12 +1531,12 @@ struct Inst {
       double Hd = 0, gA = 0, gB = 0;
       if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - ldg(&c2[(IN_UREF + j) << 5]), dl = u[j] - ldg(&c2[(IN_ULAST + j) << 5]);
+        double e = u[j] - rb_in[(IN_UREF - IN_XREF + j) * bs], dl = u[j] - rb_in[(IN_ULAST - IN_XREF + j) * bs];
         fsum += os * (cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl);
         double gr = 2 * Rj * e + 2 * Wj * dl;
         Hd = 2 * Rj + 2 * Wj; gA = gr;
         double st = gr + stu[j];
-        double lo = ldg(&c2[(IN_ULO + j) << 5]), hi = ldg(&c2[(IN_UHI + j) << 5]);
+        double lo = rb_in[(IN_ULO - IN_XREF + j) * bs], hi = rb_in[(IN_UHI - IN_XREF + j) * bs];
         if (is_fin(lo)) {
           double d = u[j] - lo, id, z = box(zb[(I_ZUL - I_ZXL + j) * bs], uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
           Hd += z * id; gB -= id; st -= z;
@@ -1752,7 +1756,7 @@ __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, lis
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
 // doubles of shared memory one thread of the step / trial kernels needs for its row ring
 constexpr int STAGED_RING_DOUBLES = Inst::RING_D * Inst::RING_W;
-constexpr int STAGED_TRIAL_RING_DOUBLES = Inst::RING_DT * Inst::RING_W + (I_T - I_ZXL);  // row ring + the 28 bound multipliers
+constexpr int STAGED_TRIAL_RING_DOUBLES = Inst::RING_DT * Inst::RING_W + (I_T - I_ZXL) + (S_DT - IN_XREF);  // row ring + 28 bound multipliers + 29 stage inputs
 template <bool REF>
 __device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {
   Inst S(P, list_E(P)[j]); S.sm = sm; S.bs = bs;
