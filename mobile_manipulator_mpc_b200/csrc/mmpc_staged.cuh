@@ -319,7 +319,26 @@ struct Inst {
   //   phase 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step
   // (Quirk 3, the terminal self-collision rows bounded by s_{N-1}, is handled where those rows are evaluated: see q3().)
   struct StaleIO {
-    RowAcc* A; double* bv;                   // phase 0/1: accumulators of stage k; bv[6] = H[pose][v]
+    // phase 0/1: this function's own share of the accumulators of stage k and of bv[6] = H[pose][v]; the caller adds them to its
+    // own after the call.  (A pointer to the caller's accumulators would force all of them into local memory for the whole
+    // kernel: the reference-mode trial kernel ran 3.5x slower than the clean one for that.)
+    RowAcc acc; double bvv[NP];
+    __device__ __forceinline__ void reset() {
+      acc.chi = -1e300; acc.clo = 1e300; acc.prim = 0; acc.sumz = 0; acc.zrows = 0; acc.nz = 0; acc.csum = acc.be0 = acc.be1 = 0;
+#pragma unroll
+      for (int e = 0; e < 21; ++e) acc.H[e] = 0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) acc.a[a] = acc.gA[a] = acc.gB[a] = acc.st[a] = bvv[a] = 0;
+      theta = 0; logsum = 0; ok = true; gphi = 0;
+    }
+    __device__ __forceinline__ void merge_into(RowAcc& A, double (&bv)[NP]) const {
+#pragma unroll
+      for (int e = 0; e < 21; ++e) A.H[e] += acc.H[e];
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { A.a[a] += acc.a[a]; A.gA[a] += acc.gA[a]; A.gB[a] += acc.gB[a]; A.st[a] += acc.st[a]; bv[a] += bvv[a]; }
+      A.csum += acc.csum; A.be0 += acc.be0; A.be1 += acc.be1; A.zrows += acc.zrows; A.sumz += acc.sumz; A.nz += acc.nz;
+      A.chi = fmax(A.chi, acc.chi); A.clo = fmin(A.clo, acc.clo); A.prim = fmax(A.prim, acc.prim);
+    }
     double theta, logsum; bool ok;           // merit ingredients (phase 1, 2)
     MinRatio rp, rd; double gphi;            // phase 2
   };
@@ -412,7 +431,7 @@ struct Inst {
           } else it_ = 1.0 / t;
           const double res = h - s_k + t;
           io.theta += fabs(res);
-          RowAcc& A = *io.A;
+          RowAcc& A = io.acc;
           A.prim = fmax(A.prim, fabs(res));
           const double zt = z * t;
           A.chi = fmax(A.chi, zt); A.clo = fmin(A.clo, zt); A.sumz += z; A.zrows += z; A.nz++;
@@ -452,14 +471,14 @@ struct Inst {
             t = tt;
           } else it_ = 1.0 / t;
           const double res = h - s_n + t, sig = z * it_, cb = sig * res;
-          RowAcc& A = *io.A;
+          RowAcc& A = io.acc;
 #pragma unroll
           for (int a = 0; a < NP; ++a)
 #pragma unroll
             for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += sig * g[a] * g[c];
           point_hess_acc(fk, pt, n, z, A.H);
 #pragma unroll
-          for (int a = 0; a < NP; ++a) { io.bv[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
+          for (int a = 0; a < NP; ++a) { io.bvv[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
         }
     }
   }
@@ -663,9 +682,10 @@ struct Inst {
       }
     }
     double bv[NP] = {0, 0, 0, 0, 0, 0};
-    if (REF) {  // compiled out of the clean-mode kernels: taking &A would force the accumulators into local memory
-      StaleIO io; io.A = &A; io.bv = bv; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp.init(); io.rd.init();
+    if (REF) {  // compiled out of the clean-mode kernels
+      StaleIO io; io.reset(); io.rp.init(); io.rd.init();
       stale_rows(k, 0, io);
+      io.merge_into(A, bv);
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
     double S2 = 2 * os * cfg.S;
@@ -1186,8 +1206,8 @@ struct Inst {
       }
     }
     double log_extra = 0;
-    if (REF) {  // compiled out of the clean-mode kernels: taking &A would force the accumulators into local memory
-      StaleIO io; io.A = nullptr; io.bv = nullptr; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp = rp; io.rd = rd;
+    if (REF) {  // compiled out of the clean-mode kernels
+      StaleIO io; io.reset(); io.rp = rp; io.rd = rd;
       stale_rows(k, 2, io);
       theta += io.theta; gphi += io.gphi; log_extra = io.logsum; rp = io.rp; rd = io.rd;
     }
@@ -1650,9 +1670,10 @@ struct Inst {
       }
     }
     double bv[NP] = {0, 0, 0, 0, 0, 0}, log_extra = 0;
-    if (REF) {  // compiled out of the clean-mode kernels: taking &A would force the accumulators into local memory
-      StaleIO io; io.A = &A; io.bv = bv; io.theta = 0; io.logsum = 0; io.ok = true; io.gphi = 0; io.rp.init(); io.rd.init();
+    if (REF) {  // compiled out of the clean-mode kernels
+      StaleIO io; io.reset(); io.rp.init(); io.rd.init();
       stale_rows(k, 1, io);
+      io.merge_into(A, bv);
       theta += io.theta; log_extra = io.logsum; ok = ok && io.ok;
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h

@@ -8,7 +8,9 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 kern = sys.argv[4] if len(sys.argv) > 4 else "auto"
 b = scenarios.make_batch(cid, B)
-S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B, obs_per_stage=b["obs_per_stage"], kernel=kern)
+from mobile_manipulator_mpc_b200 import _abi
+mode = _abi.MODE_REFERENCE if os.environ.get("MMPC_MODE") == "reference" else _abi.MODE_CLEAN   # reference: the literal NLP (quirks 1-3)
+S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B, obs_per_stage=b["obs_per_stage"], kernel=kern, mode=mode)
 d = S.to_device(b)
 out = None
 for r in range(reps):
