@@ -308,6 +308,19 @@ def main():
             l1.append(a.elapsed_time(b))
         lat1 = float(np.median(l1))
         S1.close()
+    # the same batch as the reference's NLP to the letter (MMPC_MODE_REFERENCE: stale plane columns, terminal rows on s[N-1]),
+    # one context, two timed solves: reported next to the headline, which is the stage-separable ("clean") NLP
+    ref_nlp = None
+    if rank == 0:
+        from mobile_manipulator_mpc_b200 import _abi
+        SR = BatchSolver(N=N, dt=batch["dt"], n_obs=n_obs, n_pl=n_pl, B_max=B, device=local, mode=_abi.MODE_REFERENCE)
+        dR = SR.to_device(batch); oR = SR.solve_device(dR); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); SR.solve_device(dR, out=oR); SR.solve_device(dR, out=oR); b.record(); torch.cuda.synchronize()
+        convR = int((oR["status"] == 0).sum().item())
+        ref_nlp = dict(single_context_value=convR * 2 / (a.elapsed_time(b) * 1e-3), ms_per_step=a.elapsed_time(b) / 2,
+                       converged_fraction=convR / B)
+        SR.close()
     barrier()
 
     # ---- end to end through the C ABI with host buffers (pinned staging, H2D, solve, D2H per step) ----
@@ -380,7 +393,7 @@ def main():
                                           % (S.workspace_bytes() / 1e9, (h2d + d2h) / 1e6),
                                 converged_fraction=conv_all / B_all, mean_iterations=iters_all / B_all,
                                 rounds=rounds, single_context_ms_per_step=step_ms,
-                                p50_batched_solve_latency_ms=float(np.median(lat_ms)), p50_single_instance_latency_ms=lat1,
+                                p50_batched_solve_latency_ms=float(np.median(lat_ms)), p50_single_instance_latency_ms=lat1, reference_nlp=ref_nlp,
                                 single_context_value=conv / (step_ms * 1e-3), wall_ms_timed_region=wall_ms),
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
