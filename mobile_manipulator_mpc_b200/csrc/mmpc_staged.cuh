@@ -4,19 +4,22 @@
 //
 // Mapping (B200).  One interior-point iteration of the whole batch is a short sequence of kernels
 // over compacted lists of still-active instances; all per-instance state lives in HBM in a
-// field-major / instance-minor layout  ws[(stage*STG + field) * LS + b]  so that every access of a
-// warp is a coalesced line, whichever way the threads are mapped:
+// tile-major, lane-interleaved layout  ws[((tile*(N+1) + stage)*STG + field)*32 + lane]  (see Inst)
+// so that every access of a warp of neighbouring instances is one coalesced 256-byte line:
 //
 //   eval        thread per (instance, stage)   dynamics, FK, every inequality row with gradient and
 //                                              Hessian, barrier condensation -> stage QP, KKT partials
-//   riccati     thread per instance            KKT reduction + convergence test + barrier update,
-//                                              register-resident Riccati recursion (inertia
-//                                              correction by delta_w), roll-out of the Newton step
+//   riccati     16 lanes per instance          KKT reduction + convergence test + barrier update,
+//               (mmpc_team.cuh; one thread     column-parallel register-resident Riccati recursion (inertia
+//               per instance here as A/B)      correction by delta_w), roll-out of the Newton step
 //   step        thread per (instance, stage)   slack / multiplier steps of every row and bound,
 //                                              fraction to the boundary, merit ingredients
 //   ctrl_step   thread per instance            reduction, line-search start
 //   trial       thread per (instance, stage)   candidate iterate  w + alpha d  (primal and dual) into
-//                                              the other half of a ping-pong buffer, merit values
+//                                              the other half of a ping-pong buffer, merit values, and
+//                                              (fused, the default) the evaluation of the next iteration
+// The step and trial kernels stream their row-like inputs through per-thread cp.async rings in shared
+// memory (Inst::RING_*); the trial kernel also parks the bound multipliers and stage inputs there.
 //   ctrl_trial  thread per instance            filter acceptance test; accepted instances flip their
 //                                              buffer and join the next round's eval list, rejected
 //                                              ones halve alpha and join the next round's trial list
