@@ -273,7 +273,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   staged_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(P);
   CK(cudaGetLastError());
   h->launches += 1;
-  // row ring of the step kernels: STAGED_RING_DOUBLES per thread (48 KB per block of 128)
+  // row ring of the step kernels: STAGED_RING_DOUBLES per thread (24 KB per block of 128)
   const int ring_smem = 128 * STAGED_RING_DOUBLES * (int)sizeof(double);
   const int trial_ring_smem = 128 * STAGED_TRIAL_RING_DOUBLES * (int)sizeof(double);  // row ring of the trial kernels (24 KB)
   static bool smem_attr_done = false;

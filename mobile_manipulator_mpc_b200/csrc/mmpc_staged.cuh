@@ -126,7 +126,7 @@ struct Inst {
   // with cp.async, RING_D items ahead of their use.  The items are consumed strictly in order; one commit group
   // per item, so `wait_group RING_D - 1` is "the oldest item has landed".  (Register prefetching does not work
   // here: ptxas puts the prefetch loads on the scoreboard their consumer waits on.)
-  static constexpr int RING_D = 8, RING_W = 6;
+  static constexpr int RING_D = 4, RING_W = 6;
   static constexpr int RING_DT = 4;  // depth of the trial kernel's circle-row ring
   double* sm = nullptr;  // this thread's lane of the ring: item q, value c at sm[((q % RING_D) * RING_W + c) * bs]
   int bs = 1;            // threads per block
