@@ -193,6 +193,13 @@ class MPCWholeBody:
         self.u_latest = out["U"][0]      # :330
         return self.u_latest[0, :]
 
+    def _backend_solve(self, batch, B):
+        """The one call into the C ABI (mmpc_solve_host); the product has no other backend."""
+        if self._solver is None:
+            self._solver = BatchSolver(cfg=self._cfg, B_max=max(self.batch, B), device=self.device)
+            self._solver.set_weights(Q=self.Q_value, R=self.R_value, P=self.P_value, S=self.S_value, W=self.W_value)
+        return self._solver.solve_host(batch)
+
     def solve_batch(self, x_init, traj_ref, u_ref, u_last=None, u_guess=None, circles=None, planes=None,
                     n_pl_inst=None):
         """B instances at once (host arrays).  circles/planes default to the constructor's lists."""
@@ -201,10 +208,7 @@ class MPCWholeBody:
         N = self.N
         batch = dict(x_init=x_init, x_ref=traj_ref, u_ref=u_ref,
                      u_last=np.zeros((B, N, 5)) if u_last is None else u_last, u_guess=u_guess)
-        if self._solver is None:
-            self._solver = BatchSolver(cfg=self._cfg, B_max=max(self.batch, B), device=self.device)
-            self._solver.set_weights(Q=self.Q_value, R=self.R_value, P=self.P_value, S=self.S_value, W=self.W_value)
-        c = self._solver.cfg
+        c = self._cfg
         if c.n_obs:
             batch["circles"] = np.broadcast_to(self._circles_array(), (B, c.n_obs, 3)) if circles is None else circles
         if c.n_pl:
@@ -212,6 +216,6 @@ class MPCWholeBody:
         batch["n_pl_inst"] = n_pl_inst
         if self.terminal_xy_eq:   # opti.subject_to(X[N, :2] == X_ref[N, :2])  interface_wholebody_qref.py:167
             batch["flags"] = np.ones(B, np.uint8)
-        out = self._solver.solve_host(batch)
+        out = self._backend_solve(batch, B)
         self.last_info = {k: out[k] for k in ("status", "iters", "kkt", "cost")}
         return out
