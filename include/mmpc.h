@@ -67,15 +67,16 @@ enum {
   MMPC_MODE_CLEAN = 1      /* stage-separable: -max_j c_k[i,j] <= s_k only, terminal rows on s[N]  */
 };
 
-/* execution strategy of mmpc_solve (same algorithm, same results to rounding):
- *   STAGED batch-synchronous rounds of phase kernels over compacted lists of active instances
- *          (stage-parallel evaluation / step / trial, thread-per-instance Riccati); the default
- *   LANE   one persistent thread per instance, 32 instances per warp in lock-step
- *   WARP   one warp per instance, lanes cooperate on the stages of one horizon */
-enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_LANE = 1, MMPC_KERNEL_WARP = 2, MMPC_KERNEL_STAGED = 3,
-       MMPC_KERNEL_STAGED_THREAD = 4,  /* STAGED with the one-thread-per-instance Riccati (A/B reference) */
-       MMPC_KERNEL_STAGED_UNFUSED = 5, /* STAGED with separate eval and trial kernels (A/B reference)       */
-       MMPC_KERNEL_STAGED_FAT = 6      /* STAGED with one thread per (instance, stage) item (A/B reference) */ };
+/* execution strategy of mmpc_solve (same algorithm, same results to the bit):
+ *   STAGED batch-synchronous rounds of phase kernels over compacted lists of active instances (stage-parallel
+ *          evaluation / step / trial, 16-lane column-parallel Riccati), the whole solve one CUDA graph whose
+ *          conditional WHILE nodes loop over the rounds on the device; the default (AUTO)
+ * The others are A/B references of single design decisions.  (Values 1 and 2 named two superseded kernels.) */
+enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_STAGED = 3,
+       MMPC_KERNEL_STAGED_THREAD = 4,   /* STAGED with the one-thread-per-instance Riccati                         */
+       MMPC_KERNEL_STAGED_UNFUSED = 5,  /* STAGED with separate eval and trial kernels (host loop)                 */
+       MMPC_KERNEL_STAGED_FAT = 6,      /* STAGED with one thread per (instance, stage) item in the thin rounds too */
+       MMPC_KERNEL_STAGED_HOSTLOOP = 7  /* STAGED with the host sequencing the rounds instead of the CUDA graph    */ };
 
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */

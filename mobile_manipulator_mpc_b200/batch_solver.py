@@ -49,10 +49,11 @@ class BatchSolver:
             self.set_kernel(kernel)
 
     def set_kernel(self, kernel):
-        """'auto' | 'staged' (phase kernels over active lists) | 'lane' (thread per instance) | 'warp'."""
-        k = {"auto": _abi.KERNEL_AUTO, "lane": _abi.KERNEL_LANE, "warp": _abi.KERNEL_WARP,
-             "staged": _abi.KERNEL_STAGED, "staged_thread": _abi.KERNEL_STAGED_THREAD,
-             "staged_unfused": _abi.KERNEL_STAGED_UNFUSED, "staged_fat": _abi.KERNEL_STAGED_FAT}.get(kernel, kernel)
+        """'auto' = 'staged' (phase kernels over active lists, one CUDA graph per solve) | A/B references:
+        'staged_hostloop' (the host sequences the rounds), 'staged_thread', 'staged_unfused', 'staged_fat'."""
+        k = {"auto": _abi.KERNEL_AUTO, "staged": _abi.KERNEL_STAGED, "staged_thread": _abi.KERNEL_STAGED_THREAD,
+             "staged_unfused": _abi.KERNEL_STAGED_UNFUSED, "staged_fat": _abi.KERNEL_STAGED_FAT,
+             "staged_hostloop": _abi.KERNEL_STAGED_HOSTLOOP}.get(kernel, kernel)
         check(lib().mmpc_set_kernel(self._h, int(k)))
 
     # -- lifetime -----------------------------------------------------------------------------

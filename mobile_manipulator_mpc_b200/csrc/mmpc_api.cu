@@ -10,8 +10,6 @@
 #include <vector>
 
 #include "../../include/mmpc.h"
-#include "mmpc_solver.cuh"
-#include "mmpc_lane.cuh"
 #include "mmpc_staged.cuh"
 #include "mmpc_team.cuh"
 #include "mmpc_parts.cuh"
@@ -21,20 +19,15 @@ using namespace mmpc;
 
 struct MmpcHandle {
   MmpcConfig cfg;
-  int device, B_max, sm_count, blocks_per_sm, slots;
-  int SP, KP, R;
-  size_t smem_bytes;
-  long long ws_stride;
-  double* ws;
-  unsigned* counter;
+  int device, B_max, sm_count;
   long long launches;
-  // lane-per-instance kernel: resident warps, interleaved workspace (allocated on first use)
-  int kernel, lane_warps_per_sm, lane_warps, sg_team, sg_fused, sg_parts;
-  long long lane_warp_stride;
-  double* lane_ws;
+  int kernel, sg_team, sg_fused, sg_parts;
   // staged (batch-synchronous) solver: field-major state, per-instance scalars, lists, counters
-  struct { double *ws, *qp, *rk, *gd; int *gi, *lists, *cnt; long long LS; int* pin; cudaEvent_t ev[8]; bool ready, attr_set;
+  struct { double *ws, *qp, *rk, *gd; int *gi, *lists, *cnt; SIO* io; long long LS; int* pin; cudaEvent_t ev[8]; bool ready;
            int rounds; } sg;
+  // the solve as one CUDA graph (built for a batch size, rebuilt when B, the weights or the kernel selection change)
+  struct { struct { cudaGraph_t graph; cudaGraphExec_t exec; int cap, classes; } e[4]; int next, pending_classes; bool pending; } gr;
+  int hostloop;  // MMPC_KERNEL_STAGED_HOSTLOOP: the host sequences the rounds
   // per-phase device timing of the staged solver (mmpc_set_profile / mmpc_phase_times)
   int profile;
   std::vector<cudaEvent_t>* prof_ev;
@@ -96,6 +89,9 @@ extern "C" int mmpc_struct_sizes(int32_t* cfg_bytes, int32_t* in_bytes, int32_t*
   return MMPC_OK;
 }
 
+static int set_kernel_attributes();
+static void graph_destroy(MmpcHandle* h);
+static void graph_account(MmpcHandle* h);
 static size_t circles_per_instance(const MmpcConfig& c) { return (size_t)c.n_obs * 3 * (c.obs_per_stage ? c.N + 1 : 1); }
 
 extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device, MmpcHandle** out) {
@@ -119,24 +115,15 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   if (!h) return MMPC_ERR_ARG;
   memset(h, 0, sizeof *h);
   h->cfg = *cfg; h->device = device; h->B_max = B_max; h->sm_count = prop.multiProcessorCount;
-  int N = cfg->N;
-  h->SP = N + 1; h->KP = ((N + 1 + 3) / 4) * 4; h->R = cfg->n_obs + 4 + (cfg->n_pl > 0 ? 6 : 0);
-  h->smem_bytes = (size_t)smem_doubles(N) * sizeof(double);
-  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, solve_kernel, 32, h->smem_bytes));
-  if (h->blocks_per_sm < 1) { snprintf(g_err, sizeof g_err, "solve_kernel does not fit on an SM (smem %zu B)", h->smem_bytes); return MMPC_ERR_CUDA; }
-  h->slots = h->sm_count * h->blocks_per_sm;
-  h->ws_stride = ws_doubles(N, h->KP, h->R);
-  CK(cudaMalloc(&h->ws, (size_t)h->slots * h->ws_stride * sizeof(double)));
-  CK(cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * sizeof(double)));
-  CK(cudaMalloc(&h->counter, sizeof(unsigned)));
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return MMPC_ERR_CUDA;
+  }
   h->kernel = MMPC_KERNEL_AUTO; h->sg_team = 1; h->sg_fused = 1; h->sg_parts = 1;
-  h->lane_warps_per_sm = 8;
-  h->lane_warp_stride = lane_instance_doubles(*cfg) * 32;
   {
-    int want = (B_max + 31) / 32, cap = h->sm_count * h->lane_warps_per_sm;
-    h->lane_warps = want < cap ? want : cap;
+    int rc = set_kernel_attributes();  // per device (the trial kernels need 81 KB of dynamic shared memory)
+    if (rc != MMPC_OK) { cudaStreamDestroy(h->stream); delete h; return rc; }
   }
   *out = h;
   return MMPC_OK;
@@ -155,15 +142,12 @@ extern "C" int mmpc_destroy(MmpcHandle* h) {
   if (!h) return MMPC_ERR_ARG;
   cudaSetDevice(h->device);
   free_staging(h);
-  if (h->ws) cudaFree(h->ws);
-  if (h->lane_ws) cudaFree(h->lane_ws);
   if (h->prof_ev) { for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e); delete h->prof_ev; }
-  if (h->sg.ready) {
-    cudaFree(h->sg.ws); cudaFree(h->sg.qp); cudaFree(h->sg.rk); cudaFree(h->sg.gd); cudaFree(h->sg.gi); cudaFree(h->sg.lists); cudaFree(h->sg.cnt);
-    cudaFreeHost(h->sg.pin);
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->sg.ev[i]);
-  }
-  if (h->counter) cudaFree(h->counter);
+  graph_destroy(h);
+  for (void* q : {(void*)h->sg.ws, (void*)h->sg.qp, (void*)h->sg.rk, (void*)h->sg.gd, (void*)h->sg.gi, (void*)h->sg.lists, (void*)h->sg.cnt, (void*)h->sg.io})
+    if (q) cudaFree(q);
+  if (h->sg.pin) cudaFreeHost(h->sg.pin);
+  for (int i = 0; i < 8; ++i) if (h->sg.ev[i]) cudaEventDestroy(h->sg.ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MMPC_OK;
@@ -176,174 +160,307 @@ extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* P
   if (Rd) memcpy(h->cfg.Rd, Rd, sizeof h->cfg.Rd);
   if (Wd) memcpy(h->cfg.Wd, Wd, sizeof h->cfg.Wd);
   if (S == S && S > 0) h->cfg.S = S;
+  cudaSetDevice(h->device);
+  graph_destroy(h);  // the weights are kernel parameters of every node
   return MMPC_OK;
 }
 
 extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
-  if (!h || kernel < MMPC_KERNEL_AUTO || kernel > MMPC_KERNEL_STAGED_FAT) return MMPC_ERR_ARG;
+  if (!h || (kernel != MMPC_KERNEL_AUTO && (kernel < MMPC_KERNEL_STAGED || kernel > MMPC_KERNEL_STAGED_HOSTLOOP))) return MMPC_ERR_ARG;
+  cudaSetDevice(h->device);
+  graph_destroy(h);
+  h->hostloop = kernel == MMPC_KERNEL_STAGED_HOSTLOOP;
   h->sg_parts = kernel != MMPC_KERNEL_STAGED_FAT;
   h->sg_team = kernel != MMPC_KERNEL_STAGED_THREAD;
   h->sg_fused = kernel != MMPC_KERNEL_STAGED_UNFUSED;
-  h->kernel = kernel >= MMPC_KERNEL_STAGED ? MMPC_KERNEL_STAGED : kernel;
+  h->kernel = MMPC_KERNEL_STAGED;
   return MMPC_OK;
 }
 
-static int launch_warp(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
-  KParams P; memset(&P, 0, sizeof P);
-  P.cfg = h->cfg; P.B = B;
-  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
-  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
-  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
-  P.ws = h->ws; P.ws_stride = h->ws_stride; P.counter = h->counter;
-  P.SP = h->SP; P.KP = h->KP; P.R = h->R;
-  int grid = B < h->slots ? B : h->slots;
-  solve_kernel<<<grid, 32, h->smem_bytes, st>>>(P);
-  CK(cudaGetLastError());
-  return MMPC_OK;
+// ---- staged solver: launch machinery ------------------------------------------------------------------------------
+// One interior-point round of the whole batch = seven kernels over the device-side lists of active instances (eight in
+// round 0, which also evaluates the starting point).  The kernels read the list lengths on the device and stride over
+// their grids, so a launch configuration only needs an UPPER BOUND of the active instances.  Two drivers issue the same
+// rounds through `Issuer`:
+//   graph      (default) the whole solve is ONE CUDA graph: round 0, then a chain of conditional WHILE nodes, one per size
+//              class of the active set (the bound halves ... down to the thin classes that switch to the spill-free
+//              Riccati instantiation and the warp-specialised part kernels).  The loop condition is written by a
+//              one-thread kernel at the end of each body from the device-side counts, so the host is out of the loop:
+//              one cudaGraphLaunch per solve, no per-round synchronisation, any number of solver contexts per host thread.
+//   host loop  (profiling, MMPC_HOSTLOOP=1) the host sequences rounds and learns the list lengths from a 16-byte copy that
+//              trails the launches by two rounds; used when every launch is bracketed by timing events.
+__global__ void staged_set_io_kernel(SIO io, SIO* dst) { *dst = io; }
+// cnt[0] E list, cnt[1] / cnt[2] trial lists, cnt[3] rounds executed
+__global__ void staged_cond_kernel(cudaGraphConditionalHandle hnd, int* cnt, int which, int above, int add_rounds) {
+  cnt[3] += add_rounds;
+  cudaGraphSetConditional(hnd, cnt[which] > above ? 1u : 0u);
 }
 
-static int launch_lane(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
-  if (!h->lane_ws) {
-    size_t bytes = (size_t)h->lane_warps * (size_t)h->lane_warp_stride * sizeof(double);
-    CK(cudaMalloc(&h->lane_ws, bytes));
-    CK(cudaMemset(h->lane_ws, 0, bytes));
+struct Issuer {
+  cudaStream_t st;          // stream mode
+  cudaGraph_t g;            // graph mode: nodes are chained one after the other
+  cudaGraphNode_t last; bool has_last;
+  long long issued;
+  int rc;
+  void launch(const void* fn, dim3 grid, dim3 block, size_t smem, void** args) {
+    if (rc != MMPC_OK) return;
+    cudaError_t e;
+    if (g) {
+      cudaKernelNodeParams kp; memset(&kp, 0, sizeof kp);
+      kp.func = const_cast<void*>(fn); kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args;
+      cudaGraphNode_t n;
+      e = cudaGraphAddKernelNode(&n, g, has_last ? &last : nullptr, has_last ? 1 : 0, &kp);
+      last = n; has_last = true;
+    } else {
+      e = cudaLaunchKernel(fn, grid, block, args, smem, st);
+    }
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "kernel launch / node failed: %s", cudaGetErrorString(e)); rc = MMPC_ERR_CUDA; }
+    ++issued;
   }
-  LParams P; memset(&P, 0, sizeof P);
-  P.cfg = h->cfg; P.B = B;
-  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
-  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
-  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
-  P.ws = h->lane_ws; P.warp_stride = h->lane_warp_stride; P.counter = h->counter;
-  P.R = lane_rows(h->cfg); P.STG = lane_stage_doubles(h->cfg); P.OG = (h->cfg.N + 1) * P.STG;
-  int warps = (B + 31) / 32;
-  if (warps > h->lane_warps) warps = h->lane_warps;
-  // few warps: one per block so they spread over the SMs; otherwise 8 warps per block, one block per SM
-  int tpb = warps <= h->sm_count ? 32 : 32 * h->lane_warps_per_sm;
-  int grid = (warps * 32 + tpb - 1) / tpb;
-  lane_kernel<<<grid, tpb, 0, st>>>(P);
-  CK(cudaGetLastError());
-  return MMPC_OK;
-}
+};
 
-// Staged solver: one interior-point round of the whole batch = six kernels over the device-side
-// lists of active instances.  The host only sequences rounds; it learns that the lists are empty
-// from a 16-byte copy that trails the launches by STAGED_LAG rounds, so the GPU queue never drains.
-static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
+static int ensure_workspace(MmpcHandle* h) {
+  if (h->sg.ready) return MMPC_OK;
   const MmpcConfig& cfg = h->cfg;
   const int N = cfg.N, STG = staged_stage_doubles(cfg);
-  if (!h->sg.ready) {
-    long long LS = ((long long)h->B_max + 31) / 32 * 32;
-    h->sg.LS = LS;
-    CK(cudaMalloc(&h->sg.ws, (size_t)(N + 1) * STG * LS * sizeof(double)));
-    CK(cudaMalloc(&h->sg.qp, (size_t)(N + 1) * QS * LS * sizeof(double)));
-    CK(cudaMalloc(&h->sg.rk, (size_t)(N + 1) * RS * LS * sizeof(double)));
-    CK(cudaMalloc(&h->sg.gd, (size_t)staged_inst_doubles(cfg) * LS * sizeof(double)));
-    CK(cudaMalloc(&h->sg.gi, (size_t)J_NFIELDS * LS * sizeof(int)));
-    CK(cudaMalloc(&h->sg.lists, (size_t)3 * LS * sizeof(int)));
-    CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
-    CK(cudaMallocHost(&h->sg.pin, 8 * 4 * sizeof(int)));
-    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming | cudaEventBlockingSync));  // the host thread sleeps, it does not spin: several contexts per GPU and ranks per box share the cores
-    h->sg.ready = true;
-  }
+  long long LS = ((long long)h->B_max + 31) / 32 * 32;
+  h->sg.LS = LS;
+  CK(cudaMalloc(&h->sg.ws, (size_t)(N + 1) * STG * LS * sizeof(double)));
+  CK(cudaMalloc(&h->sg.qp, (size_t)(N + 1) * QS * LS * sizeof(double)));
+  CK(cudaMalloc(&h->sg.rk, (size_t)(N + 1) * RS * LS * sizeof(double)));
+  CK(cudaMalloc(&h->sg.gd, (size_t)staged_inst_doubles(cfg) * LS * sizeof(double)));
+  CK(cudaMalloc(&h->sg.gi, (size_t)J_NFIELDS * LS * sizeof(int)));
+  CK(cudaMalloc(&h->sg.lists, (size_t)3 * LS * sizeof(int)));
+  CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
+  CK(cudaMalloc(&h->sg.io, sizeof(SIO)));
+  CK(cudaMallocHost(&h->sg.pin, (8 * 4 + 4) * sizeof(int)));
+  for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming | cudaEventBlockingSync));  // the host thread sleeps, it does not spin: several contexts per GPU and ranks per box share the cores
+  h->sg.ready = true;
+  return MMPC_OK;
+}
+
+static SParams staged_params(const MmpcHandle* h, int32_t B) {
+  const MmpcConfig& cfg = h->cfg;
   SParams P; memset(&P, 0, sizeof P);
-  P.cfg = cfg; P.B = B;
-  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
-  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
-  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  P.cfg = cfg; P.B = B; P.io = h->sg.io;
   P.ws = h->sg.ws; P.qp = h->sg.qp; P.rk = h->sg.rk; P.team = h->sg_team; P.fused = h->sg_fused;
   const PartPlan plan = part_plan(cfg);
-  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10 && cfg.mode == MMPC_MODE_CLEAN) ? 1 : 0; P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
-  P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = STG; P.ND = staged_inst_doubles(cfg);
+  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10 && cfg.mode == MMPC_MODE_CLEAN) ? 1 : 0;
+  P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
+  P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = staged_stage_doubles(cfg); P.ND = staged_inst_doubles(cfg);
+  return P;
+}
+
+static const int ring_smem = 128 * STAGED_RING_DOUBLES * (int)sizeof(double);              // row ring of the step kernels: 24 KB per block of 128
+static const int trial_ring_smem = 128 * STAGED_TRIAL_RING_DOUBLES * (int)sizeof(double);  // row ring + parked multipliers and inputs of the trial kernels: 81 KB
+
+// cudaFuncSetAttribute is per device: called by mmpc_create after cudaSetDevice (idempotent, so concurrent creates are fine)
+static int set_kernel_attributes() {
+  CK(cudaFuncSetAttribute(staged_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
+  CK(cudaFuncSetAttribute(staged_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
+  CK(cudaFuncSetAttribute(staged_trial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
+  CK(cudaFuncSetAttribute(staged_trial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
+  return MMPC_OK;
+}
+
+// thin classes: every instance gets its own half warp at TEAM_WARPS_THIN warps per SM -> the spill-free Riccati; every
+// tile of 32 (instance, stage) items gets its own SM -> the warp-specialised part kernels (clean NLP only)
+static bool class_thin_team(const MmpcHandle* h, long long ub) { return ub * 16 <= (long long)h->sm_count * TEAM_WARPS_THIN * 32; }
+static bool class_thin_parts(const MmpcHandle* h, const SParams& P, long long ub) {
+  static const long long parts_tiles = getenv("MMPC_PARTS_TILES") ? atoll(getenv("MMPC_PARTS_TILES")) : -1;  // A/B knob
+  return P.parts && (ub * (P.cfg.N + 1) + 31) / 32 <= (parts_tiles >= 0 ? parts_tiles : (long long)h->sm_count);
+}
+
+// Issues round r for at most `ub` active instances.  `mark` (host loop with profiling) is called in front of every launch.
+template <class Mark>
+static void issue_round(MmpcHandle* h, Issuer& I, SParams P, int r, long long ub, bool with_eval, Mark&& mark) {
+  const MmpcConfig& cfg = h->cfg;
+  const int N = cfg.N;
+  static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
+  static const int team_cap = getenv("MMPC_TEAM_GRID") ? atoi(getenv("MMPC_TEAM_GRID")) : 0;  // A/B: blocks per SM of the team kernel (0: one block per 2 instances)
+  const int cap = h->sm_count * cap_mult;
+  const bool ref = cfg.mode == MMPC_MODE_REFERENCE;
+  const bool q3 = ref && cfg.terminal_rows_on_sN == 0;  // terminal self-collision rows on s[N-1] (SURVEY.md 8(a) row 9)
+  const PartPlan plan = part_plan(cfg);
+  auto clampi = [](long long v, long long lo, long long hi) { return (int)(v < lo ? lo : v > hi ? hi : v); };
+  const long long items = ub * (N + 1);
+  const int gs = clampi((items + 127) / 128, 1, cap);
+  const int g64 = clampi((ub + 63) / 64, 1, 1 << 30);
+  int gt = clampi((ub * 16 + MMPC_TEAM_BLOCK - 1) / MMPC_TEAM_BLOCK, 1, 1 << 30);
+  if (team_cap > 0 && gt > team_cap * h->sm_count) gt = team_cap * h->sm_count;
+  const int gw = clampi((ub * 32 + 127) / 128, 1, cap);  // one warp per instance
+  const int gtile = clampi((items + 31) / 32, 1, 8LL * cap);
+  const int tcur = 1 + (r & 1), tnext = 1 + ((r + 1) & 1);
+  const int cthreads = ub > 16384 ? 1024 : ub > 2048 ? 256 : 64;
+  const bool thin_team = class_thin_team(h, ub), thin = class_thin_parts(h, P, ub);
+  int dst, src, want;
+  void* a1[] = {&P};
+  void* a4[] = {&P, &dst, &src, &want};
+  mark(MMPC_PHASE_COMPACT);
+  dst = 0; src = tcur; want = ST_ACTIVE;
+  I.launch((const void*)staged_compact_kernel, dim3(1), dim3(cthreads), 0, a4);
+  if (with_eval) {  // fused: the trial kernel has already evaluated every later accepted point
+    mark(MMPC_PHASE_EVAL);
+    I.launch(ref ? (const void*)staged_eval_kernel<true> : (const void*)staged_eval_kernel<false>, dim3(gs), dim3(128), 0, a1);
+  }
+  mark(MMPC_PHASE_SOLVE);
+  if (P.team) {
+    const void* fn = q3 ? (thin_team ? (const void*)staged_solve_team_kernel<true, TEAM_WARPS_THIN> : (const void*)staged_solve_team_kernel<true, TEAM_WARPS_BULK>)
+                        : (thin_team ? (const void*)staged_solve_team_kernel<false, TEAM_WARPS_THIN> : (const void*)staged_solve_team_kernel<false, TEAM_WARPS_BULK>);
+    I.launch(fn, dim3(gt), dim3(MMPC_TEAM_BLOCK), 0, a1);
+  } else I.launch((const void*)staged_solve_kernel, dim3(g64), dim3(64), 0, a1);
+  mark(MMPC_PHASE_STEP);
+  if (thin) I.launch((const void*)staged_parts_kernel<false>, dim3(gtile), dim3(32 * plan.n_parts), 0, a1);
+  else I.launch(ref ? (const void*)staged_step_kernel<true> : (const void*)staged_step_kernel<false>, dim3(gs), dim3(128), ring_smem, a1);
+  mark(MMPC_PHASE_CTRL_STEP);
+  I.launch((const void*)staged_ctrl_step_kernel, dim3(gw), dim3(128), 0, a1);
+  mark(MMPC_PHASE_COMPACT);
+  dst = tnext; src = tcur; want = ST_TRIAL;
+  I.launch((const void*)staged_compact_kernel, dim3(1), dim3(cthreads), 0, a4);
+  P.tsel = tnext;
+  mark(MMPC_PHASE_TRIAL);
+  if (thin) I.launch((const void*)staged_parts_kernel<true>, dim3(gtile), dim3(32 * plan.n_parts), 0, a1);
+  else I.launch(ref ? (const void*)staged_trial_kernel<true> : (const void*)staged_trial_kernel<false>, dim3(gs), dim3(128), trial_ring_smem, a1);
+  mark(MMPC_PHASE_CTRL_TRIAL);
+  I.launch((const void*)staged_ctrl_trial_kernel, dim3(gw), dim3(128), 0, a1);
+}
+
+static void issue_init(MmpcHandle* h, Issuer& I, SParams P) {
+  void* a1[] = {&P};
+  I.launch((const void*)staged_init_kernel, dim3((P.B + 127) / 128), dim3(128), 0, a1);
+}
+
+// ---- driver 1: the whole solve as one CUDA graph with device-side loops --------------------------------------------------
+static void graph_destroy(MmpcHandle* h) {
+  graph_account(h);
+  for (auto& e : h->gr.e) {
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+    if (e.graph) cudaGraphDestroy(e.graph);
+    e.exec = nullptr; e.graph = nullptr; e.cap = 0;
+  }
+}
+
+// launch configurations are chosen for a capacity, not for the batch size: B_max itself, else the next power of two (>= 64)
+static int graph_capacity(const MmpcHandle* h, int32_t B) {
+  long long c = 64;
+  while (c < B) c *= 2;
+  return (int)(c >= h->B_max ? h->B_max : c);
+}
+
+static int graph_build(MmpcHandle* h, int32_t B, int slot) {
+  auto& E = h->gr.e[slot];
+  if (E.exec) cudaGraphExecDestroy(E.exec);
+  if (E.graph) cudaGraphDestroy(E.graph);
+  E.exec = nullptr; E.graph = nullptr; E.cap = 0;
+  SParams P = staged_params(h, B);
+  cudaGraph_t g;
+  CK(cudaGraphCreate(&g, 0));
+  E.graph = g;
+  Issuer I; memset(&I, 0, sizeof I); I.g = g; I.rc = MMPC_OK;
+  auto nomark = [](int) {};
+  issue_init(h, I, P);
+  issue_round(h, I, P, 0, B, true, nomark);
+  // size classes of the active set: B, B/2, B/4, ... and the two thin thresholds; a loop per class, entered in turn
+  // (the active set only shrinks).  Class c runs while  count > lower bound of c  with launch bounds for `ub[c]`.
+  std::vector<long long> ub;
+  {
+    const long long t_team = (long long)h->sm_count * TEAM_WARPS_THIN * 32 / 16;                    // largest thin-team count
+    const long long t_parts = P.parts ? ((long long)h->sm_count * 32) / (h->cfg.N + 1) : 0;          // largest part-kernel count
+    const long long t_floor = 64;                                                                    // last class: grids for <= 64 instances
+    long long v = B;
+    ub.push_back(v);
+    while (v > 2 * t_team) { v = (v + 1) / 2; ub.push_back(v); }
+    for (long long t : {t_team, t_parts, t_floor}) if (t > 0 && t < ub.back()) ub.push_back(t);
+  }
+  for (size_t c = 0; c < ub.size(); ++c) {
+    const int low = c + 1 < ub.size() ? (int)ub[c + 1] : 0;   // run this class while more than `low` instances are active
+    cudaGraphConditionalHandle hnd;
+    CK(cudaGraphConditionalHandleCreate(&hnd, g, 0, 0));
+    // entry condition: the trial list of the last round (parity 0 rounds write list 2) holds every active instance
+    int* cnt = h->sg.cnt; int which = 2, above = low, add = 0;
+    void* ac[] = {&hnd, &cnt, &which, &above, &add};
+    I.launch((const void*)staged_cond_kernel, dim3(1), dim3(1), 0, ac);
+    if (I.rc != MMPC_OK) return I.rc;
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = hnd; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+    cudaGraphNode_t wn;
+    CK(cudaGraphAddNode(&wn, g, &I.last, 1, &cp));
+    I.last = wn;
+    Issuer Bd; memset(&Bd, 0, sizeof Bd); Bd.g = cp.conditional.phGraph_out[0]; Bd.rc = MMPC_OK;
+    issue_round(h, Bd, P, 1, ub[c], false, nomark);   // lists ping-pong over rounds: a body is an odd and an even round
+    issue_round(h, Bd, P, 2, ub[c], false, nomark);
+    add = 2;
+    Bd.launch((const void*)staged_cond_kernel, dim3(1), dim3(1), 0, ac);
+    if (Bd.rc != MMPC_OK) return Bd.rc;
+  }
+  // the counters of the solve (rounds executed) for mmpc_launch_count / mmpc_phase_times
+  {
+    cudaGraphNode_t mn;
+    CK(cudaGraphAddMemcpyNode1D(&mn, g, &I.last, 1, h->sg.pin + 32, h->sg.cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  CK(cudaGraphInstantiate(&E.exec, g, 0));
+  E.cap = B; E.classes = (int)ub.size();
+  return MMPC_OK;
+}
+
+static int launch_staged_graph(MmpcHandle* h, int32_t B, cudaStream_t st) {
+  const int cap = graph_capacity(h, B);
+  int slot = -1;
+  for (int i = 0; i < 4; ++i) if (h->gr.e[i].exec && h->gr.e[i].cap == cap) slot = i;
+  if (slot < 0) {
+    slot = h->gr.next; h->gr.next = (h->gr.next + 1) & 3;
+    int rc = graph_build(h, cap, slot);
+    if (rc != MMPC_OK) { graph_destroy(h); return rc; }
+  }
+  h->sg.pin[32 + 3] = -1;
+  CK(cudaGraphLaunch(h->gr.e[slot].exec, st));
+  h->gr.pending = true; h->gr.pending_classes = h->gr.e[slot].classes;
+  return MMPC_OK;
+}
+
+// launches the GPU executed for graph solves: 1 (io) + 1 (init) + 8 (round 0) + 7 per later round + one condition kernel per
+// class entry and per loop body; valid once the caller has synchronised the stream of the solve
+static void graph_account(MmpcHandle* h) {
+  if (!h->gr.pending) return;
+  const int rounds = h->sg.pin[32 + 3];
+  if (rounds < 0) return;  // the solve has not finished yet
+  h->gr.pending = false;
+  h->sg.rounds = 1 + rounds;
+  h->launches += 2 + 8 + 7LL * rounds + h->gr.pending_classes + rounds / 2;
+}
+
+// ---- driver 2: the host sequences rounds (profiling; MMPC_HOSTLOOP=1) ----------------------------------------------------
+static int launch_staged_hostloop(MmpcHandle* h, int32_t B, cudaStream_t st) {
+  SParams P = staged_params(h, B);
+  Issuer I; memset(&I, 0, sizeof I); I.st = st; I.rc = MMPC_OK;
   // profiling: one timing event in front of every launch; the time up to the next event is
   // charged to that launch's phase (events are stream-ordered, so this is device time)
   std::vector<int> marks;
   size_t nmark = 0;
-  auto mark = [&](int phase) -> int {
+  int mrc = MMPC_OK;
+  auto mark = [&](int phase) {
     h->phase_launches[phase < 0 ? 0 : phase] += (phase >= 0);
-    if (!h->profile) return MMPC_OK;
+    if (!h->profile || mrc != MMPC_OK) return;
     if (!h->prof_ev) h->prof_ev = new std::vector<cudaEvent_t>();
-    if (nmark == h->prof_ev->size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->prof_ev->push_back(e); }
-    CK(cudaEventRecord((*h->prof_ev)[nmark++], st));
+    if (nmark == h->prof_ev->size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { mrc = MMPC_ERR_CUDA; return; }
+      h->prof_ev->push_back(e);
+    }
+    if (cudaEventRecord((*h->prof_ev)[nmark++], st) != cudaSuccess) { mrc = MMPC_ERR_CUDA; return; }
     marks.push_back(phase);
-    return MMPC_OK;
   };
-#define MARK(ph) do { int rc_ = mark(ph); if (rc_ != MMPC_OK) return rc_; } while (0)
   for (int i = 0; i < MMPC_NPHASE; ++i) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
-  MARK(MMPC_PHASE_INIT);
-  staged_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(P);
-  CK(cudaGetLastError());
-  h->launches += 1;
-  // row ring of the step kernels: STAGED_RING_DOUBLES per thread (24 KB per block of 128)
-  const int ring_smem = 128 * STAGED_RING_DOUBLES * (int)sizeof(double);
-  const int trial_ring_smem = 128 * STAGED_TRIAL_RING_DOUBLES * (int)sizeof(double);  // row ring of the trial kernels (24 KB)
-  static bool smem_attr_done = false;
-  if (!smem_attr_done) {
-    smem_attr_done = true;
-    CK(cudaFuncSetAttribute(staged_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
-    CK(cudaFuncSetAttribute(staged_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem));
-    CK(cudaFuncSetAttribute(staged_trial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
-    CK(cudaFuncSetAttribute(staged_trial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
-    CK(cudaFuncSetAttribute(staged_trial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
-    CK(cudaFuncSetAttribute(staged_trial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, trial_ring_smem));
-  }
-  static const int cap_mult = getenv("MMPC_GRID_CAP") ? atoi(getenv("MMPC_GRID_CAP")) : 128;  // blocks per SM before grid-striding (A/B: 128 beats 16 by 1.7 %)
-  const int LAG = 2, cap = h->sm_count * cap_mult;
-  const bool ref = cfg.mode == MMPC_MODE_REFERENCE;
-  const bool q3 = ref && cfg.terminal_rows_on_sN == 0;  // terminal self-collision rows on s[N-1] (SURVEY.md 8(a) row 9)
+  mark(MMPC_PHASE_INIT);
+  issue_init(h, I, P);
+  const int LAG = 2;
   long long ub = B;  // upper bound of the active instances (the lists only shrink)
   int r = 0;
   for (;; ++r) {
-    long long items = ub * (N + 1);
-    int gs = (int)((items + 127) / 128 < cap ? (items + 127) / 128 : cap);
-    int gi_ = (int)((ub + 127) / 128), g64 = (int)((ub + 63) / 64);
-    static const int team_cap = getenv("MMPC_TEAM_GRID") ? atoi(getenv("MMPC_TEAM_GRID")) : 0;  // A/B: blocks per SM of the team kernel (0: one block per 8 instances)
-    int gt = (int)((ub * 16 + MMPC_TEAM_BLOCK - 1) / MMPC_TEAM_BLOCK);
-    if (team_cap > 0 && gt > team_cap * h->sm_count) gt = team_cap * h->sm_count;
-    int gw = (int)((ub * 32 + 127) / 128 < cap ? (ub * 32 + 127) / 128 : cap);  // one warp per instance
-    if (gw < 1) gw = 1;
-    int gtile = (int)((items + 31) / 32 < 8 * cap ? (items + 31) / 32 : 8 * cap);
-    if (gtile < 1) gtile = 1;
-    if (gs < 1) gs = 1; if (gi_ < 1) gi_ = 1; if (g64 < 1) g64 = 1; if (gt < 1) gt = 1;
-    MARK(MMPC_PHASE_COMPACT);
-    const int tcur = 1 + (r & 1), tnext = 1 + ((r + 1) & 1);
-    const int cthreads = ub > 16384 ? 1024 : ub > 2048 ? 256 : 64;
-    staged_compact_kernel<<<1, cthreads, 0, st>>>(P, 0, tcur, ST_ACTIVE);
-    if (!P.fused || r == 0) {  // fused: the trial kernel has already evaluated the accepted point
-      MARK(MMPC_PHASE_EVAL);
-      if (ref) staged_eval_kernel<true><<<gs, 128, 0, st>>>(P); else staged_eval_kernel<false><<<gs, 128, 0, st>>>(P);
-    }
-    MARK(MMPC_PHASE_SOLVE);
-    if (P.team) {
-      // thin round: every instance gets its own half warp at TEAM_WARPS_THIN warps per SM -> the spill-free instantiation
-      const bool thin_team = ub * 16 <= (long long)h->sm_count * TEAM_WARPS_THIN * 32;
-      if (q3) {
-        if (thin_team) staged_solve_team_kernel<true, TEAM_WARPS_THIN><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
-        else staged_solve_team_kernel<true, TEAM_WARPS_BULK><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
-      } else {
-        if (thin_team) staged_solve_team_kernel<false, TEAM_WARPS_THIN><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
-        else staged_solve_team_kernel<false, TEAM_WARPS_BULK><<<gt, MMPC_TEAM_BLOCK, 0, st>>>(P);
-      }
-    }
-    else staged_solve_kernel<<<g64, 64, 0, st>>>(P);
-    MARK(MMPC_PHASE_STEP);
-    static const long long parts_tiles = getenv("MMPC_PARTS_TILES") ? atoll(getenv("MMPC_PARTS_TILES")) : -1;  // A/B knob
-    const bool thin = P.parts && (items + 31) / 32 <= (parts_tiles >= 0 ? parts_tiles : (long long)h->sm_count);  // every tile gets its own SM
-    if (thin) staged_parts_kernel<false><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
-    else if (ref) staged_step_kernel<true><<<gs, 128, ring_smem, st>>>(P);
-    else staged_step_kernel<false><<<gs, 128, ring_smem, st>>>(P);
-    MARK(MMPC_PHASE_CTRL_STEP);
-    staged_ctrl_step_kernel<<<gw, 128, 0, st>>>(P);
-    MARK(MMPC_PHASE_COMPACT);
-    staged_compact_kernel<<<1, cthreads, 0, st>>>(P, tnext, tcur, ST_TRIAL);
-    P.tsel = tnext;
-    MARK(MMPC_PHASE_TRIAL);
-    if (thin) staged_parts_kernel<true><<<gtile, 32 * plan.n_parts, 0, st>>>(P);
-    else if (ref) staged_trial_kernel<true><<<gs, 128, trial_ring_smem, st>>>(P);
-    else staged_trial_kernel<false><<<gs, 128, trial_ring_smem, st>>>(P);
-    MARK(MMPC_PHASE_CTRL_TRIAL);
-    staged_ctrl_trial_kernel<<<gw, 128, 0, st>>>(P);
-    CK(cudaGetLastError());
-    h->launches += (!P.fused || r == 0) ? 8 : 7;
+    issue_round(h, I, P, r, ub, !P.fused || r == 0, mark);
+    if (I.rc != MMPC_OK) return I.rc;
+    if (mrc != MMPC_OK) { snprintf(g_err, sizeof g_err, "profiling event failed"); return mrc; }
     // the list lengths of this round trail the launches by LAG rounds
     int slot = r & 7;
     CK(cudaMemcpyAsync(h->sg.pin + 4 * slot, h->sg.cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -360,16 +477,33 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     if (r > 4000000) break;
   }
   if (h->profile) {
-    MARK(-1);
+    mark(-1);
     CK(cudaEventSynchronize((*h->prof_ev)[nmark - 1]));
     for (size_t i = 0; i + 1 < nmark; ++i) {
       float ms = 0; CK(cudaEventElapsedTime(&ms, (*h->prof_ev)[i], (*h->prof_ev)[i + 1]));
       if (marks[i] >= 0) h->phase_ms[marks[i]] += ms;
     }
   }
-#undef MARK
+  h->launches += I.issued + 1;
   h->sg.rounds = r + 1;
   return MMPC_OK;
+}
+
+static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, cudaStream_t st) {
+  int rc = ensure_workspace(h);
+  if (rc != MMPC_OK) return rc;
+  graph_account(h);
+  SIO io; memset(&io, 0, sizeof io);
+  io.x_init = in->x_init; io.x_ref = in->x_ref; io.u_ref = in->u_ref; io.u_last = in->u_last; io.u_guess = in->u_guess;
+  io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags;
+  io.U = out->U; io.X = out->X; io.s = out->s; io.cost = out->cost; io.kkt = out->kkt; io.iters = out->iters; io.status = out->status;
+  io.B = B;
+  staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io);
+  CK(cudaGetLastError());
+  static const bool force_hostloop = getenv("MMPC_HOSTLOOP") && atoi(getenv("MMPC_HOSTLOOP")) != 0;
+  // (the unfused A/B variant evaluates in every round: host loop only)
+  if (h->profile || force_hostloop || h->hostloop || !h->sg_fused) return launch_staged_hostloop(h, B, st);
+  return launch_staged_graph(h, B, st);
 }
 
 extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const MmpcBatchOut* out, void* stream) {
@@ -379,17 +513,10 @@ extern "C" int mmpc_solve(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const
   if ((h->cfg.n_obs > 0 && !in->circles) || (h->cfg.n_pl > 0 && !in->planes)) return MMPC_ERR_ARG;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
-  int kernel = h->kernel == MMPC_KERNEL_AUTO ? MMPC_KERNEL_STAGED : h->kernel;
-  // the terminal equality (flags) is implemented by the staged solver with the fused trial kernel only
-  if (in->flags && (kernel != MMPC_KERNEL_STAGED || !h->sg_fused)) return MMPC_ERR_UNSUPPORTED;
-  // so are the reference NLP's bug-for-bug rows (MMPC_MODE_REFERENCE)
-  if (h->cfg.mode != MMPC_MODE_CLEAN && (kernel != MMPC_KERNEL_STAGED || !h->sg_fused)) return MMPC_ERR_UNSUPPORTED;
-  if (kernel == MMPC_KERNEL_STAGED) return launch_staged(h, B, in, out, st);
-  int rc = kernel == MMPC_KERNEL_LANE ? launch_lane(h, B, in, out, st) : launch_warp(h, B, in, out, st);
-  if (rc != MMPC_OK) return rc;
-  h->launches += 1;
-  return MMPC_OK;
+  // the terminal equality (flags) and the reference NLP's bug-for-bug rows (MMPC_MODE_REFERENCE) are implemented by
+  // the fused trial + evaluation kernel only
+  if ((in->flags || h->cfg.mode != MMPC_MODE_CLEAN) && !h->sg_fused) return MMPC_ERR_UNSUPPORTED;
+  return launch_staged(h, B, in, out, st);
 }
 
 template <class T>
@@ -569,6 +696,7 @@ extern "C" int mmpc_phase_times(const MmpcHandle* h, double* ms, int64_t* launch
     if (ms) ms[i] = h->phase_ms[i];
     if (launches) launches[i] = h->phase_launches[i];
   }
+  graph_account(const_cast<MmpcHandle*>(h));
   if (rounds) *rounds = h->sg.rounds;
   return MMPC_OK;
 }
@@ -641,13 +769,17 @@ extern "C" int mmpc_episode_update(MmpcHandle* h, int32_t B, int32_t M, int32_t 
   return MMPC_OK;
 }
 
-extern "C" int64_t mmpc_launch_count(const MmpcHandle* h) { return h ? h->launches : 0; }
+extern "C" int64_t mmpc_launch_count(const MmpcHandle* h) {
+  if (!h) return 0;
+  graph_account(const_cast<MmpcHandle*>(h));  // rounds of the last graph solve (the caller has synchronised its stream)
+  return h->launches;
+}
 
 extern "C" int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* blocks_per_sm, int32_t* smem_bytes) {
   if (!h) return MMPC_ERR_ARG;
   if (sm_count) *sm_count = h->sm_count;
-  if (blocks_per_sm) *blocks_per_sm = h->blocks_per_sm;
-  if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
+  if (blocks_per_sm) *blocks_per_sm = TEAM_WARPS_BULK;                                  // resident warps per SM of the Riccati kernel
+  if (smem_bytes) *smem_bytes = (int32_t)(Team::SMEM_DOUBLES * 2 * sizeof(double));     // its ring, per warp (two instances)
   return MMPC_OK;
 }
 

@@ -1,6 +1,5 @@
-// mmpc_ipm.cuh -- scalar pieces of the interior-point iteration shared by the lane-per-instance
-// kernel (mmpc_lane.cuh) and the warp-cooperative kernel (mmpc_solver.cuh): IPOPT's scaled KKT
-// error, the bound push of the starting point, and a cheap running log-barrier sum.
+// mmpc_ipm.cuh -- scalar pieces of the interior-point iteration shared by the phase kernels: IPOPT's
+// scaled KKT error, the bound push of the starting point, and a cheap running log-barrier sum.
 #pragma once
 #include "mmpc_model.cuh"
 
@@ -33,7 +32,7 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi) {
 
 // Reciprocal instead of an IEEE division (a double division is ~35 instructions with its slow-path
 // check; one reciprocal feeds every quotient with the same denominator).
-#if defined(MMPC_EMULATE) || defined(MMPC_EMULATE_LANE)
+#if defined(MMPC_EMULATE_LANE)
 __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 #else
 #ifdef MMPC_RCP_RN
@@ -53,7 +52,7 @@ __device__ __forceinline__ double rcp(double x) {
 #endif
 // 1/sqrt(x) for the squared distances of the circle and self-collision rows (x > 0, normal): MUFU.RSQ64H seed (relative
 // error 2^-22) and two Newton steps, no special-case path.
-#if defined(MMPC_EMULATE) || defined(MMPC_EMULATE_LANE) || defined(MMPC_RCP_RN)
+#if defined(MMPC_EMULATE_LANE) || defined(MMPC_RCP_RN)
 __device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
 #else
 __device__ __forceinline__ double rsq(double x) {

@@ -41,14 +41,23 @@
 
 namespace mmpc {
 
-struct SParams {
-  MmpcConfig cfg;
-  int B;
+// The caller's arrays of one mmpc_solve call (include/mmpc.h: MmpcBatchIn / MmpcBatchOut).  They live in a small block of
+// DEVICE memory that a one-thread kernel rewrites in front of every solve, so the kernel parameters -- and with them the
+// CUDA graph of the solve (mmpc_api.cu) -- do not change when the caller passes other buffers.  Only init() reads the
+// inputs and only finish() / finish_stage() / ctrl_step() write the outputs.
+struct SIO {
   const double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes;
   const int32_t* n_pl_inst;
   const uint8_t* flags;
   double *U, *X, *s, *cost, *kkt;
   int32_t *iters, *status;
+  int B;           // instances of this call
+};
+
+struct SParams {
+  MmpcConfig cfg;
+  int B;           // capacity the launch configurations were chosen for (>= io->B)
+  const SIO* io;   // device memory (host memory under tests/emu)
   double* ws;      // per-stage records, field-major / instance-minor
   double* qp;      // stage QP records      qp[(k*LS + b)*QS + f]
   double* rk;      // Riccati records       rk[(k*LS + b)*RS + f]
@@ -213,25 +222,26 @@ struct Inst {
   // guess (:302-304) + IPOPT bound push; s lifted so every row starts strictly feasible;
   // objective scaling.
   __device__ void init() {
-    const double* xref = P.x_ref + (long long)b * (N + 1) * NX;
-    const double* uref = P.u_ref + (long long)b * N * NU;
-    const double* ulast = P.u_last + (long long)b * N * NU;
-    npl = P.n_pl_inst ? ldg(P.n_pl_inst + b) : cfg.n_pl;
+    const double* xref = P.io->x_ref + (long long)b * (N + 1) * NX;
+    const double* uref = P.io->u_ref + (long long)b * N * NU;
+    const double* ulast = P.io->u_last + (long long)b * N * NU;
+    npl = P.io->n_pl_inst ? ldg(P.io->n_pl_inst + b) : cfg.n_pl;
+    npl = npl < 0 ? 0 : (npl > cfg.n_pl ? cfg.n_pl : npl);  // a caller's value outside [0, n_pl] must not index past the plane tables
     J(J_NPL) = npl;
     for (int j = 0; j < cfg.n_pl; ++j)
-      for (int c = 0; c < 6; ++c) D(D_PL + 6 * j + c) = ldg(P.planes + ((long long)b * cfg.n_pl + j) * 6 + c);
+      for (int c = 0; c < 6; ++c) D(D_PL + 6 * j + c) = ldg(P.io->planes + ((long long)b * cfg.n_pl + j) * 6 + c);
     if (!cfg.obs_per_stage)
-      for (int i = 0; i < 3 * nobs; ++i) D(D_CIRC + i) = ldg(P.circles + (long long)b * 3 * nobs + i);
+      for (int i = 0; i < 3 * nobs; ++i) D(D_CIRC + i) = ldg(P.io->circles + (long long)b * 3 * nobs + i);
     double gmax = 0;
     const bool refmode = cfg.mode == MMPC_MODE_REFERENCE && npl > 1;
     double cprev[6][MMPC_MAX_PLANES], ccur[6][MMPC_MAX_PLANES];
     for (int k = 0; k <= N; ++k) {
       double x[NX];
       if (cfg.obs_per_stage)
-        for (int i = 0; i < 3 * nobs; ++i) W2(k, S_DT + R + i) = ldg(P.circles + ((long long)b * (N + 1) + k) * 3 * nobs + i);
+        for (int i = 0; i < 3 * nobs; ++i) W2(k, S_DT + R + i) = ldg(P.io->circles + ((long long)b * (N + 1) + k) * 3 * nobs + i);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = fmax(fmin(ldg(P.x_init + (long long)b * NX + i), cfg.xlim[1][i]), cfg.xlim[0][i]);  // :290-291
+        double v = fmax(fmin(ldg(P.io->x_init + (long long)b * NX + i), cfg.xlim[1][i]), cfg.xlim[0][i]);  // :290-291
         if (k >= 1) v = push_in(v, cfg.xlim[0][i], cfg.xlim[1][i]);
         double xr = ldg(xref + k * NX + i);
         x[i] = v; W(k, I_X + i) = v; W(k, I_LAM + i) = 0; W2(k, IN_XREF + i) = xr;
@@ -245,7 +255,7 @@ struct Inst {
           double ul = ldg(ulast + k * NU + j), ur = ldg(uref + k * NU + j);
           double lo = fmax(cfg.ulim[0][j], ul + cfg.dulim[0][j]);  // mpc_wholebody_qref.py:203 and :205 merged
           double hi = fmin(cfg.ulim[1][j], ul + cfg.dulim[1][j]);
-          double v = P.u_guess ? ldg(P.u_guess + ((long long)b * N + k) * NU + j) : ul;
+          double v = P.io->u_guess ? ldg(P.io->u_guess + ((long long)b * N + k) * NU + j) : ul;
           v = push_in(v, lo, hi);
           W(k, I_U + j) = v; W2(k, IN_UREF + j) = ur; W2(k, IN_ULAST + j) = ul; W2(k, IN_ULO + j) = lo; W2(k, IN_UHI + j) = hi;
           W(k, I_ZUL + j) = 1; W(k, I_ZUU + j) = 1;
@@ -301,7 +311,7 @@ struct Inst {
     D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
     D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
     J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0;
-    J(J_FLAGS) = P.flags ? (int)P.flags[b] : 0;
+    J(J_FLAGS) = P.io->flags ? (int)P.io->flags[b] : 0;
   }
 
   struct RowAcc {
@@ -1007,23 +1017,23 @@ struct Inst {
       for (int i = 0; i < NX; ++i) {
         double v = W(k, it + I_X + i), e = v - W2(k, IN_XREF + i);
         fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
-        if (P.X) P.X[((long long)b * (N + 1) + k) * NX + i] = v;
+        if (P.io->X) P.io->X[((long long)b * (N + 1) + k) * NX + i] = v;
       }
       if (k < N)
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           double v = W(k, it + I_U + j), e = v - W2(k, IN_UREF + j), dl = v - W2(k, IN_ULAST + j);
           fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
-          P.U[((long long)b * N + k) * NU + j] = v;
+          P.io->U[((long long)b * N + k) * NU + j] = v;
         }
       double s = W(k, it + I_S);
       fsum += cfg.S * s * s;
-      if (P.s) P.s[(long long)b * (N + 1) + k] = s;
+      if (P.io->s) P.io->s[(long long)b * (N + 1) + k] = s;
     }
-    if (P.cost) P.cost[b] = fsum;
-    if (P.kkt) P.kkt[b] = D(D_E0);
-    if (P.iters) P.iters[b] = J(J_IT);
-    P.status[b] = status;
+    if (P.io->cost) P.io->cost[b] = fsum;
+    if (P.io->kkt) P.io->kkt[b] = D(D_E0);
+    if (P.io->iters) P.io->iters[b] = J(J_IT);
+    P.io->status[b] = status;
     J(J_STATE) = ST_DONE;
   }
 
@@ -1228,18 +1238,18 @@ struct Inst {
     for (int i = 0; i < NX; ++i) {
       double v = W(k, it + I_X + i), e = v - W2(k, IN_XREF + i);
       fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
-      if (P.X) P.X[((long long)b * (N + 1) + k) * NX + i] = v;
+      if (P.io->X) P.io->X[((long long)b * (N + 1) + k) * NX + i] = v;
     }
     if (k < N)
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
         double v = W(k, it + I_U + j), e = v - W2(k, IN_UREF + j), dl = v - W2(k, IN_ULAST + j);
         fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
-        P.U[((long long)b * N + k) * NU + j] = v;
+        P.io->U[((long long)b * N + k) * NU + j] = v;
       }
     double s = W(k, it + I_S);
     fsum += cfg.S * s * s;
-    if (P.s) P.s[(long long)b * (N + 1) + k] = s;
+    if (P.io->s) P.io->s[(long long)b * (N + 1) + k] = s;
     W2(k, S_PART + 0) = fsum;
   }
 
@@ -1255,10 +1265,10 @@ struct Inst {
       for (int k = lane; k <= N; k += NL) fsum += W2(k, S_PART + 0);
       fsum = lanes_sum<NL>(fsum);
       if (lane == 0) {
-        if (P.cost) P.cost[b] = fsum;
-        if (P.kkt) P.kkt[b] = D(D_E0);
-        if (P.iters) P.iters[b] = J(J_IT);
-        P.status[b] = J(J_STATUS);
+        if (P.io->cost) P.io->cost[b] = fsum;
+        if (P.io->kkt) P.io->kkt[b] = D(D_E0);
+        if (P.io->iters) P.io->iters[b] = J(J_IT);
+        P.io->status[b] = J(J_STATUS);
         J(J_STATE) = ST_DONE;
       }
       return false;
@@ -1842,8 +1852,9 @@ __global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_const
 // ---- kernels: grid-stride loops over the device-side list counts --------------------------------------
 __global__ void __launch_bounds__(128) staged_init_kernel(const __grid_constant__ SParams P) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < P.B) { body_init(P, b); list_n(P, 1)[b] = b; }  // every instance starts in the first source list
-  if (b == 0) P.cnt[1] = P.B;
+  const int B = P.io->B;
+  if (b < B) { body_init(P, b); list_n(P, 1)[b] = b; }  // every instance starts in the first source list
+  if (b == 0) { P.cnt[1] = B; P.cnt[3] = 0; }
 }
 template <bool REF>
 __global__ void __launch_bounds__(128) staged_eval_kernel(const __grid_constant__ SParams P) {

@@ -1,15 +1,13 @@
 // mmpc_warp.cuh -- the handful of warp primitives the solver kernel uses.
 //
-// Under nvcc these are the CUDA intrinsics.  Under -DMMPC_EMULATE (tests/emu/, g++ only) the
-// same names are provided by a 32-coroutine lane emulator so the *kernel source itself* can be
-// executed and debugged on a CPU-only box; the emulator is test infrastructure and is never
-// part of the shipped library (the product path has no CPU fallback).
+// Under nvcc these are the CUDA intrinsics.  Under -DMMPC_EMULATE_LANE (tests/emu/, g++ only) the
+// same names are provided by a lane emulator (one lane at a time, 16 coroutines for the team phase) so
+// the *kernel source itself* can be executed and debugged on a CPU-only box; the emulator is test
+// infrastructure and is never part of the shipped library (the product path has no CPU fallback).
 #pragma once
 
 #if defined(MMPC_EMULATE_LANE)
 #include "emu_lane_runtime.h"  // tests/emu/emu_lane_runtime.h (one lane at a time, votes are the identity)
-#elif defined(MMPC_EMULATE)
-#include "emu_runtime.h"  // tests/emu/emu_runtime.h
 #else
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>

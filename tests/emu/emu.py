@@ -15,13 +15,10 @@ def lib():
     global _LIB
     if _LIB is None:
         subprocess.check_call(["make", "-s", "-C", _HERE])
-        _LIB = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu.so"))
-        _LIB.mmpc_emu_solve.argtypes = [C.POINTER(_abi.MmpcConfig), C.c_int32, C.POINTER(_abi.MmpcBatchIn),
-                                        C.POINTER(_abi.MmpcBatchOut)]
-        _LIB.lane = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_lane.so"))
-        _LIB.lane.mmpc_emu_lane_solve.argtypes = _LIB.mmpc_emu_solve.argtypes
-        _LIB.staged = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_staged.so"))
-        _LIB.staged.mmpc_emu_staged_solve.argtypes = _LIB.mmpc_emu_solve.argtypes + [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]
+        _LIB = C.CDLL(os.path.join(_HERE, "_build", "libmmpc_emu_staged.so"))
+        _LIB.staged = _LIB
+        _LIB.staged.mmpc_emu_staged_solve.argtypes = [C.POINTER(_abi.MmpcConfig), C.c_int32, C.POINTER(_abi.MmpcBatchIn),
+                                                      C.POINTER(_abi.MmpcBatchOut), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]
         _LIB.staged.mmpc_emu_ik.argtypes = [C.c_int32] + [C.c_void_p] * 4
         _LIB.staged.mmpc_emu_episode_update.argtypes = [C.c_int32] * 4 + [C.POINTER(_abi.MmpcEpisodeIO)]
     return _LIB
@@ -45,7 +42,7 @@ def episode_update(N, M, n_manip, io):
     assert lib().staged.mmpc_emu_episode_update(N, io["x"].shape[0], M, n_manip, C.byref(e)) == 0
 
 
-def solve(batch, cfg, kernel="warp"):
+def solve(batch, cfg, kernel="staged"):
     B = batch["x_init"].shape[0]
     N = cfg.N
     f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
@@ -59,16 +56,13 @@ def solve(batch, cfg, kernel="warp"):
     out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
                kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])
-    if kernel.startswith("staged"):
-        # staged: product default (team Riccati, fused trial+evaluation, warp-specialised parts);
-        # staged_thread: one-thread Riccati; staged_fat: one thread per item; staged_unfused: separate eval
-        rounds = C.c_int32(0)
-        team = 1 if kernel in ("staged", "staged_noparts") else 0
-        fused = 0 if kernel == "staged_unfused" else 1
-        parts = 1 if kernel in ("staged", "staged_thread") else 0
-        assert lib().staged.mmpc_emu_staged_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo), C.byref(rounds), team, fused, parts) == 0
-        out["rounds"] = rounds.value
-        return out
-    fn = lib().mmpc_emu_solve if kernel == "warp" else lib().lane.mmpc_emu_lane_solve
-    assert fn(C.byref(cfg), B, C.byref(bi), C.byref(bo)) == 0
+    # staged: product default (team Riccati, fused trial+evaluation, warp-specialised parts);
+    # staged_thread: one-thread Riccati; staged_fat: one thread per item; staged_unfused: separate eval
+    assert kernel.startswith("staged"), kernel
+    rounds = C.c_int32(0)
+    team = 1 if kernel in ("staged", "staged_noparts") else 0
+    fused = 0 if kernel == "staged_unfused" else 1
+    parts = 1 if kernel in ("staged", "staged_thread") else 0
+    assert lib().staged.mmpc_emu_staged_solve(C.byref(cfg), B, C.byref(bi), C.byref(bo), C.byref(rounds), team, fused, parts) == 0
+    out["rounds"] = rounds.value
     return out

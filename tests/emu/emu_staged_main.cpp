@@ -44,9 +44,12 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   SParams P; memset(&P, 0, sizeof P);
   static double row_ring[STAGED_RING_DOUBLES > STAGED_TRIAL_RING_DOUBLES ? STAGED_RING_DOUBLES : STAGED_TRIAL_RING_DOUBLES];  // the step / trial row ring of the one emulated thread
   P.cfg = *cfg; P.B = B;
-  P.x_init = in->x_init; P.x_ref = in->x_ref; P.u_ref = in->u_ref; P.u_last = in->u_last; P.u_guess = in->u_guess;
-  P.circles = in->circles; P.planes = in->planes; P.n_pl_inst = in->n_pl_inst; P.flags = in->flags;
-  P.U = out->U; P.X = out->X; P.s = out->s; P.cost = out->cost; P.kkt = out->kkt; P.iters = out->iters; P.status = out->status;
+  SIO io;
+  io.x_init = in->x_init; io.x_ref = in->x_ref; io.u_ref = in->u_ref; io.u_last = in->u_last; io.u_guess = in->u_guess;
+  io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags;
+  io.U = out->U; io.X = out->X; io.s = out->s; io.cost = out->cost; io.kkt = out->kkt; io.iters = out->iters; io.status = out->status;
+  io.B = B;
+  P.io = &io;
   P.R = staged_rows(*cfg); P.ITSZ = staged_itsz(*cfg); P.STG = staged_stage_doubles(*cfg); P.LS = (B + 31) / 32 * 32; P.ND = staged_inst_doubles(*cfg);
   std::vector<double> ws((size_t)(cfg->N + 1) * P.STG * P.LS, 0.0), gd((size_t)staged_inst_doubles(*cfg) * P.LS, 0.0);
   std::vector<double> qp((size_t)(cfg->N + 1) * QS * P.LS, 0.0), rk((size_t)(cfg->N + 1) * RS * P.LS, 0.0);
@@ -55,7 +58,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   std::vector<char*> stacks(16);
   for (int i = 0; i < 16; ++i) stacks[i] = (char*)malloc(1 << 18);
   std::vector<int> gi((size_t)J_NFIELDS * P.LS, 0), lists((size_t)3 * P.LS, 0);
-  int cnt[3] = {0, 0, 0};
+  int cnt[4] = {0, 0, 0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
   for (int b = 0; b < B; ++b) { body_init(P, b); lists[P.LS + b] = b; }
   cnt[1] = B;

@@ -1,5 +1,5 @@
-"""CPU tier: the CUDA solver *sources* (csrc/mmpc_staged.cuh + mmpc_team.cuh, mmpc_lane.cuh,
-mmpc_solver.cuh) executed by the CPU emulators of tests/emu against the independent dense oracle
+"""CPU tier: the CUDA solver *sources* (csrc/mmpc_staged.cuh + mmpc_team.cuh + mmpc_parts.cuh) executed by the CPU
+emulator of tests/emu against the independent dense oracle
 (oracle/mmpc_oracle.c).  This is how the kernels are debugged on the GPU-less authoring box; the
 real parity tests are the -m gpu ones."""
 import numpy as np
@@ -23,8 +23,8 @@ def _compare(batch, kernel, tol_cost=1e-6, tol_u=1e-4):
 
 
 # staged = phase bodies + 16-lane team Riccati (the product default); staged_thread = phase bodies +
-# one-thread-per-instance Riccati; lane / warp = the two persistent single-kernel solvers
-@pytest.mark.parametrize("kernel", ["staged", "staged_thread", "lane", "warp"])
+# one-thread-per-instance Riccati
+@pytest.mark.parametrize("kernel", ["staged", "staged_thread"])
 def test_config1_bit_level_agreement(kernel):
     b = scenarios.make_batch(1, 1)
     o, e = _compare(b, kernel)
@@ -32,7 +32,7 @@ def test_config1_bit_level_agreement(kernel):
     assert np.abs(o["X"] - e["X"]).max() < 1e-9 and np.abs(o["U"] - e["U"]).max() < 1e-9
 
 
-@pytest.mark.parametrize("kernel,B3,B5", [("staged", 4, 2), ("staged_thread", 12, 3), ("lane", 12, 3), ("warp", 12, 3)])
+@pytest.mark.parametrize("kernel,B3,B5", [("staged", 4, 2), ("staged_thread", 12, 3)])
 def test_config3_and_moving_obstacles(kernel, B3, B5):
     _compare(scenarios.make_batch(3, B3), kernel)
     _compare(scenarios.make_batch(5, B5), kernel)
