@@ -216,9 +216,11 @@ typedef struct MmpcEpisodeIO {
  * episode in io->traj (>= n_manip + 1). */
 int mmpc_episode_update(MmpcHandle* h, int32_t B, int32_t M, int32_t n_manip, const MmpcEpisodeIO* io, void* stream);
 
-/* Phases of the staged solver (one kernel each per round; COMPACT runs twice per round). */
+/* Phases of the staged solver (one kernel each per round; COMPACT runs twice per round).  mmpc_phase_times fills MMPC_NPHASE entries. */
 enum { MMPC_PHASE_COMPACT = 0, MMPC_PHASE_EVAL = 1, MMPC_PHASE_SOLVE = 2, MMPC_PHASE_STEP = 3, MMPC_PHASE_CTRL_STEP = 4,
-       MMPC_PHASE_TRIAL = 5, MMPC_PHASE_CTRL_TRIAL = 6, MMPC_PHASE_INIT = 7, MMPC_NPHASE = 8 };
+       MMPC_PHASE_TRIAL = 5, MMPC_PHASE_CTRL_TRIAL = 6, MMPC_PHASE_INIT = 7,
+       MMPC_PHASE_POSE = 8, /* MMPC_MODE_REFERENCE: forward kinematics + plane margins of every stage, once per evaluated point */
+       MMPC_NPHASE = 9 };
 
 /* Device-side timing of the phases (measurement support for bench.py's roofline).  With profiling on,
  * mmpc_solve brackets every launch of the staged solver with CUDA events on its stream and

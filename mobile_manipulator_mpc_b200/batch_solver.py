@@ -33,7 +33,7 @@ def _diag(M, n, name):
 
 
 class BatchSolver:
-    def __init__(self, N=20, dt=0.1, n_obs=3, n_pl=3, B_max=1, mode=_abi.MODE_CLEAN, device=0,
+    def __init__(self, N=20, dt=0.1, n_obs=3, n_pl=3, B_max=1, mode=_abi.MODE_REFERENCE, device=0,
                  obs_per_stage=False, cfg=None, kernel=None, **overrides):
         if cfg is None:
             cfg = _abi.default_config(N=N, dt=dt, n_obs=n_obs, n_pl=n_pl, mode=mode)
@@ -77,14 +77,14 @@ class BatchSolver:
         check(lib().mmpc_occupancy(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(sm_count=a.value, instances_per_sm=b.value, smem_bytes=c.value)
 
-    PHASES = ("compact", "eval", "solve", "step", "ctrl_step", "trial", "ctrl_trial", "init")
+    PHASES = ("compact", "eval", "solve", "step", "ctrl_step", "trial", "ctrl_trial", "init", "pose")
 
     def set_profile(self, on=True):
         check(lib().mmpc_set_profile(self._h, int(bool(on))))
 
     def phase_times(self):
         """Device ms and launches per phase of the last solve (needs set_profile(True)), and its rounds."""
-        ms = (C.c_double * 8)(); ln = (C.c_int64 * 8)(); rounds = C.c_int32()
+        ms = (C.c_double * 9)(); ln = (C.c_int64 * 9)(); rounds = C.c_int32()
         check(lib().mmpc_phase_times(self._h, ms, ln, C.byref(rounds)))
         return ({p: ms[i] for i, p in enumerate(self.PHASES)}, {p: int(ln[i]) for i, p in enumerate(self.PHASES)},
                 int(rounds.value))
@@ -120,7 +120,24 @@ class BatchSolver:
         return dict(x_init=(B, 9), x_ref=(B, N + 1, 9), u_ref=(B, N, 5), u_last=(B, N, 5), u_guess=(B, N, 5),
                     circles=circ, planes=(B, c.n_pl, 6))
 
-    def solve_host(self, batch, want=("X", "s", "cost", "kkt", "iters")):
+    def host_outputs(self, B, want=("X", "s", "cost", "kkt", "iters"), pinned=False):
+        """Result arrays of solve_host; ``pinned``: page-locked (torch) so that mmpc_solve_host copies into them by DMA."""
+        N = self.cfg.N
+        shapes = dict(U=((B, N, 5), np.float64), status=((B,), np.int32), X=((B, N + 1, 9), np.float64), s=((B, N + 1), np.float64),
+                      cost=((B,), np.float64), kkt=((B,), np.float64), iters=((B,), np.int32))
+        out = {}
+        for k in ("U", "status") + tuple(want):
+            shp, dt = shapes[k]
+            if pinned:
+                import torch
+                t = torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int32).pin_memory()
+                out.setdefault("_keep", []).append(t)
+                out[k] = t.numpy()
+            else:
+                out[k] = np.empty(shp, dt)
+        return out
+
+    def solve_host(self, batch, want=("X", "s", "cost", "kkt", "iters"), out=None):
         B = int(np.asarray(batch["x_init"]).shape[0])
         if B > self.B_max:
             raise ValueError(f"B={B} exceeds B_max={self.B_max}")
@@ -144,11 +161,8 @@ class BatchSolver:
         if flags is not None:
             flags = np.ascontiguousarray(flags, dtype=np.uint8); keep.append(flags)
         bi = _abi.MmpcBatchIn(*ptrs, _abi.ptr(npl), _abi.ptr(flags))
-        N = self.cfg.N
-        out = dict(U=np.empty((B, N, 5)), status=np.empty(B, np.int32))
-        full = dict(X=(B, N + 1, 9), s=(B, N + 1), cost=(B,), kkt=(B,))
-        for k in want:
-            out[k] = np.empty(B, np.int32) if k == "iters" else np.empty(full[k])
+        if out is None:
+            out = self.host_outputs(B, want)
         bo = _abi.MmpcBatchOut(*[_abi.ptr(out.get(k)) for k in _OUT_KEYS])
         check(lib().mmpc_solve_host(self._h, B, C.byref(bi), C.byref(bo)))
         return out

@@ -35,20 +35,44 @@ class ClosedLoop:
         self.shift_guess, self.idx = shift_guess, tuple(idx)
         self.out = None
         self.steps = 0
+        self._conv = []
+        self.failed = torch.zeros((), dtype=torch.int64, device=dev)
+        c = self.solver.cfg
+        self.q_lo = torch.tensor(list(c.xlim[0])[6:], dtype=torch.float64, device=dev)
+        self.q_hi = torch.tensor(list(c.xlim[1])[6:], dtype=torch.float64, device=dev)
 
-    def step(self):
-        """One MPC step of every instance; returns (u0 [B,5], status [B]) as device tensors."""
+    def reset_counters(self):
+        self._conv = []
+
+    def conv_per_step(self):
+        """converged instances of every counted step, as one device tensor (no host sync until it is read)"""
+        return torch.stack(self._conv) if self._conv else torch.zeros(0, dtype=torch.int64, device=self.dev)
+
+    def step(self, count=False):
+        """One MPC step of every instance; returns (u0 [B,5], status [B]) as device tensors.  Nothing here waits for the
+        device: the solve is one CUDA-graph launch, so a host thread can keep several sub-batches in flight."""
         S = self.solver
         x_ref, u_ref = S.window(self.x, self.x_glob, None, self.idx)
         inp = dict(x_init=self.x, x_ref=x_ref, u_ref=u_ref, u_last=self.u_last, u_guess=self.u_guess)
         inp.update({k: v for k, v in self.static.items() if v is not None})
         self.out = S.solve_device(inp, out=self.out)
         U = self.out["U"]
+        st = self.out["status"]
+        ok = (st == _abi.STATUS_CONVERGED) | (st == _abi.STATUS_ACCEPTABLE)
         u0 = U[:, 0, :].contiguous()
-        self.x = S.plant_step(self.x, u0)
-        self.u_last = U.clone()                                   # U_last := previous U*, same index (:310)
-        self.u_guess = S.shift(U) if self.shift_guess else None   # only the GUESS is shifted
+        # solve() clips the caller's x_init[6:] IN PLACE (controllers/mpc_wholebody_qref.py:290): the plant sees the clipped joints
+        x_in = self.x.clone()
+        x_in[:, 6:] = torch.minimum(torch.maximum(x_in[:, 6:], self.q_lo), self.q_hi)
+        xn = S.plant_step(x_in, u0)
+        # a failed solve is fatal in the reference (:329); a batch cannot die, so a failed instance holds its state and its
+        # U_last for this step (and is counted: ``failed``)
+        self.x = torch.where(ok[:, None], xn, x_in)
+        self.u_last = torch.where(ok[:, None, None], U, self.u_last)   # U_last := previous U*, same index (:310)
+        self.failed = self.failed + (~ok).sum()
+        self.u_guess = S.shift(self.u_last) if self.shift_guess else None   # only the GUESS is shifted
         self.steps += 1
+        if count:
+            self._conv.append((self.out["status"] == _abi.STATUS_CONVERGED).sum())
         return u0, self.out["status"]
 
     def run(self, steps):

@@ -299,7 +299,10 @@ static void issue_round(MmpcHandle* h, Issuer& I, SParams P, int r, long long ub
   mark(MMPC_PHASE_COMPACT);
   dst = 0; src = tcur; want = ST_ACTIVE;
   I.launch((const void*)staged_compact_kernel, dim3(1), dim3(cthreads), 0, a4);
+  int which = 0;
+  void* a2[] = {&P, &which};
   if (with_eval) {  // fused: the trial kernel has already evaluated every later accepted point
+    if (ref) { mark(MMPC_PHASE_POSE); I.launch((const void*)staged_pose_kernel, dim3(gs), dim3(128), 0, a2); }
     mark(MMPC_PHASE_EVAL);
     I.launch(ref ? (const void*)staged_eval_kernel<true> : (const void*)staged_eval_kernel<false>, dim3(gs), dim3(128), 0, a1);
   }
@@ -318,6 +321,7 @@ static void issue_round(MmpcHandle* h, Issuer& I, SParams P, int r, long long ub
   dst = tnext; src = tcur; want = ST_TRIAL;
   I.launch((const void*)staged_compact_kernel, dim3(1), dim3(cthreads), 0, a4);
   P.tsel = tnext;
+  if (ref) { which = 1; mark(MMPC_PHASE_POSE); I.launch((const void*)staged_pose_kernel, dim3(gs), dim3(128), 0, a2); }
   mark(MMPC_PHASE_TRIAL);
   if (thin) I.launch((const void*)staged_parts_kernel<true>, dim3(gtile), dim3(32 * plan.n_parts), 0, a1);
   else I.launch(ref ? (const void*)staged_trial_kernel<true> : (const void*)staged_trial_kernel<false>, dim3(gs), dim3(128), trial_ring_smem, a1);
@@ -419,15 +423,16 @@ static int launch_staged_graph(MmpcHandle* h, int32_t B, cudaStream_t st) {
   return MMPC_OK;
 }
 
-// launches the GPU executed for graph solves: 1 (io) + 1 (init) + 8 (round 0) + 7 per later round + one condition kernel per
-// class entry and per loop body; valid once the caller has synchronised the stream of the solve
+// launches the GPU executed for graph solves: 1 (io) + 1 (init) + 8 (round 0) + 7 per later round (+ the pose kernel in
+// reference mode) + one condition kernel per class entry and per loop body; valid once the caller has synchronised the stream of the solve
 static void graph_account(MmpcHandle* h) {
   if (!h->gr.pending) return;
   const int rounds = h->sg.pin[32 + 3];
   if (rounds < 0) return;  // the solve has not finished yet
   h->gr.pending = false;
   h->sg.rounds = 1 + rounds;
-  h->launches += 2 + 8 + 7LL * rounds + h->gr.pending_classes + rounds / 2;
+  const int ref = h->cfg.mode == MMPC_MODE_REFERENCE;   // the pose kernel: once more in round 0, once per round
+  h->launches += 2 + 8 + 2 * ref + (7LL + ref) * rounds + h->gr.pending_classes + rounds / 2;
 }
 
 // ---- driver 2: the host sequences rounds (profiling; MMPC_HOSTLOOP=1) ----------------------------------------------------
@@ -551,10 +556,18 @@ extern "C" int mmpc_solve_host(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, 
   cudaStream_t st = h->stream;
   MmpcBatchIn din; memset(&din, 0, sizeof din);
   MmpcBatchOut dout; memset(&dout, 0, sizeof dout);
+  // a caller's array that already is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is copied by DMA
+  // straight from / to where it lies; a pageable one goes through this handle's pinned staging buffer
+  auto pinned = [](const void* q) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
 #define UP(name, n, T)                                                                       \
   if (in->name) {                                                                            \
-    memcpy(h->h.name, in->name, (n) * sizeof(T));                                            \
-    CK(cudaMemcpyAsync(h->d.name, h->h.name, (n) * sizeof(T), cudaMemcpyHostToDevice, st));  \
+    const void* src_ = in->name;                                                             \
+    if (!pinned(src_)) { memcpy(h->h.name, src_, (n) * sizeof(T)); src_ = h->h.name; }       \
+    CK(cudaMemcpyAsync(h->d.name, src_, (n) * sizeof(T), cudaMemcpyHostToDevice, st));       \
     din.name = h->d.name;                                                                    \
   }
   UP(x_init, b * 9, double); UP(x_ref, b * (N + 1) * 9, double); UP(u_ref, b * N * 5, double);
@@ -570,15 +583,23 @@ extern "C" int mmpc_solve_host(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, 
   if (out->iters) dout.iters = h->d.iters;
   rc = mmpc_solve(h, B, &din, &dout, st);
   if (rc != MMPC_OK) return rc;
-#define DOWN(name, n, T) if (out->name) CK(cudaMemcpyAsync(h->h.name, h->d.name, (n) * sizeof(T), cudaMemcpyDeviceToHost, st))
+  bool direct[7]; int di = 0;
+#define DOWN(name, n, T)                                                                                      \
+  {                                                                                                            \
+    direct[di] = out->name && pinned(out->name);                                                               \
+    if (out->name) CK(cudaMemcpyAsync(direct[di] ? (void*)out->name : (void*)h->h.name, h->d.name, (n) * sizeof(T), cudaMemcpyDeviceToHost, st)); \
+    ++di;                                                                                                      \
+  }
   DOWN(U, b * N * 5, double); DOWN(X, b * (N + 1) * 9, double); DOWN(s, b * (N + 1), double);
   DOWN(cost, b, double); DOWN(kkt, b, double); DOWN(iters, b, int32_t); DOWN(status, b, int32_t);
 #undef DOWN
   CK(cudaStreamSynchronize(st));
-#define OUTC(name, n, T) if (out->name) memcpy(out->name, h->h.name, (n) * sizeof(T))
+  di = 0;
+#define OUTC(name, n, T) { if (out->name && !direct[di]) memcpy(out->name, h->h.name, (n) * sizeof(T)); ++di; }
   OUTC(U, b * N * 5, double); OUTC(X, b * (N + 1) * 9, double); OUTC(s, b * (N + 1), double);
   OUTC(cost, b, double); OUTC(kkt, b, double); OUTC(iters, b, int32_t); OUTC(status, b, int32_t);
 #undef OUTC
+  graph_account(h);
   return MMPC_OK;
 }
 

@@ -113,8 +113,11 @@ __host__ __device__ inline int staged_stale_rows(const MmpcConfig& c) {
 }
 __host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + 4 + (c.n_pl > 0 ? 6 : 0) + staged_stale_rows(c); }
 __host__ __device__ inline int staged_itsz(const MmpcConfig& c) { return I_T + 2 * staged_rows(c); }
+// MMPC_MODE_REFERENCE: the plane margins c[i][j] of the stage's six body points (6 x n_pl, i-major), written once per
+// evaluated point by the pose kernel and read by the three threads (stages k-1, k, k+1) whose stale-column rows need them
+__host__ __device__ inline int staged_marg_doubles(const MmpcConfig& c) { return staged_stale_rows(c) > 0 ? 6 * c.n_pl : 0; }
 __host__ __device__ inline int staged_stage_doubles(const MmpcConfig& c) {
-  return 2 * staged_itsz(c) + S_FIXED + staged_rows(c) + (c.obs_per_stage ? 3 * c.n_obs : 0);
+  return 2 * staged_itsz(c) + S_FIXED + staged_rows(c) + (c.obs_per_stage ? 3 * c.n_obs : 0) + staged_marg_doubles(c);
 }
 __host__ __device__ inline int staged_inst_doubles(const MmpcConfig& c) { return D_CIRC + (c.obs_per_stage ? 0 : 3 * c.n_obs); }
 
@@ -156,7 +159,9 @@ struct Inst {
     gi = p.gi + ((tile * J_NFIELDS) << 5) + ln;
     N = cfg.N; R = p.R; STG = p.STG; ITSZ = p.ITSZ; B2 = 2 * p.ITSZ; nobs = cfg.n_obs; dt = cfg.dt;
     npl = 0;
+    MG = S_DT + R + (cfg.obs_per_stage ? 3 * nobs : 0);
   }
+  int MG;  // offset (second block) of the plane-margin cache of a stage, see staged_marg_doubles
   __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << 5]; }
   __device__ __forceinline__ double& W2(int k, int o) const { return w[(k * STG + B2 + o) << 5]; }
   // base pointer of a block of fields of stage k (field f of the block is p[f << 5]): with it the field offsets
@@ -362,6 +367,43 @@ struct Inst {
       p[a] = cand ? fma(alpha, W2(kk, S_DX + POSE2X[a]), v) : v;
     }
   }
+  __device__ __forceinline__ void xy_at(int kk, int it, bool cand, double alpha, double (&p)[2]) const {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      double v = W(kk, it + I_X + a);
+      p[a] = cand ? fma(alpha, W2(kk, S_DX + a), v) : v;
+    }
+  }
+  __device__ __forceinline__ void load_fk(int kk, FK& f) const {
+    f.cp = W2(kk, S_FK + 0); f.sp = W2(kk, S_FK + 1);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { f.vr[q] = W2(kk, S_FK + 2 + q); f.vh[q] = W2(kk, S_FK + 5 + q); }
+  }
+  __device__ __forceinline__ void load_margins(int kk, double (&c)[6][MMPC_MAX_PLANES]) const {
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < npl; ++j) c[i][j] = W2(kk, MG + i * cfg.n_pl + j);
+  }
+  // pose kernel (thread per instance and stage, MMPC_MODE_REFERENCE only): forward kinematics and plane margins of stage k
+  // at the candidate  w + alpha d  (cand) or at the current iterate, into the stage's FK cache and margin cache.  Runs in
+  // front of the evaluation of the starting point and in front of every trial.
+  __device__ void pose_pass(int k, bool cand) {
+    load_npl();
+    const int it = J(J_CUR) * ITSZ;
+    const double alpha = cand ? D(D_ALPHA) : 0.0;
+    double p[NP]; pose_at(k, it, cand, alpha, p);
+    FK f;
+    double c[6][MMPC_MAX_PLANES];
+    if (npl >= 2) {
+      margins(p, f, c);
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < npl; ++j) W2(k, MG + i * cfg.n_pl + j) = c[i][j];
+    } else fk_eval(p[2], p[3], p[4], p[5], f);
+    W2(k, S_FK + 0) = f.cp; W2(k, S_FK + 1) = f.sp;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { W2(k, S_FK + 2 + q) = f.vr[q]; W2(k, S_FK + 5 + q) = f.vh[q]; }
+  }
   // plane margins c[i][j] of the six body points at one pose (:78-80)
   __device__ __forceinline__ void margins(const double (&p)[NP], FK& f, double (&c)[6][MMPC_MAX_PLANES]) const {
     fk_eval(p[2], p[3], p[4], p[5], f);
@@ -392,12 +434,17 @@ struct Inst {
     const bool cand = phase == 1;
     const double mu = D(D_MU), alpha = cand ? D(D_ALPHA) : 0.0, ad = cand ? D(D_AD) : 0.0;
     const int nst = cfg.n_pl - 1, r0 = nobs + 10;
-    double pk[NP], pm[NP], pn[NP];
+    // Margins and forward kinematics of the stages k-1, k, k+1 at the point this phase works on (the candidate in phase 1,
+    // the current iterate otherwise): computed ONCE per stage by pose_pass() in the kernel launched just before, read here.
+    // (Recomputing them cost three forward kinematics -- twelve sincos -- per thread: the reference-mode trial kernel ran
+    // 3x as long as the clean one.)  The owner of a row and the neighbour that adds its pose terms see the same stored
+    // numbers, so they always agree on the arg-max column.
+    double pk[2], pm[2] = {0, 0};
     double ck[6][MMPC_MAX_PLANES], cm[6][MMPC_MAX_PLANES], cn[6][MMPC_MAX_PLANES];
-    FK fk, fm, fn;
-    pose_at(k, it, cand, alpha, pk); margins(pk, fk, ck);
-    if (k >= 1) { pose_at(k - 1, it, cand, alpha, pm); margins(pm, fm, cm); }
-    if (k < N && phase != 2) { pose_at(k + 1, it, cand, alpha, pn); margins(pn, fn, cn); }
+    FK fk, fm;
+    xy_at(k, it, cand, alpha, pk); load_fk(k, fk); load_margins(k, ck);
+    if (k >= 1) { xy_at(k - 1, it, cand, alpha, pm); load_fk(k - 1, fm); load_margins(k - 1, cm); }
+    if (k < N && phase != 2) load_margins(k + 1, cn);
     const double s_k = cand ? fma(alpha, W2(k, S_DS), W(k, it + I_S)) : W(k, it + I_S);
     // ---- rows of slack s_k (owned) ----
     if (k >= 1) {
@@ -413,7 +460,7 @@ struct Inst {
           const int r = r0 + i * nst + j;
           int jb; const double h = stale_max(ck, cm, i, j, jb);
           const bool here = jb <= j;  // the arg-max column belongs to stage k
-          const double (&pp)[NP] = here ? pk : pm;
+          const double* pp = here ? pk : pm;
           const FK& ff = here ? fk : fm;
           Point pt; point_eval(pp[0], pp[1], ff, BODY[i], pt);
           const double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)};
@@ -524,10 +571,14 @@ struct Inst {
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = (k < N) ? W(k, it + I_U + j) : 0.0;
     double s = W(k, it + I_S);
-    FK f; fk_eval(x[2], x[6], x[7], x[8], f);
-    W2(k, S_FK + 0) = f.cp; W2(k, S_FK + 1) = f.sp;
+    FK f;
+    if (REF) load_fk(k, f);  // the pose kernel has just evaluated it
+    else {
+      fk_eval(x[2], x[6], x[7], x[8], f);
+      W2(k, S_FK + 0) = f.cp; W2(k, S_FK + 1) = f.sp;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { W2(k, S_FK + 2 + q) = f.vr[q]; W2(k, S_FK + 5 + q) = f.vh[q]; }
+      for (int q = 0; q < 3; ++q) { W2(k, S_FK + 2 + q) = f.vr[q]; W2(k, S_FK + 5 + q) = f.vh[q]; }
+    }
     A.chi = -1e300; A.clo = 1e300; A.prim = 0; A.sumz = 0; A.zrows = 0; A.nz = 0; A.csum = A.be0 = A.be1 = 0;
 #pragma unroll
     for (int e = 0; e < 21; ++e) A.H[e] = 0;
@@ -1465,10 +1516,14 @@ struct Inst {
       u[j] = fma(alpha, duo[j], uo[j]);
       if (k < N) cj[(I_U + j) << 5] = u[j];
     }
-    FK f; fk_eval(x[2], x[6], x[7], x[8], f);
-    c2[(S_FK + 0) << 5] = f.cp; c2[(S_FK + 1) << 5] = f.sp;
+    FK f;
+    if (REF) load_fk(k, f);  // the pose kernel has just evaluated the candidate's forward kinematics
+    else {
+      fk_eval(x[2], x[6], x[7], x[8], f);
+      c2[(S_FK + 0) << 5] = f.cp; c2[(S_FK + 1) << 5] = f.sp;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { c2[(S_FK + 2 + q) << 5] = f.vr[q]; c2[(S_FK + 5 + q) << 5] = f.vh[q]; }
+      for (int q = 0; q < 3; ++q) { c2[(S_FK + 2 + q) << 5] = f.vr[q]; c2[(S_FK + 5 + q) << 5] = f.vh[q]; }
+    }
     double es = 0, hpp = 0, sum_lam = 0;
     int n_eq = 0;
     // dynamics :180 at the candidate -- defect and costate terms (A^T lam_{k+1}, B^T lam_{k+1})
@@ -1805,6 +1860,11 @@ __device__ inline void body_trial(const SParams& P, int j, int k, double* sm, in
   Inst S(P, list_T(P)[j]); S.sm = sm; S.bs = bs;
   if (P.fused) S.template trial_eval<REF>(k); else S.trial(k);
 }
+// which: 0 = the E list at the current iterate (front of the stand-alone evaluation), 1 = the trial list at the candidate
+__device__ inline void body_pose(const SParams& P, int j, int k, int which) {
+  Inst S(P, which ? list_T(P)[j] : list_E(P)[j]);
+  S.pose_pass(k, which != 0);
+}
 template <int NL>
 __device__ inline void body_ctrl_trial(const SParams& P, int j, int lane) { Inst S(P, list_T(P)[j]); S.template ctrl_trial<NL>(lane); }
 
@@ -1894,6 +1954,12 @@ __global__ void __launch_bounds__(128, MMPC_TRIAL_MINB) staged_trial_kernel(cons
   const long long tot = (long long)n * (P.cfg.N + 1);
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
     body_trial<REF>(P, (int)(t % n), (int)(t / n), ring + threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(128) staged_pose_kernel(const __grid_constant__ SParams P, int which) {
+  const int n = which ? P.cnt[P.tsel] : P.cnt[0];
+  const long long tot = (long long)n * (P.cfg.N + 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x)
+    body_pose(P, (int)(t % n), (int)(t / n), which);
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[P.tsel];  // one warp per instance

@@ -105,12 +105,16 @@ class BatchedInterface:
                        planes=g(self.planes), n_pl_inst=g(self.n_pl_inst), flags=g(self.flags))
             out = S.solve_device(inp, want=())
             U = out["U"]
-            self.u_last.index_copy_(0, idx, U)                                          # U_last := previous U* (:310, :330)
-            self.status.index_copy_(0, idx, out["status"])
+            st = out["status"]
+            ok = (st == _abi.STATUS_CONVERGED) | (st == _abi.STATUS_ACCEPTABLE)
+            # a failed solve is fatal in the reference (controllers/mpc_wholebody_qref.py:329); here the episode holds its state
+            # and its U_last for this step and is counted
+            self.u_last.index_copy_(0, idx, torch.where(ok[:, None, None], U, inp["u_last"]))   # U_last := previous U* (:310, :330)
+            self.status.index_copy_(0, idx, st)
             xn = S.plant_step(inp["x_init"], U[:, 0, :].contiguous())                  # :143
-            self.x.index_copy_(0, idx, xn)
+            self.x.index_copy_(0, idx, torch.where(ok[:, None], xn, inp["x_init"]))
             n_solved += n
-            self.nonconverged += int((out["status"] != _abi.STATUS_CONVERGED).sum())
+            self.nonconverged += int((~ok).sum())
         self.steps += 1
         self.solves += n_solved
         return n_solved

@@ -69,6 +69,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     const int tcur = 1 + (r & 1), tnext = 1 + ((r + 1) & 1);
     compact_list(P, 0, tcur, ST_ACTIVE);
     int nE = cnt[0];
+    if (ref && (!fused || r == 0)) for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) body_pose(P, j, k, 0);
     if (!fused || r == 0)  // fused: only the starting point needs the stand-alone evaluation
       for (int k = 0; k <= N; ++k) for (int j = 0; j < nE; ++j) { if (ref) body_eval<true>(P, j, k); else body_eval<false>(P, j, k); }
     for (int j = 0; j < nE; ++j) { if (team) run_team(P, j, stacks); else body_solve(P, j); }
@@ -81,6 +82,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
     compact_list(P, tnext, tcur, ST_TRIAL);
     P.tsel = tnext;
     int nT = cnt[tnext];
+    if (ref) for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) body_pose(P, j, k, 1);
     for (int k = 0; k <= N; ++k) for (int j = 0; j < nT; ++j) {
       if (!parts) { if (ref) body_trial<true>(P, j, k, row_ring, 1); else body_trial<false>(P, j, k, row_ring, 1); }
       else body_parts_item(P, list_T(P)[j], k, true);

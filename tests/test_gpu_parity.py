@@ -15,7 +15,10 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def _solver(batch, B=None, **kw):
+    """mode defaults to the stage-separable NLP HERE (these tests name the oracle's mode explicitly); the product's default is
+    MMPC_MODE_REFERENCE."""
     from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    kw.setdefault("mode", _abi.MODE_CLEAN)
     return BatchSolver(N=batch["N"], dt=batch["dt"], n_obs=batch["n_obs"], n_pl=batch["n_pl"],
                        B_max=B or batch["x_init"].shape[0], obs_per_stage=batch["obs_per_stage"], **kw)
 
@@ -302,15 +305,18 @@ def test_closed_loop_on_device_matches_host_loop():
         u0_dev, st_dev = L.step()
         xr = np.stack([scenarios.local_window(x_glob[i], np.zeros((x_glob.shape[1] - 1, 5)), x[i], [0, 1], 20)[0] for i in range(B)])
         hb = dict(b); hb.update(x_init=x, x_ref=xr, u_ref=np.zeros((B, 20, 5)), u_last=u_last)
-        ref = solver.solve(hb, mode=_abi.MODE_CLEAN, threads=os.cpu_count() or 4)
+        ref = solver.solve(hb, mode=_abi.MODE_REFERENCE, threads=os.cpu_count() or 4)   # ClosedLoop solves the reference's NLP (the default)
         ok = (ref["status"] == 0) & (st_dev.cpu().numpy() == 0)
         assert ok.mean() >= 0.9
         assert np.abs(L.out["X"].cpu().numpy()[:, 0] - np.clip(x, scenarios.XLIM[0], scenarios.XLIM[1])).max() < 1e-12   # same plant state
         assert np.abs(u0_dev.cpu().numpy() - ref["U"][:, 0])[ok].max() < 1e-4
-        # continue the host loop from the DEVICE solution so that round-off bifurcations cannot accumulate
+        # continue the host loop from the DEVICE solution so that round-off bifurcations cannot accumulate; solve() clips
+        # x_init[6:] in place (:290) before the plant sees it; an instance whose solve failed holds its state and U_last
         U = L.out["U"].cpu().numpy()
-        x = M.f_kinematics(np.clip(x, scenarios.XLIM[0], scenarios.XLIM[1]), U[:, 0], 0.1)
-        u_last = U
+        okd = np.isin(st_dev.cpu().numpy(), (_abi.STATUS_CONVERGED, _abi.STATUS_ACCEPTABLE))
+        xc = x.copy(); xc[:, 6:] = np.clip(x[:, 6:], scenarios.XLIM[0, 6:], scenarios.XLIM[1, 6:])
+        x = np.where(okd[:, None], M.f_kinematics(xc, U[:, 0], 0.1), xc)
+        u_last = np.where(okd[:, None, None], U, u_last)
         assert np.abs(L.x.cpu().numpy() - x).max() < 1e-12
 
 
@@ -384,3 +390,52 @@ def test_ragged_and_extreme_sizes():
     with pytest.raises(MmpcError):   # literal reference NLP: the terminal rows need a stage N-1 >= 1
         BatchSolver(N=1, mode=_abi.MODE_REFERENCE)
     BatchSolver(N=1, mode=_abi.MODE_REFERENCE, terminal_rows_on_sN=1).close()
+
+
+def test_model_values_match_reference_code_1e12():
+    """mmpc_eval_model against values computed by the REFERENCE'S OWN model code (tests/golden/ref_model_values.npz, written
+    by tests/golden/make_ref_rows.py from the unmodified robot_models/*.py and MPCWholeBody.reset()): f_kinematics,
+    forward_tranformation, obsAvoid rows, self-collision rows and plane margins of 1,000 random states."""
+    import torch
+    from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    g = np.load(os.path.join(GOLD, "ref_model_values.npz"))
+    x, u, circ = g["x"], g["u"], g["circles"]
+    Mn, nobs = x.shape[0], circ.shape[0]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    close = lambda a, b: np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b))
+    for nm in ("s1", "s2"):
+        planes = g["planes_" + nm]
+        S = BatchSolver(N=20, dt=0.1, n_obs=nobs, n_pl=planes.shape[0], B_max=1)
+        f, fk, rows = S.eval_model(t(x), t(u), t(np.tile(circ, (Mn, 1, 1))), t(np.tile(planes, (Mn, 1, 1))))
+        f, fk, rows = f.cpu().numpy(), fk.cpu().numpy(), rows.cpu().numpy()
+        assert close(f, g["f"]).all() and close(fk, g["fk"]).all()
+        assert close(rows[:, :nobs], g["circle_rows"]).all()
+        assert close(rows[:, nobs:nobs + 4], g["self_rows"]).all()
+        assert close(rows[:, nobs + 4:].reshape(Mn, 6, -1), g["margins_" + nm]).all()
+        S.close()
+
+
+@pytest.mark.parametrize("mode", [_abi.MODE_REFERENCE, _abi.MODE_CLEAN])
+def test_graph_solve_equals_host_sequenced_solve_bitwise(mode):
+    """The CUDA graph with device-side WHILE loops (default) and the host-sequenced rounds run the same kernels on the same
+    lists: every output must be identical to the bit, for a batch that passes through several size classes, for a batch
+    smaller than the graph's capacity, and for a single instance."""
+    batch = scenarios.make_batch(3, 3000)
+    Sg = _solver(batch, mode=mode)
+    Sh = _solver(batch, mode=mode, kernel="staged_hostloop")
+    for B in (3000, 777, 1):
+        b = {k: (v[:B] if isinstance(v, np.ndarray) else v) for k, v in batch.items()}
+        a, c = Sg.solve_host(b), Sh.solve_host(b)
+        if mode == _abi.MODE_REFERENCE:
+            for k in ("U", "X", "s", "cost", "kkt", "iters", "status"):
+                assert np.array_equal(a[k], c[k]), (B, k)
+        else:
+            # the clean NLP switches to the warp-specialised part kernels in thin rounds; the two drivers switch at different
+            # rounds and the part kernels sum in another order: same optimum to rounding, not to the bit
+            assert np.array_equal(a["status"], c["status"])
+            ok = a["status"] == 0
+            assert np.abs(a["cost"] - c["cost"])[ok].max() <= 1e-9 * np.abs(c["cost"][ok]).max()
+            assert np.abs(a["U"] - c["U"])[ok].max() < 1e-7
+        assert (a["status"] == 0).mean() >= 0.95
+    assert Sg.launch_count() > 0
+    Sg.close(); Sh.close()
