@@ -58,17 +58,18 @@ class ClosedLoop:
         self.out = S.solve_device(inp, out=self.out)
         U = self.out["U"]
         st = self.out["status"]
-        ok = (st == _abi.STATUS_CONVERGED) | (st == _abi.STATUS_ACCEPTABLE)
+        ok = (st != _abi.STATUS_NAN) & (st != _abi.STATUS_FACTOR)   # an iterate exists (converged, or the best point of a stalled search)
         u0 = U[:, 0, :].contiguous()
         # solve() clips the caller's x_init[6:] IN PLACE (controllers/mpc_wholebody_qref.py:290): the plant sees the clipped joints
         x_in = self.x.clone()
         x_in[:, 6:] = torch.minimum(torch.maximum(x_in[:, 6:], self.q_lo), self.q_hi)
         xn = S.plant_step(x_in, u0)
-        # a failed solve is fatal in the reference (:329); a batch cannot die, so a failed instance holds its state and its
-        # U_last for this step (and is counted: ``failed``)
+        # A failed solve is fatal in the reference (:329).  A batch cannot die: a solve without a finite iterate (NaN,
+        # factorisation failure) holds the instance's state and U_last for this step; a stalled one (line search, iteration
+        # cap) applies its last iterate.  ``failed`` counts every solve that is not converged / acceptable.
         self.x = torch.where(ok[:, None], xn, x_in)
         self.u_last = torch.where(ok[:, None, None], U, self.u_last)   # U_last := previous U*, same index (:310)
-        self.failed = self.failed + (~ok).sum()
+        self.failed = self.failed + ((st != _abi.STATUS_CONVERGED) & (st != _abi.STATUS_ACCEPTABLE)).sum()
         self.u_guess = S.shift(self.u_last) if self.shift_guess else None   # only the GUESS is shifted
         self.steps += 1
         if count:

@@ -337,28 +337,9 @@ struct Inst {
   //   phase 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step
   // (Quirk 3, the terminal self-collision rows bounded by s_{N-1}, is handled where those rows are evaluated: see q3().)
   struct StaleIO {
-    // phase 0/1: this function's own share of the accumulators of stage k and of bv[6] = H[pose][v]; the caller adds them to its
-    // own after the call.  (A pointer to the caller's accumulators would force all of them into local memory for the whole
-    // kernel: the reference-mode trial kernel ran 3.5x slower than the clean one for that.)
-    RowAcc acc; double bvv[NP];
-    __device__ __forceinline__ void reset() {
-      acc.chi = -1e300; acc.clo = 1e300; acc.prim = 0; acc.sumz = 0; acc.zrows = 0; acc.nz = 0; acc.csum = acc.be0 = acc.be1 = 0;
-#pragma unroll
-      for (int e = 0; e < 21; ++e) acc.H[e] = 0;
-#pragma unroll
-      for (int a = 0; a < NP; ++a) acc.a[a] = acc.gA[a] = acc.gB[a] = acc.st[a] = bvv[a] = 0;
-      theta = 0; logsum = 0; ok = true; gphi = 0;
-    }
-    __device__ __forceinline__ void merge_into(RowAcc& A, double (&bv)[NP]) const {
-#pragma unroll
-      for (int e = 0; e < 21; ++e) A.H[e] += acc.H[e];
-#pragma unroll
-      for (int a = 0; a < NP; ++a) { A.a[a] += acc.a[a]; A.gA[a] += acc.gA[a]; A.gB[a] += acc.gB[a]; A.st[a] += acc.st[a]; bv[a] += bvv[a]; }
-      A.csum += acc.csum; A.be0 += acc.be0; A.be1 += acc.be1; A.zrows += acc.zrows; A.sumz += acc.sumz; A.nz += acc.nz;
-      A.chi = fmax(A.chi, acc.chi); A.clo = fmin(A.clo, acc.clo); A.prim = fmax(A.prim, acc.prim);
-    }
     double theta, logsum; bool ok;           // merit ingredients (phase 1, 2)
     MinRatio rp, rd; double gphi;            // phase 2
+    __device__ __forceinline__ void reset() { theta = 0; logsum = 0; ok = true; gphi = 0; }
   };
   __device__ __forceinline__ void pose_at(int kk, int it, bool cand, double alpha, double (&p)[NP]) const {
 #pragma unroll
@@ -428,45 +409,69 @@ struct Inst {
     }
     return -cb;
   }
-  __device__ __noinline__ void stale_rows(int k, int phase, StaleIO& io) const {
+  // the same for ONE body point whose margins sit in registers (fully unrolled over the plane slots)
+  __device__ __forceinline__ double stale_max1(const double (&cm)[MMPC_MAX_PLANES], const double (&cm1)[MMPC_MAX_PLANES], int j, int& best) const {
+    double cb = 0; best = 0;
+#pragma unroll
+    for (int jj = 0; jj < MMPC_MAX_PLANES; ++jj) {
+      const double c = jj <= j ? cm[jj] : cm1[jj];
+      const bool take = jj < npl && ((jj == 0) || (npl == 2 ? !(cb > c) : (c > cb)));
+      if (take) { cb = c; best = jj; }
+    }
+    return -cb;
+  }
+  __device__ __forceinline__ void load_margins1(int kk, int i, double (&c)[MMPC_MAX_PLANES]) const {
+#pragma unroll
+    for (int j = 0; j < MMPC_MAX_PLANES; ++j) c[j] = j < npl ? W2(kk, MG + i * cfg.n_pl + j) : 0.0;
+  }
+  __device__ __forceinline__ static void pick_fk(bool first, const FK& a, const FK& b, FK& o) {
+    o.cp = first ? a.cp : b.cp; o.sp = first ? a.sp : b.sp;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { o.vr[q] = first ? a.vr[q] : b.vr[q]; o.vh[q] = first ? a.vh[q] : b.vh[q]; }
+  }
+  // PHASE 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step.
+  // Inlined into its three call sites with the phase as a compile-time constant: the accumulators stay in registers
+  // (out of line they lived in local memory, and every H += was a load and a store).
+  // A, bv: the caller's own accumulators of stage k (phases 0 and 1)
+  template <int PHASE>
+  __device__ __forceinline__ void stale_rows(int k, RowAcc& A, double (&bv)[NP], StaleIO& io) const {
     if (npl < 2) return;
     const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
-    const bool cand = phase == 1;
+    constexpr bool cand = PHASE == 1;
     const double mu = D(D_MU), alpha = cand ? D(D_ALPHA) : 0.0, ad = cand ? D(D_AD) : 0.0;
     const int nst = cfg.n_pl - 1, r0 = nobs + 10;
     // Margins and forward kinematics of the stages k-1, k, k+1 at the point this phase works on (the candidate in phase 1,
-    // the current iterate otherwise): computed ONCE per stage by pose_pass() in the kernel launched just before, read here.
-    // (Recomputing them cost three forward kinematics -- twelve sincos -- per thread: the reference-mode trial kernel ran
-    // 3x as long as the clean one.)  The owner of a row and the neighbour that adds its pose terms see the same stored
+    // the current iterate otherwise): computed ONCE per stage by pose_pass() in the kernel launched just before, read here,
+    // one body point at a time.  The owner of a row and the neighbour that adds its pose terms see the same stored
     // numbers, so they always agree on the arg-max column.
     double pk[2], pm[2] = {0, 0};
-    double ck[6][MMPC_MAX_PLANES], cm[6][MMPC_MAX_PLANES], cn[6][MMPC_MAX_PLANES];
     FK fk, fm;
-    xy_at(k, it, cand, alpha, pk); load_fk(k, fk); load_margins(k, ck);
-    if (k >= 1) { xy_at(k - 1, it, cand, alpha, pm); load_fk(k - 1, fm); load_margins(k - 1, cm); }
-    if (k < N && phase != 2) load_margins(k + 1, cn);
+    xy_at(k, it, cand, alpha, pk); load_fk(k, fk);
+    if (k >= 1) { xy_at(k - 1, it, cand, alpha, pm); load_fk(k - 1, fm); } else fm = fk;
     const double s_k = cand ? fma(alpha, W2(k, S_DS), W(k, it + I_S)) : W(k, it + I_S);
     // ---- rows of slack s_k (owned) ----
     if (k >= 1) {
       double dpk[NP], dpm[NP], dsk = 0;
-      if (phase == 2) {
+      if (PHASE == 2) {
 #pragma unroll
         for (int a = 0; a < NP; ++a) { dpk[a] = W2(k, S_DX + POSE2X[a]); dpm[a] = W2(k - 1, S_DX + POSE2X[a]); }
         dsk = W2(k, S_DS);
       }
 #pragma unroll 1
-      for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i) {
+        double ck[MMPC_MAX_PLANES], cm[MMPC_MAX_PLANES];
+        load_margins1(k, i, ck); load_margins1(k - 1, i, cm);
+#pragma unroll 1
         for (int j = 0; j < npl - 1; ++j) {
           const int r = r0 + i * nst + j;
-          int jb; const double h = stale_max(ck, cm, i, j, jb);
+          int jb; const double h = stale_max1(ck, cm, j, jb);
           const bool here = jb <= j;  // the arg-max column belongs to stage k
-          const double* pp = here ? pk : pm;
-          const FK& ff = here ? fk : fm;
-          Point pt; point_eval(pp[0], pp[1], ff, BODY[i], pt);
+          FK ff; pick_fk(here, fk, fm, ff);
+          Point pt; point_eval(here ? pk[0] : pm[0], here ? pk[1] : pm[1], ff, BODY[i], pt);
           const double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)};
           double g[NP]; point_grad(ff, pt, n, g);  // grad h = +g (at the arg-max stage)
           double t = W(k, it + I_T + r), z = W(k, it + I_T + R + r);
-          if (phase == 2) {
+          if (PHASE == 2) {
             double gd_ = 0;
 #pragma unroll
             for (int a = 0; a < NP; ++a) gd_ = fma(g[a], here ? dpk[a] : dpm[a], gd_);
@@ -491,7 +496,6 @@ struct Inst {
           } else it_ = 1.0 / t;
           const double res = h - s_k + t;
           io.theta += fabs(res);
-          RowAcc& A = io.acc;
           A.prim = fmax(A.prim, fabs(res));
           const double zt = z * t;
           A.chi = fmax(A.chi, zt); A.clo = fmin(A.clo, zt); A.sumz += z; A.zrows += z; A.nz++;
@@ -508,15 +512,19 @@ struct Inst {
             for (int a = 0; a < NP; ++a) { A.a[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
           }
         }
+      }
     }
     // ---- rows of slack s_{k+1} whose arg-max column belongs to x_k: pose terms and H[pose][v] of stage k ----
-    if (k < N && phase != 2) {
+    if (k < N && PHASE != 2) {
       const double s_n = cand ? fma(alpha, W2(k + 1, S_DS), W(k + 1, it + I_S)) : W(k + 1, it + I_S);
 #pragma unroll 1
-      for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i) {
+        double ck[MMPC_MAX_PLANES], cn[MMPC_MAX_PLANES];
+        load_margins1(k, i, ck); load_margins1(k + 1, i, cn);
+#pragma unroll 1
         for (int j = 0; j < npl - 1; ++j) {
           const int r = r0 + i * nst + j;
-          int jb; const double h = stale_max(cn, ck, i, j, jb);
+          int jb; const double h = stale_max1(cn, ck, j, jb);
           if (jb <= j) continue;  // belongs to stage k+1: its owner handles it
           Point pt; point_eval(pk[0], pk[1], fk, BODY[i], pt);
           const double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)};
@@ -531,15 +539,15 @@ struct Inst {
             t = tt;
           } else it_ = 1.0 / t;
           const double res = h - s_n + t, sig = z * it_, cb = sig * res;
-          RowAcc& A = io.acc;
 #pragma unroll
           for (int a = 0; a < NP; ++a)
 #pragma unroll
             for (int c = a; c < NP; ++c) A.H[pidx(a, c)] += sig * g[a] * g[c];
           point_hess_acc(fk, pt, n, z, A.H);
 #pragma unroll
-          for (int a = 0; a < NP; ++a) { io.bvv[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
+          for (int a = 0; a < NP; ++a) { bv[a] -= sig * g[a]; A.gA[a] += cb * g[a]; A.gB[a] += it_ * g[a]; A.st[a] += z * g[a]; }
         }
+      }
     }
   }
 
@@ -748,8 +756,7 @@ struct Inst {
     double bv[NP] = {0, 0, 0, 0, 0, 0};
     if (REF) {  // compiled out of the clean-mode kernels
       StaleIO io; io.reset(); io.rp.init(); io.rd.init();
-      stale_rows(k, 0, io);
-      io.merge_into(A, bv);
+      stale_rows<0>(k, A, bv, io);
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
     double S2 = 2 * os * cfg.S;
@@ -1272,7 +1279,8 @@ struct Inst {
     double log_extra = 0;
     if (REF) {  // compiled out of the clean-mode kernels
       StaleIO io; io.reset(); io.rp = rp; io.rd = rd;
-      stale_rows(k, 2, io);
+      RowAcc Adummy; double bvdummy[NP];   // phase 2 touches neither
+      stale_rows<2>(k, Adummy, bvdummy, io);
       theta += io.theta; gphi += io.gphi; log_extra = io.logsum; rp = io.rp; rd = io.rd;
     }
     c2[(S_PART + 0) << 5] = rp.value(tau); c2[(S_PART + 1) << 5] = rd.value(tau); c2[(S_PART + 2) << 5] = gphi; c2[(S_PART + 3) << 5] = theta;
@@ -1740,8 +1748,7 @@ struct Inst {
     double bv[NP] = {0, 0, 0, 0, 0, 0}, log_extra = 0;
     if (REF) {  // compiled out of the clean-mode kernels
       StaleIO io; io.reset(); io.rp.init(); io.rd.init();
-      stale_rows(k, 1, io);
-      io.merge_into(A, bv);
+      stale_rows<1>(k, A, bv, io);
       theta += io.theta; log_extra = io.logsum; ok = ok && io.ok;
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
@@ -1935,7 +1942,7 @@ __global__ void __launch_bounds__(64) staged_solve_kernel(const __grid_constant_
 #define MMPC_TRIAL_MINB 2
 #endif
 template <bool REF>
-__global__ void __launch_bounds__(128, MMPC_STEP_MINB) staged_step_kernel(const __grid_constant__ SParams P) {
+__global__ void __launch_bounds__(128, REF ? MMPC_STEP_MINB - 1 : MMPC_STEP_MINB) staged_step_kernel(const __grid_constant__ SParams P) {
   extern __shared__ double ring[];  // STAGED_RING_DOUBLES per thread, thread-interleaved
   const int n = P.cnt[0];
   const long long tot = (long long)n * (P.cfg.N + 1);

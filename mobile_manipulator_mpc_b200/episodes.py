@@ -106,15 +106,17 @@ class BatchedInterface:
             out = S.solve_device(inp, want=())
             U = out["U"]
             st = out["status"]
-            ok = (st == _abi.STATUS_CONVERGED) | (st == _abi.STATUS_ACCEPTABLE)
-            # a failed solve is fatal in the reference (controllers/mpc_wholebody_qref.py:329); here the episode holds its state
-            # and its U_last for this step and is counted
+            ok = (st != _abi.STATUS_NAN) & (st != _abi.STATUS_FACTOR)   # an iterate exists (converged, or the best point of a stalled search)
+            # A failed solve is fatal in the reference (controllers/mpc_wholebody_qref.py:329).  A batch cannot die: a solve that
+            # ends without a finite iterate (NaN, factorisation failure) leaves the episode where it is for this step; one that
+            # stalled (line search, iteration cap) applies its last iterate, like the restated Interface (oracle/episode.py).
+            # Both are counted in ``nonconverged``.
             self.u_last.index_copy_(0, idx, torch.where(ok[:, None, None], U, inp["u_last"]))   # U_last := previous U* (:310, :330)
             self.status.index_copy_(0, idx, st)
             xn = S.plant_step(inp["x_init"], U[:, 0, :].contiguous())                  # :143
             self.x.index_copy_(0, idx, torch.where(ok[:, None], xn, inp["x_init"]))
             n_solved += n
-            self.nonconverged += int((~ok).sum())
+            self.nonconverged += int(((st != _abi.STATUS_CONVERGED) & (st != _abi.STATUS_ACCEPTABLE)).sum())
         self.steps += 1
         self.solves += n_solved
         return n_solved

@@ -311,9 +311,9 @@ def test_closed_loop_on_device_matches_host_loop():
         assert np.abs(L.out["X"].cpu().numpy()[:, 0] - np.clip(x, scenarios.XLIM[0], scenarios.XLIM[1])).max() < 1e-12   # same plant state
         assert np.abs(u0_dev.cpu().numpy() - ref["U"][:, 0])[ok].max() < 1e-4
         # continue the host loop from the DEVICE solution so that round-off bifurcations cannot accumulate; solve() clips
-        # x_init[6:] in place (:290) before the plant sees it; an instance whose solve failed holds its state and U_last
+        # x_init[6:] in place (:290) before the plant sees it; an instance whose solve ended without a finite iterate holds its state and U_last
         U = L.out["U"].cpu().numpy()
-        okd = np.isin(st_dev.cpu().numpy(), (_abi.STATUS_CONVERGED, _abi.STATUS_ACCEPTABLE))
+        okd = ~np.isin(st_dev.cpu().numpy(), (_abi.STATUS_NAN, _abi.STATUS_FACTOR))
         xc = x.copy(); xc[:, 6:] = np.clip(x[:, 6:], scenarios.XLIM[0, 6:], scenarios.XLIM[1, 6:])
         x = np.where(okd[:, None], M.f_kinematics(xc, U[:, 0], 0.1), xc)
         u_last = np.where(okd[:, None, None], U, u_last)
