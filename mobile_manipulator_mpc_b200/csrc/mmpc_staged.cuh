@@ -93,9 +93,12 @@ constexpr int R_K = 0, R_KFF = 45, R_W = 50, R_CV = 64, R_L0 = 65, R_P = 66, R_P
 constexpr int SGY_S = 9, SGY_U = 10, SGY_V = 15;
 // per-instance doubles
 constexpr int D_MU = 0, D_REGLAST = 1, D_THMAX = 2, D_THMIN = 3, D_E0 = 4, D_OS = 5, D_ALPHA = 6, D_AD = 7,
-              D_GPHI = 8, D_THETA = 9, D_PHI0 = 10, D_FILT = 11, D_PL = 43, D_CIRC = 43 + 6 * MMPC_MAX_PLANES;
-// per-instance ints
-constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_FLAGS = 7, J_NFIELDS = 8;
+              D_GPHI = 8, D_THETA = 9, D_PHI0 = 10, D_FILT = 11, D_AP0 = 43, D_PL = 44, D_CIRC = 44 + 6 * MMPC_MAX_PLANES;
+// per-instance ints.  J_FRST: IPOPT's filter reset heuristic (filter_reset_trigger 5, max_filter_resets 5), packed:
+// bits 0-7 successive iterations whose last rejection was the filter's, bits 8-15 resets so far, bit 16 the last rejection of
+// the running line search was the filter's
+constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_FLAGS = 7, J_FRST = 8, J_NFIELDS = 9;
+constexpr int FILTER_RESET_TRIGGER = 5, MAX_FILTER_RESETS = 5;
 constexpr int ST_ACTIVE = 0, ST_DONE = 1, ST_TRIAL = 2, ST_FINISH = 3;  // FINISH: results are written by the step kernels of this round
 //  // ACTIVE: next phase is eval; TRIAL: next phase is a trial
 // partial slots
@@ -315,7 +318,7 @@ struct Inst {
     }
     D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
     D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
-    J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0;
+    J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0; J(J_FRST) = 0;
     J(J_FLAGS) = P.io->flags ? (int)P.io->flags[b] : 0;
   }
 
@@ -1121,7 +1124,7 @@ struct Inst {
     while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
       mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
     }
-    if (mu_changed) { J(J_NFILT) = 0; D(D_MU) = mu; }
+    if (mu_changed) { J(J_NFILT) = 0; J(J_FRST) = J(J_FRST) & 0xff00; D(D_MU) = mu; }
     double reg = 0, reg_last = D(D_REGLAST);
     int tries = 0;
     for (;;) {
@@ -1342,8 +1345,17 @@ struct Inst {
     gphi = lanes_sum<NL>(gphi); theta = lanes_sum<NL>(theta); fsum = lanes_sum<NL>(fsum); logsum = lanes_sum<NL>(logsum);
     if (lane == 0) {
       if (D(D_THMAX) < 0) { D(D_THMAX) = 1e4 * fmax(1.0, theta); D(D_THMIN) = 1e-4 * fmax(1.0, theta); }
-      D(D_ALPHA) = ap; D(D_AD) = ad; D(D_GPHI) = gphi; D(D_THETA) = theta; D(D_PHI0) = fsum - D(D_MU) * logsum;
+      D(D_ALPHA) = ap; D(D_AP0) = ap; D(D_AD) = ad; D(D_GPHI) = gphi; D(D_THETA) = theta; D(D_PHI0) = fsum - D(D_MU) * logsum;
       J(J_LS) = 0;
+      {  // filter reset heuristic, at the start of the iteration's line search (IpFilterLSAcceptor: InitThisLineSearch)
+        const int fr = J(J_FRST);
+        int cnt = fr & 0xff, nres = (fr >> 8) & 0xff;
+        if (nres < MAX_FILTER_RESETS) {
+          if (fr >> 16 & 1) { if (++cnt >= FILTER_RESET_TRIGGER) { J(J_NFILT) = 0; nres++; cnt = 0; } }
+          else cnt = 0;
+        }
+        J(J_FRST) = cnt | (nres << 8);
+      }
       J(J_STATE) = ST_TRIAL;
     }
     return true;
@@ -1800,7 +1812,6 @@ struct Inst {
     for (int q = lane; q < nfilt; q += NL)
       if (th1 >= D(D_FILT + 2 * q) && ph1 >= D(D_FILT + 2 * q + 1)) dom = 1.0;
     dom = lanes_max<NL>(dom);
-    ok = ok && !(dom > 0.5);
     if (ok) {
       bool sw = (gphi < 0) && (alpha * pow(-gphi, 2.3) > pow(theta_k, 1.1));
       if (theta_k <= D(D_THMIN) && sw) {
@@ -1809,10 +1820,22 @@ struct Inst {
         ok = (th1 <= (1 - 1e-5) * theta_k) || (ph1 <= phi0 - 1e-8 * theta_k); ftype = false;
       }
     }
+    const int fr = J(J_FRST);
+    const double ap0 = D(D_AP0);
     lanes_sync<NL>();  // every lane has read the instance state before lane 0 rewrites it
-    if (!ok) {
-      if (lane == 0) { D(D_ALPHA) = alpha * 0.5; J(J_LS) = lsn + 1; }
-      if (lsn + 1 >= 50) { if (lane == 0) finish(MMPC_STATUS_LINESEARCH); return 2; }
+    if (!ok || dom > 0.5) {
+      const int lastf = (ok && dom > 0.5) ? 1 : 0;  // sufficient progress, but the filter said no
+      const int nres = (fr >> 8) & 0xff;
+      if (lsn + 1 >= 50) {
+        // IPOPT would enter its restoration phase here; in its place: clear the filter (while resets are left) and search again
+        if (nres < MAX_FILTER_RESETS && nfilt > 0) {
+          if (lane == 0) { J(J_NFILT) = 0; J(J_FRST) = ((nres + 1) << 8) | (lastf << 16); D(D_ALPHA) = ap0; J(J_LS) = 0; }
+          return 1;
+        }
+        if (lane == 0) finish(MMPC_STATUS_LINESEARCH);
+        return 2;
+      }
+      if (lane == 0) { D(D_ALPHA) = alpha * 0.5; J(J_LS) = lsn + 1; J(J_FRST) = (fr & 0xffff) | (lastf << 16); }
       return 1;
     }
     if (lane == 0) {

@@ -463,7 +463,7 @@ struct Team {
       while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
         mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
       }
-      if (mu_changed && c == 0) { S.J(J_NFILT) = 0; S.D(D_MU) = mu; }
+      if (mu_changed && c == 0) { S.J(J_NFILT) = 0; S.J(J_FRST) = S.J(J_FRST) & 0xff00; S.D(D_MU) = mu; }
     }
     bool need = fin < 0;
     double reg = 0;

@@ -675,7 +675,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     sc.S *= os;
   }
   enum { MAXFILT = 16 };
-  double filt_th[MAXFILT], filt_ph[MAXFILT], theta_max = -1, theta_min = -1; int nfilt = 0;
+  double filt_th[MAXFILT], filt_ph[MAXFILT], theta_max = -1, theta_min = -1; int nfilt = 0, n_freset = 0, cnt_frej = 0, last_rej_filter = 0;
   double mu = cfg->mu_init, tol = cfg->tol, nu = 1.0, reg_last = 0;
   const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5, tau_min = 0.99;
   int it = 0, status = MMPC_STATUS_MAX_ITER; double E0 = 1e300;
@@ -690,7 +690,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     while (kkt_error(&kp, mu) <= kap_eps * mu && mu > tol / 10) {
       mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = 1;
     }
-    if (mu_changed) { evaluate(w, mu, &kp); nfilt = 0; }
+    if (mu_changed) { evaluate(w, mu, &kp); nfilt = 0; cnt_frej = 0; last_rej_filter = 0; }
     double tau = fmax(tau_min, 1 - mu);
     /* factorise with inertia correction */
     double reg = 0; int tries = 0, fail;
@@ -752,6 +752,13 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     Merit m0 = merit_eval(w, w->x, w->u, w->s, w->t, fkt, 0);
     double theta_k = m0.theta, phi0 = m0.f - mu * m0.logsum, D = gphi;
     if (theta_max < 0) { theta_max = 1e4 * fmax(1, theta_k); theta_min = 1e-4 * fmax(1, theta_k); }
+    /* IPOPT's filter reset heuristic (filter_reset_trigger 5, max_filter_resets 5): if in 5 successive iterations the last
+     * rejected trial point was rejected by the filter although it made sufficient progress, the filter is cleared */
+    if (n_freset < 5) {
+      if (last_rej_filter) { if (++cnt_frej >= 5) { nfilt = 0; n_freset++; cnt_frej = 0; } }
+      else cnt_frej = 0;
+    }
+    last_rej_filter = 0;
     double alpha = ap; int accepted = 0, ftype = 0;
     for (int ls = 0; ls < 50; ++ls) {
       for (int i = 0; i < (N + 1) * NX; ++i) xt[i] = w->x[i] + alpha * w->dx[i];
@@ -761,7 +768,8 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
       Merit m1 = merit_eval(w, xt, ut, st, tt, fkt, 1);
       double th1 = m1.theta, ph1 = m1.f - mu * m1.logsum;
       int ok = m1.ok && th1 < theta_max;
-      for (int q = 0; ok && q < nfilt; ++q) if (th1 >= filt_th[q] && ph1 >= filt_ph[q]) ok = 0;
+      int dom = 0;
+      for (int q = 0; q < nfilt; ++q) if (th1 >= filt_th[q] && ph1 >= filt_ph[q]) dom = 1;
       if (ok) {
         int sw = (gphi < 0) && (alpha * pow(-gphi, 2.3) > pow(theta_k, 1.1));
         if (theta_k <= theta_min && sw) {
@@ -770,8 +778,10 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
           ok = (th1 <= (1 - 1e-5) * theta_k) || (ph1 <= phi0 - 1e-8 * theta_k); ftype = 0;
         }
       }
-      if (ok) { accepted = 1; break; }
+      if (ok && !dom) { accepted = 1; break; }
+      last_rej_filter = ok && dom;
       alpha *= 0.5;
+      if (ls == 49 && n_freset < 5 && nfilt > 0) { nfilt = 0; n_freset++; cnt_frej = 0; alpha = ap; ls = -1; }  /* in place of IPOPT's restoration phase: clear the filter, search again */
     }
     if (accepted && !ftype) {
       if (nfilt == MAXFILT) { memmove(filt_th, filt_th + 1, sizeof(double) * (MAXFILT - 1)); memmove(filt_ph, filt_ph + 1, sizeof(double) * (MAXFILT - 1)); nfilt--; }
