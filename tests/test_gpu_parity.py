@@ -23,6 +23,44 @@ def _solver(batch, B=None, **kw):
                        B_max=B or batch["x_init"].shape[0], obs_per_stage=batch["obs_per_stage"], **kw)
 
 
+def _parity_counts(name, batch, o, ref, nlp_mode, max_unconverged, max_outliers):
+    """Exact counts of the GPU <-> oracle comparison of one batch, written to gpurun_out/parity_report.json (copied to
+    profiles/ by hand) and asserted against fixed integers.  An OUTLIER is an instance both solvers converged on whose cost
+    differs by more than 1e-5 relative or whose u0 differs by more than 1e-4; it is only tolerated when BOTH points are
+    feasible KKT points of the dense restated NLP (violation <= 1e-6, scaled KKT error <= 1e-8), i.e. two local optima of the
+    non-convex problem reached through round-off, and every one of them is listed in the report."""
+    import json
+    B = int(o["status"].shape[0])
+    both = (o["status"] == 0) & (ref["status"] == 0)
+    rel = np.abs(o["cost"] - ref["cost"]) / np.maximum(np.abs(ref["cost"]), 1e-300)
+    du0 = np.abs(o["U"][:, 0] - ref["U"][:, 0]).max(axis=1)
+    out_idx = [int(b) for b in np.nonzero(both & ((rel > 1e-5) | (du0 > 1e-4)))[0]]
+    listed = []
+    for b in out_idx:
+        P = nlp.from_batch(batch, b, nlp_mode)
+        va = P.violation(P.pack(o["X"][b], o["U"][b], o["s"][b])); vb = P.violation(P.pack(ref["X"][b], ref["U"][b], ref["s"][b]))
+        listed.append(dict(instance=b, cost_gpu=float(o["cost"][b]), cost_oracle=float(ref["cost"][b]), du0=float(du0[b]),
+                           violation_gpu=float(va), violation_oracle=float(vb), kkt_gpu=float(o["kkt"][b]), kkt_oracle=float(ref["kkt"][b]),
+                           iters_gpu=int(o["iters"][b]), iters_oracle=int(ref["iters"][b])))
+        assert va <= 1e-6 and vb <= 1e-6 and o["kkt"][b] <= 1e-8 and ref["kkt"][b] <= 1e-8, listed[-1]
+    rep = dict(test=name, B=B, nlp=nlp_mode, gpu_status_histogram=np.bincount(o["status"], minlength=6).tolist(),
+               oracle_status_histogram=np.bincount(ref["status"], minlength=6).tolist(), both_converged=int(both.sum()),
+               status_differs=[int(b) for b in np.nonzero(o["status"] != ref["status"])[0]],
+               max_rel_cost_err_non_outliers=float(rel[both & ~np.isin(np.arange(B), out_idx)].max()) if both.any() else None,
+               max_du0_non_outliers=float(du0[both & ~np.isin(np.arange(B), out_idx)].max()) if both.any() else None,
+               outliers=listed)
+    d = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(d):
+        path = os.path.join(d, "parity_report.json")
+        allr = json.load(open(path)) if os.path.exists(path) else {}
+        allr[name] = rep
+        json.dump(allr, open(path, "w"), indent=1)
+    assert int((o["status"] != 0).sum()) <= max_unconverged, rep
+    assert int((ref["status"] != 0).sum()) <= max_unconverged, rep
+    assert len(out_idx) <= max_outliers, rep
+    return both, rel, du0
+
+
 def _gold(name):
     g = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=True)
     batch = {k[3:]: (g[k].item() if g[k].ndim == 0 else g[k]) for k in g.files if k.startswith("in_")}
@@ -86,30 +124,26 @@ def test_config1_tight_tolerance_u0_1e4():
 
 
 # ---- batched parity against the oracle ------------------------------------------------------------------
-@pytest.mark.parametrize("cid,B,N", [(1, 1, 20), (1, 1, 10), (2, 512, 20), (3, 512, 20), (5, 96, 40)])
-def test_batched_solve_matches_oracle(cid, B, N):
+# (config id, B, N, unconverged instances allowed per solver, outliers allowed): exact integers, from the B200 run recorded in
+# profiles/r2_parity_report.json
+@pytest.mark.parametrize("cid,B,N,max_unc,max_out", [(1, 1, 20, 0, 0), (1, 1, 10, 0, 0), (2, 512, 20, 1, 2), (3, 512, 20, 1, 2), (5, 96, 40, 1, 1)])
+def test_batched_solve_matches_oracle(cid, B, N, max_unc, max_out):
     batch = scenarios.make_batch(cid, B, N=N)
     S = _solver(batch)
     o = S.solve_host(batch)
     ref = solver.solve(batch, mode=_abi.MODE_CLEAN, threads=os.cpu_count() or 4)
-    both = (o["status"] == 0) & (ref["status"] == 0)
-    assert (o["status"] == 0).mean() >= 0.97 and both.mean() >= 0.96
-    rel = np.abs(o["cost"] - ref["cost"])[both] / np.abs(ref["cost"][both])
-    du0 = np.abs(o["U"][:, 0] - ref["U"][:, 0]).max(axis=1)[both]
-    # north_star: 1e-5 relative on the optimal cost, 1e-4 absolute on u0.  A handful of non-convex
-    # instances may bifurcate to another local minimum through round-off; bound their share.
-    assert (rel <= 1e-5).mean() >= 0.99, rel.max()
-    assert (du0 <= 1e-4).mean() >= 0.99, du0.max()
+    # north_star: 1e-5 relative on the optimal cost, 1e-4 absolute on u0, for EVERY instance both solvers converged on except
+    # the listed outliers (other local optimum of the non-convex NLP, both feasible KKT points)
+    both, rel, du0 = _parity_counts("clean_config%d_B%d_N%d" % (cid, B, N), batch, o, ref, "clean", max_unc, max_out)
     assert (o["kkt"][o["status"] == 0] <= 1e-8).all()
-    # same active obstacle rows (g - s >= -1e-6) on a sample
-    for b in np.nonzero(both)[0][:16]:
+    # same active obstacle rows (g - s >= -1e-6), both directions, on every commonly converged non-outlier instance (first 64)
+    good = np.nonzero(both & (rel <= 1e-5) & (du0 <= 1e-4))[0]
+    for b in good[:64]:
         P = nlp.from_batch(batch, int(b), "clean")
         wa = P.pack(o["X"][b], o["U"][b], o["s"][b]); wb = P.pack(ref["X"][b], ref["U"][b], ref["s"][b])
         assert P.violation(wa) <= 1e-6
-        if rel[np.nonzero(both)[0].tolist().index(b)] <= 1e-5:
-            ga, gb = P.ineq(wa, with_boxes=False), P.ineq(wb, with_boxes=False)
-            strong = gb >= -1e-9
-            assert (ga[strong] >= -1e-6).all()
+        ga, gb = P.ineq(wa, with_boxes=False), P.ineq(wb, with_boxes=False)
+        assert (ga[gb >= -1e-9] >= -1e-6).all() and (gb[ga >= -1e-9] >= -1e-6).all(), int(b)
 
 
 def test_edge_cases_no_obstacles_and_warm_start():
@@ -247,24 +281,22 @@ def test_terminal_xy_equality_flag_matches_oracle():
     assert np.abs(o2["X"][on, -1, :2] - bb["x_ref"][on, -1, :2]).max() < 1e-7
 
 
-@pytest.mark.parametrize("cid,B", [(1, 1), (2, 256), (3, 256)])
-def test_reference_mode_matches_oracle(cid, B):
-    """MMPC_MODE_REFERENCE: the bug-for-bug NLP (stale plane columns) on the GPU
-    against the oracle's literal restatement of it; the stale rows change the optimum of many random
-    instances, so this is not covered by the clean-mode tests."""
+@pytest.mark.parametrize("cid,B,max_unc,max_out", [(1, 1, 0, 0), (2, 512, 1, 2), (3, 512, 1, 3), (5, 64, 1, 1)])
+def test_reference_mode_matches_oracle(cid, B, max_unc, max_out):
+    """MMPC_MODE_REFERENCE: the bug-for-bug NLP (stale plane columns, terminal rows on s[N-1]) on the GPU
+    against the oracle's literal restatement of it, exact counts (see _parity_counts)."""
     batch = scenarios.make_batch(cid, B)
     S = _solver(batch, mode=_abi.MODE_REFERENCE)
     o = S.solve_host(batch)
     ref = solver.solve(batch, mode=_abi.MODE_REFERENCE, threads=os.cpu_count() or 4)
-    both = (o["status"] == 0) & (ref["status"] == 0)
-    assert (o["status"] == 0).mean() >= 0.95 and both.mean() >= 0.94
-    rel = np.abs(o["cost"] - ref["cost"])[both] / np.abs(ref["cost"][both])
-    du0 = np.abs(o["U"][:, 0] - ref["U"][:, 0]).max(axis=1)[both]
-    assert (rel <= 1e-5).mean() >= 0.98, rel.max()
-    assert (du0 <= 1e-4).mean() >= 0.98, du0.max()
-    for b in np.nonzero(both)[0][:8]:
+    both, rel, du0 = _parity_counts("reference_config%d_B%d" % (cid, B), batch, o, ref, "reference", max_unc, max_out)
+    good = np.nonzero(both & (rel <= 1e-5) & (du0 <= 1e-4))[0]
+    for b in good[:32]:
         P = nlp.from_batch(batch, int(b), "reference")
-        assert P.violation(P.pack(o["X"][b], o["U"][b], o["s"][b])) <= 1e-6
+        wa = P.pack(o["X"][b], o["U"][b], o["s"][b]); wb = P.pack(ref["X"][b], ref["U"][b], ref["s"][b])
+        assert P.violation(wa) <= 1e-6
+        ga, gb = P.ineq(wa, with_boxes=False), P.ineq(wb, with_boxes=False)
+        assert (ga[gb >= -1e-9] >= -1e-6).all() and (gb[ga >= -1e-9] >= -1e-6).all(), int(b)   # same active obstacle set
 
 
 def test_reference_mode_goldens():
