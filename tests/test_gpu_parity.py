@@ -126,7 +126,7 @@ def test_config1_tight_tolerance_u0_1e4():
 # ---- batched parity against the oracle ------------------------------------------------------------------
 # (config id, B, N, unconverged instances allowed per solver, outliers allowed): exact integers, from the B200 run recorded in
 # profiles/r2_parity_report.json
-@pytest.mark.parametrize("cid,B,N,max_unc,max_out", [(1, 1, 20, 0, 0), (1, 1, 10, 0, 0), (2, 512, 20, 1, 2), (3, 512, 20, 1, 2), (5, 96, 40, 1, 1)])
+@pytest.mark.parametrize("cid,B,N,max_unc,max_out", [(1, 1, 20, 0, 0), (1, 1, 10, 0, 0), (2, 512, 20, 0, 0), (3, 512, 20, 0, 0), (5, 96, 40, 0, 0)])
 def test_batched_solve_matches_oracle(cid, B, N, max_unc, max_out):
     batch = scenarios.make_batch(cid, B, N=N)
     S = _solver(batch)
@@ -281,7 +281,7 @@ def test_terminal_xy_equality_flag_matches_oracle():
     assert np.abs(o2["X"][on, -1, :2] - bb["x_ref"][on, -1, :2]).max() < 1e-7
 
 
-@pytest.mark.parametrize("cid,B,max_unc,max_out", [(1, 1, 0, 0), (2, 512, 1, 2), (3, 512, 1, 3), (5, 64, 1, 1)])
+@pytest.mark.parametrize("cid,B,max_unc,max_out", [(1, 1, 0, 0), (2, 512, 1, 1), (3, 512, 0, 2), (5, 64, 0, 0)])
 def test_reference_mode_matches_oracle(cid, B, max_unc, max_out):
     """MMPC_MODE_REFERENCE: the bug-for-bug NLP (stale plane columns, terminal rows on s[N-1]) on the GPU
     against the oracle's literal restatement of it, exact counts (see _parity_counts)."""
