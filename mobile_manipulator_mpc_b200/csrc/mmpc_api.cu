@@ -230,7 +230,7 @@ static int ensure_workspace(MmpcHandle* h) {
   CK(cudaMalloc(&h->sg.rk, (size_t)(N + 1) * RS * LS * sizeof(double)));
   CK(cudaMalloc(&h->sg.gd, (size_t)staged_inst_doubles(cfg) * LS * sizeof(double)));
   CK(cudaMalloc(&h->sg.gi, (size_t)J_NFIELDS * LS * sizeof(int)));
-  CK(cudaMalloc(&h->sg.lists, (size_t)3 * LS * sizeof(int)));
+  CK(cudaMalloc(&h->sg.lists, (size_t)4 * LS * sizeof(int)));   // E, two trial lists, the Riccati's ordering of E
   CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
   CK(cudaMalloc(&h->sg.io, sizeof(SIO)));
   CK(cudaMallocHost(&h->sg.pin, (8 * 4 + 4) * sizeof(int)));

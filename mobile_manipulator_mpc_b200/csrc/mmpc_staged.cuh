@@ -97,7 +97,8 @@ constexpr int D_MU = 0, D_REGLAST = 1, D_THMAX = 2, D_THMIN = 3, D_E0 = 4, D_OS 
 // per-instance ints.  J_FRST: IPOPT's filter reset heuristic (filter_reset_trigger 5, max_filter_resets 5), packed:
 // bits 0-7 successive iterations whose last rejection was the filter's, bits 8-15 resets so far, bit 16 the last rejection of
 // the running line search was the filter's
-constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_FLAGS = 7, J_FRST = 8, J_NFIELDS = 9;
+constexpr int J_STATE = 0, J_IT = 1, J_NFILT = 2, J_LS = 3, J_CUR = 4, J_NPL = 5, J_STATUS = 6, J_FLAGS = 7, J_FRST = 8,
+              J_REGF = 9 /* 1: the factorisation of the last iteration needed delta_w > 0 */, J_NFIELDS = 10;
 constexpr int FILTER_RESET_TRIGGER = 5, MAX_FILTER_RESETS = 5;
 constexpr int ST_ACTIVE = 0, ST_DONE = 1, ST_TRIAL = 2, ST_FINISH = 3;  // FINISH: results are written by the step kernels of this round
 //  // ACTIVE: next phase is eval; TRIAL: next phase is a trial
@@ -318,7 +319,7 @@ struct Inst {
     }
     D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
     D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
-    J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0; J(J_FRST) = 0;
+    J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0; J(J_FRST) = 0; J(J_REGF) = 0;
     J(J_FLAGS) = P.io->flags ? (int)P.io->flags[b] : 0;
   }
 
@@ -1129,7 +1130,7 @@ struct Inst {
     int tries = 0;
     for (;;) {
       int fail = riccati(reg, mu, it);
-      if (!fail) { if (reg > 0) D(D_REGLAST) = reg; break; }
+      if (!fail) { if (reg > 0) D(D_REGLAST) = reg; J(J_REGF) = reg > 0; break; }
       if (reg == 0) reg = (reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3);
       else reg *= (reg_last == 0 ? 100 : 8);
       if (++tries > 40 || reg > 1e20) { finish(MMPC_STATUS_FACTOR); return; }
@@ -1867,6 +1868,11 @@ __device__ __forceinline__ int& inst_state(const SParams& P, int b) {
 __device__ __forceinline__ int* list_E(const SParams& P) { return P.lists; }
 __device__ __forceinline__ int* list_T(const SParams& P) { return P.lists + P.tsel * P.LS; }
 __device__ __forceinline__ int* list_n(const SParams& P, int which) { return P.lists + which * P.LS; }
+// The Riccati kernel's view of the E list (same entries, list 3): first the instances whose last factorisation needed no
+// regularisation, then the ones that did.  Two instances share a warp in lock step and a warp repeats its sweep until both
+// are factorised, so pairing like with like keeps the convex instances (3 of 4 iterations) out of the retries, and lets a
+// warp of two non-convex ones abandon the delta_w = 0 attempt at the first pivot both have lost.
+__device__ __forceinline__ int* list_S(const SParams& P) { return P.lists + 3 * P.LS; }
 
 // ---- phase bodies on list items (shared by the kernels and by tests/emu) -----------------------------
 __device__ inline void body_init(const SParams& P, int b) { Inst S(P, b); S.init(); }
@@ -1904,30 +1910,41 @@ inline void compact_list(const SParams& P, int dst, int src, int want) {
   int n = 0; int* out = list_n(P, dst); const int* in = list_n(P, src);
   for (int i = 0; i < P.cnt[src]; ++i) if (inst_state(P, in[i]) == want) out[n++] = in[i];
   P.cnt[dst] = n;
+  if (dst == 0) for (int i = 0; i < n; ++i) list_S(P)[i] = out[i];  // (the order of the Riccati's list does not change any result)
 }
 #else
 // Ordered compaction  list dst <- { b in list src : state(b) == want }  by one block of 1024 threads: warp w
 // scans a contiguous chunk of the source list 32 entries at a time (coalesced), counts with ballots, the warp
 // totals are scanned through shared memory, and the second pass writes the survivors in order.  Every
 // active instance is in the previous round's trial list, so the source shrinks with the active set.
+// regularised(b): the factorisation of instance b's last iteration needed delta_w > 0
+__device__ __forceinline__ bool inst_regularised(const SParams& P, int b) {
+  return P.gi[((((long long)(b >> 5)) * J_NFIELDS + J_REGF) << 5) + (b & 31)] != 0;
+}
 __global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_constant__ SParams P, int dst, int src, int want) {
-  __shared__ int wtot[32];
+  __shared__ int wtot[32], wreg[32];
   int* out = list_n(P, dst); const int* in = list_n(P, src);
+  const bool split = dst == 0;  // the E list also gets its Riccati ordering (list_S)
+  int* outs = list_S(P);
   const int n = P.cnt[src];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
   const int chunk = ((n + blockDim.x - 1) / blockDim.x) * 32;  // entries per warp, multiple of 32
   const int lo = warp * chunk, hi = min(n, lo + chunk);
-  int c = 0;
+  int c = 0, cr = 0;
   for (int i0 = lo; i0 < hi; i0 += 32) {
     int i = i0 + lane;
-    bool f = i < hi && inst_state(P, in[i]) == want;
+    int b = i < hi ? in[i] : 0;
+    bool f = i < hi && inst_state(P, b) == want;
     c += __popc(__ballot_sync(FULL, f));
+    if (split) cr += __popc(__ballot_sync(FULL, f && inst_regularised(P, b)));
   }
-  if (lane == 0) wtot[warp] = c;
+  if (lane == 0) { wtot[warp] = c; wreg[warp] = cr; }
   __syncthreads();
-  int off = 0, tot = 0;
-  for (int w2 = 0; w2 < nw; ++w2) { int v = wtot[w2]; if (w2 < warp) off += v; tot += v; }
+  int off = 0, tot = 0, offr = 0, totr = 0;
+  for (int w2 = 0; w2 < nw; ++w2) { int v = wtot[w2], vr = wreg[w2]; if (w2 < warp) { off += v; offr += vr; } tot += v; totr += vr; }
+  int off0 = off - offr;          // position among the unregularised ones
+  offr += tot - totr;             // the regularised ones follow them
   for (int i0 = lo; i0 < hi; i0 += 32) {
     int i = i0 + lane;
     int b = i < hi ? in[i] : 0;
@@ -1935,6 +1952,13 @@ __global__ void __launch_bounds__(1024) staged_compact_kernel(const __grid_const
     unsigned m = __ballot_sync(FULL, f);
     if (f) out[off + __popc(m & ((1u << lane) - 1))] = b;
     off += __popc(m);
+    if (split) {
+      const bool r = f && inst_regularised(P, b);
+      unsigned mr = __ballot_sync(FULL, r), m0 = m & ~mr;
+      if (r) outs[offr + __popc(mr & ((1u << lane) - 1))] = b;
+      else if (f) outs[off0 + __popc(m0 & ((1u << lane) - 1))] = b;
+      offr += __popc(mr); off0 += __popc(m0);
+    }
   }
   if (threadIdx.x == 0) P.cnt[dst] = tot;
 }

@@ -471,7 +471,7 @@ struct Team {
     for (;;) {
       const int fail = riccati<Q3>(reg, mu, it);
       if (need) {
-        if (!fail) { need = false; if (reg > 0 && c == 0) S.D(D_REGLAST) = reg; }
+        if (!fail) { need = false; if (c == 0) { if (reg > 0) S.D(D_REGLAST) = reg; S.J(J_REGF) = reg > 0; } }
         else {
           if (reg == 0) reg = (reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3);
           else reg *= (reg_last == 0 ? 100 : 8);
@@ -489,7 +489,7 @@ struct Team {
 // Q3: the literal reference NLP (Inst::q3) -- the host picks the instantiation from the configuration
 template <bool Q3>
 __device__ inline void body_solve_team(const SParams& P, int j, int c, double* sm) {
-  Team T(P, list_E(P)[j], c, sm);
+  Team T(P, list_S(P)[j], c, sm);
   T.template solve<Q3>();
 }
 

@@ -57,7 +57,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   EmuTeam* tw = new EmuTeam(); g_team = tw;
   std::vector<char*> stacks(16);
   for (int i = 0; i < 16; ++i) stacks[i] = (char*)malloc(1 << 18);
-  std::vector<int> gi((size_t)J_NFIELDS * P.LS, 0), lists((size_t)3 * P.LS, 0);
+  std::vector<int> gi((size_t)J_NFIELDS * P.LS, 0), lists((size_t)4 * P.LS, 0);
   int cnt[4] = {0, 0, 0, 0};
   P.ws = ws.data(); P.gd = gd.data(); P.gi = gi.data(); P.lists = lists.data(); P.cnt = cnt;
   for (int b = 0; b < B; ++b) { body_init(P, b); lists[P.LS + b] = b; }
