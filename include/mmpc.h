@@ -24,6 +24,7 @@
  *     planes [B][n_pl][6]  obstacle_manipulation_list entries (point xyz, normal xyz)  demo_wholebody_qref.py:21-33
  *     n_pl_inst[B] int32   planes actually used by instance b (NULL -> cfg.n_pl for all)
  *     flags  [B] uint8     bit0: terminal xy equality  interface_wholebody_qref.py:167
+ *     x_guess[B][N+1][9]   initial guess of X (NULL -> tile(x_init), the reference behaviour :302)
  * Outputs:
  *     U [B][N][5]  X [B][N+1][9]  s [B][N+1]   sol.value(U/X/s)   (:329-330)
  *     cost[B]  sol.value(cost) (:317)     kkt[B]  final scaled NLP error (IPOPT E_0)
@@ -67,6 +68,17 @@ enum {
   MMPC_MODE_CLEAN = 1      /* stage-separable: -max_j c_k[i,j] <= s_k only, terminal rows on s[N]  */
 };
 
+/* Which of the reference's controllers the handle solves.
+ *   WHOLEBODY  controllers/mpc_wholebody_qref.py::MPCWholeBody (the hot path; everything above)
+ *   BASE       controllers/mpc_base.py::MPCBase (:114-189): the unicycle base alone -- 6 states x y psi dx dy dpsi, 2 controls
+ *              dV dw, ground circles against one slack per stage (weight M), boxes on x y dx dy dpsi and on u, the yaw error
+ *              of the cost taken through angleDiff (:59-84), and X warm-started from the previous solution (:196-201).  It is
+ *              solved as the whole-body NLP with the arm taken out: arrays keep the 9 / 5 layout, the three arm states and
+ *              controls are unbounded, carry a unit control weight and no state weight, so they stay at their initial
+ *              values and do not interact with the base (no FK row exists: no self-collision rows, n_pl must be 0, mode
+ *              MMPC_MODE_CLEAN).  S plays the role of M.  Host class: mobile_manipulator_mpc_b200/controllers/mpc_base.py. */
+enum { MMPC_MODEL_WHOLEBODY = 0, MMPC_MODEL_BASE = 1 };
+
 /* execution strategy of mmpc_solve (same algorithm, same results to the bit):
  *   STAGED batch-synchronous rounds of phase kernels over compacted lists of active instances (stage-parallel
  *          evaluation / step / trial, 16-lane column-parallel Riccati), the whole solve one CUDA graph whose
@@ -88,7 +100,7 @@ typedef struct MmpcConfig {
   int32_t terminal_rows_on_sN; /* MMPC_MODE_REFERENCE: 0 (default) = the four terminal self-collision rows are bounded by s[N-1],
                                   the reference's leaked loop variable (:263-265); 1 = by s[N] (what a
                                   reader of the reference would expect).  Same optimum unless the barrier path forks. */
-  int32_t reserved1;
+  int32_t model;         /* MMPC_MODEL_*: 0 = MPCWholeBody (controllers/mpc_wholebody_qref.py), 1 = MPCBase (controllers/mpc_base.py) */
   double dt;             /* robot.dt, demo_wholebody_qref.py:10                                  */
   double Qd[9], Pd[9], Rd[5], Wd[5], S; /* diagonals of Q,P,R,W and S (:12-16); setWeight :119   */
   double ulim[2][5];     /* (:17)  rows: lower, upper                                            */
@@ -112,6 +124,8 @@ typedef struct MmpcBatchIn {
   const double* planes;     /* may be NULL iff n_pl == 0 */
   const int32_t* n_pl_inst; /* may be NULL */
   const uint8_t* flags;     /* may be NULL */
+  const double* x_guess;    /* may be NULL: X <- tile(x_init), what MPCWholeBody.solve does (:302).  [B][N+1][9]: initial guess of
+                               X[1..N] (row 0 is ignored: X[0] = x_init); MPCBase warm-starts X like this (mpc_base.py:196-201) */
 } MmpcBatchIn;
 
 typedef struct MmpcBatchOut {

@@ -14,6 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_LINESEARCH, STATUS_FACTOR, STATUS_NAN, STATUS_ACCEPTABLE = range(6)
 STATUS_NAMES = ("converged", "max_iter", "linesearch", "factor", "nan", "acceptable")
 MODE_REFERENCE, MODE_CLEAN = 0, 1
+MODEL_WHOLEBODY, MODEL_BASE = 0, 1
 KERNEL_AUTO, KERNEL_STAGED, KERNEL_STAGED_THREAD, KERNEL_STAGED_UNFUSED, KERNEL_STAGED_FAT, KERNEL_STAGED_HOSTLOOP = 0, 3, 4, 5, 6, 7
 
 _d = C.c_double
@@ -22,7 +23,7 @@ _d = C.c_double
 class MmpcConfig(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("n_obs", C.c_int32), ("n_pl", C.c_int32), ("mode", C.c_int32),
-        ("obs_per_stage", C.c_int32), ("max_iter", C.c_int32), ("terminal_rows_on_sN", C.c_int32), ("reserved1", C.c_int32),
+        ("obs_per_stage", C.c_int32), ("max_iter", C.c_int32), ("terminal_rows_on_sN", C.c_int32), ("model", C.c_int32),
         ("dt", _d),
         ("Qd", _d * 9), ("Pd", _d * 9), ("Rd", _d * 5), ("Wd", _d * 5), ("S", _d),
         ("ulim", (_d * 5) * 2), ("xlim", (_d * 9) * 2), ("dulim", (_d * 5) * 2),
@@ -33,7 +34,7 @@ class MmpcConfig(C.Structure):
 
 class MmpcBatchIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes", "n_pl_inst", "flags")]
+                ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes", "n_pl_inst", "flags", "x_guess")]
 
 
 class MmpcBatchOut(C.Structure):

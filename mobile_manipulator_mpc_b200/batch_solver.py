@@ -160,7 +160,12 @@ class BatchSolver:
         flags = batch.get("flags")
         if flags is not None:
             flags = np.ascontiguousarray(flags, dtype=np.uint8); keep.append(flags)
-        bi = _abi.MmpcBatchIn(*ptrs, _abi.ptr(npl), _abi.ptr(flags))
+        xg = batch.get("x_guess")
+        if xg is not None:
+            xg = np.ascontiguousarray(xg, dtype=np.float64); keep.append(xg)
+            if xg.shape != (B, self.cfg.N + 1, 9):
+                raise ValueError(f"x_guess: expected shape {(B, self.cfg.N + 1, 9)}, got {xg.shape}")
+        bi = _abi.MmpcBatchIn(*ptrs, _abi.ptr(npl), _abi.ptr(flags), _abi.ptr(xg))
         if out is None:
             out = self.host_outputs(B, want)
         bo = _abi.MmpcBatchOut(*[_abi.ptr(out.get(k)) for k in _OUT_KEYS])
@@ -189,8 +194,10 @@ class BatchSolver:
                 raise ValueError(f"{k}: need contiguous float64 tensor of shape {shp[k]}")
             ptrs.append(C.c_void_p(a.data_ptr()))
         npl, flags = batch.get("n_pl_inst"), batch.get("flags")
+        xg = batch.get("x_guess")
         bi = _abi.MmpcBatchIn(*ptrs, None if npl is None else C.c_void_p(npl.data_ptr()),
-                              None if flags is None else C.c_void_p(flags.data_ptr()))
+                              None if flags is None else C.c_void_p(flags.data_ptr()),
+                              None if xg is None else C.c_void_p(xg.data_ptr()))
         N = self.cfg.N
         if out is None:
             out = dict(U=torch.empty((B, N, 5), dtype=torch.float64, device=dev),
@@ -209,7 +216,7 @@ class BatchSolver:
         dev = torch.device("cuda", self.device)
         out = {}
         for k, v in batch.items():
-            if isinstance(v, np.ndarray) and k in _IN_KEYS:
+            if isinstance(v, np.ndarray) and (k in _IN_KEYS or k == "x_guess"):
                 out[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
             elif k == "n_pl_inst" and v is not None:
                 out[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.int32)).to(dev)

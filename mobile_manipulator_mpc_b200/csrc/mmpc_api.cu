@@ -34,7 +34,7 @@ struct MmpcHandle {
   double phase_ms[MMPC_NPHASE];
   long long phase_launches[MMPC_NPHASE];
   // staging for mmpc_solve_host
-  struct { double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes, *U, *X, *s, *cost, *kkt;
+  struct { double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes, *x_guess, *U, *X, *s, *cost, *kkt;
            int32_t *n_pl_inst, *iters, *status; uint8_t* flags; } d, h;
   cudaStream_t stream;
   char err[256];
@@ -51,7 +51,7 @@ static thread_local char g_err[256] = "";
     }                                                                                              \
   } while (0)
 
-extern "C" int mmpc_version(void) { return 100; }
+extern "C" int mmpc_version(void) { return 200; }
 
 extern "C" const char* mmpc_error_string(int code) {
   switch (code) {
@@ -66,7 +66,7 @@ extern "C" const char* mmpc_error_string(int code) {
 
 extern "C" void mmpc_default_config(MmpcConfig* c) {
   memset(c, 0, sizeof *c);
-  c->N = 20; c->n_obs = 3; c->n_pl = 3; c->mode = MMPC_MODE_REFERENCE; c->obs_per_stage = 0; c->max_iter = 2000;
+  c->N = 20; c->n_obs = 3; c->n_pl = 3; c->mode = MMPC_MODE_REFERENCE; c->obs_per_stage = 0; c->max_iter = 2000; c->model = MMPC_MODEL_WHOLEBODY;
   c->dt = 0.1;
   const double q[9] = {25, 25, 0, 0, 0, 5, 5, 5, 5};
   const double r[5] = {0.1, 0.1, 0, 0, 0}, w[5] = {0, 0, 0.1, 0.1, 0.1};
@@ -98,6 +98,9 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   if (!cfg || !out || B_max < 1) return MMPC_ERR_ARG;
   if (cfg->N < 1 || cfg->N > 63 || cfg->n_obs < 0 || cfg->n_pl < 0 || cfg->n_pl > MMPC_MAX_PLANES) return MMPC_ERR_ARG;
   if (cfg->mode != MMPC_MODE_CLEAN && cfg->mode != MMPC_MODE_REFERENCE) return MMPC_ERR_ARG;
+  if (cfg->model != MMPC_MODEL_WHOLEBODY && cfg->model != MMPC_MODEL_BASE) return MMPC_ERR_ARG;
+  // the base-only controller (controllers/mpc_base.py) has no arm: no plane rows, no bug-for-bug rows
+  if (cfg->model == MMPC_MODEL_BASE && (cfg->n_pl != 0 || cfg->mode != MMPC_MODE_CLEAN)) return MMPC_ERR_UNSUPPORTED;
   // the literal reference NLP bounds the terminal self-collision rows by s[N-1]: the starting point relies on x_N = x_{N-1},
   // which needs a stage N-1 >= 1 (stage 0 is the un-pushed initial state)
   if (cfg->mode == MMPC_MODE_REFERENCE && cfg->terminal_rows_on_sN == 0 && cfg->N < 2) return MMPC_ERR_UNSUPPORTED;
@@ -245,7 +248,7 @@ static SParams staged_params(const MmpcHandle* h, int32_t B) {
   P.cfg = cfg; P.B = B; P.io = h->sg.io;
   P.ws = h->sg.ws; P.qp = h->sg.qp; P.rk = h->sg.rk; P.team = h->sg_team; P.fused = h->sg_fused;
   const PartPlan plan = part_plan(cfg);
-  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10 && cfg.mode == MMPC_MODE_CLEAN) ? 1 : 0;
+  P.parts = (h->sg_parts && h->sg_fused && plan.n_parts <= 10 && cfg.mode == MMPC_MODE_CLEAN && cfg.model == MMPC_MODEL_WHOLEBODY) ? 1 : 0;
   P.gd = h->sg.gd; P.gi = h->sg.gi; P.lists = h->sg.lists; P.cnt = h->sg.cnt; P.LS = h->sg.LS;
   P.R = staged_rows(cfg); P.ITSZ = staged_itsz(cfg); P.STG = staged_stage_doubles(cfg); P.ND = staged_inst_doubles(cfg);
   return P;
@@ -500,7 +503,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   graph_account(h);
   SIO io; memset(&io, 0, sizeof io);
   io.x_init = in->x_init; io.x_ref = in->x_ref; io.u_ref = in->u_ref; io.u_last = in->u_last; io.u_guess = in->u_guess;
-  io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags;
+  io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags; io.x_guess = in->x_guess;
   io.U = out->U; io.X = out->X; io.s = out->s; io.cost = out->cost; io.kkt = out->kkt; io.iters = out->iters; io.status = out->status;
   io.B = B;
   staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io);
@@ -538,7 +541,7 @@ static int ensure_staging(MmpcHandle* h) {
   int rc;
 #define SA(name, n) if ((rc = stage_alloc(&h->d.name, &h->h.name, (n))) != MMPC_OK) return rc
   SA(x_init, B * 9); SA(x_ref, B * (N + 1) * 9); SA(u_ref, B * N * 5); SA(u_last, B * N * 5); SA(u_guess, B * N * 5);
-  SA(circles, B * circles_per_instance(h->cfg)); SA(planes, B * (size_t)h->cfg.n_pl * 6);
+  SA(circles, B * circles_per_instance(h->cfg)); SA(planes, B * (size_t)h->cfg.n_pl * 6); SA(x_guess, B * (N + 1) * 9);
   SA(U, B * N * 5); SA(X, B * (N + 1) * 9); SA(s, B * (N + 1)); SA(cost, B); SA(kkt, B);
   SA(n_pl_inst, B); SA(iters, B); SA(status, B); SA(flags, B);
 #undef SA
@@ -573,7 +576,7 @@ extern "C" int mmpc_solve_host(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, 
   UP(x_init, b * 9, double); UP(x_ref, b * (N + 1) * 9, double); UP(u_ref, b * N * 5, double);
   UP(u_last, b * N * 5, double); UP(u_guess, b * N * 5, double);
   UP(circles, b * circles_per_instance(h->cfg), double); UP(planes, b * (size_t)h->cfg.n_pl * 6, double);
-  UP(n_pl_inst, b, int32_t); UP(flags, b, uint8_t);
+  UP(n_pl_inst, b, int32_t); UP(flags, b, uint8_t); UP(x_guess, b * (N + 1) * 9, double);
 #undef UP
   dout.U = h->d.U; dout.status = h->d.status;
   if (out->X) dout.X = h->d.X;

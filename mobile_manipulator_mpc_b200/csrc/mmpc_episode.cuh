@@ -70,17 +70,6 @@ __device__ inline int ik_solve(const double* q0, double xt, double zt, double* q
   return (r0 * r0 + r1 * r1 > 1e-10) ? 1 : 0;
 }
 
-// angleDiff (controllers/mpc_wholebody_qref.py:92-117): a - b folded to the nearest representative
-__device__ inline double angle_diff(double a, double b) {
-  const double PI = 3.14159265358979323846;
-  a = fmod(a + PI, 2 * PI) - PI;
-  b = fmod(b + PI, 2 * PI) - PI;
-  const double d = a - b;
-  if (a * b >= 0) return d;
-  if (a > b) return d <= PI ? d : d - 2 * PI;
-  return d > -PI ? d : d + 2 * PI;
-}
-
 struct EpisodeArgs {
   int B, N, M, n_manip;
   MmpcEpisodeIO io;

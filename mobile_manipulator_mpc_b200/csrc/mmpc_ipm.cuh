@@ -7,6 +7,18 @@ namespace mmpc {
 
 __device__ constexpr int POSE2X[6] = {0, 1, 2, 6, 7, 8};
 
+// angleDiff (controllers/mpc_wholebody_qref.py:92-117, controllers/mpc_base.py:59-84): a - b folded to the nearest
+// representative; casadi fmod == C fmod (sign of the dividend)
+__device__ inline double angle_diff(double a, double b) {
+  const double PI = 3.14159265358979323846;
+  a = fmod(a + PI, 2 * PI) - PI;
+  b = fmod(b + PI, 2 * PI) - PI;
+  const double d = a - b;
+  if (a * b >= 0) return d;
+  if (a > b) return d <= PI ? d : d - 2 * PI;
+  return d > -PI ? d : d + 2 * PI;
+}
+
 struct KktParts {
   double e_stat, e_prim, c_hi, c_lo, sum_lam, sum_z;
   int n_z, n_eq;

@@ -49,6 +49,7 @@ struct SIO {
   const double *x_init, *x_ref, *u_ref, *u_last, *u_guess, *circles, *planes;
   const int32_t* n_pl_inst;
   const uint8_t* flags;
+  const double* x_guess;
   double *U, *X, *s, *cost, *kkt;
   int32_t *iters, *status;
   int B;           // instances of this call
@@ -115,7 +116,9 @@ constexpr int NPART = 8;
 __host__ __device__ inline int staged_stale_rows(const MmpcConfig& c) {
   return (c.mode == MMPC_MODE_REFERENCE && c.n_pl > 1) ? 6 * (c.n_pl - 1) : 0;
 }
-__host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + 4 + (c.n_pl > 0 ? 6 : 0) + staged_stale_rows(c); }
+// self-collision rows of a stage: 4, none in the base-only model (controllers/mpc_base.py has no arm)
+__host__ __device__ inline int staged_self_rows(const MmpcConfig& c) { return c.model == MMPC_MODEL_BASE ? 0 : 4; }
+__host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + staged_self_rows(c) + (c.n_pl > 0 ? 6 : 0) + staged_stale_rows(c); }
 __host__ __device__ inline int staged_itsz(const MmpcConfig& c) { return I_T + 2 * staged_rows(c); }
 // MMPC_MODE_REFERENCE: the plane margins c[i][j] of the stage's six body points (6 x n_pl, i-major), written once per
 // evaluated point by the pose kernel and read by the three threads (stages k-1, k, k+1) whose stale-column rows need them
@@ -164,6 +167,12 @@ struct Inst {
     N = cfg.N; R = p.R; STG = p.STG; ITSZ = p.ITSZ; B2 = 2 * p.ITSZ; nobs = cfg.n_obs; dt = cfg.dt;
     npl = 0;
     MG = S_DT + R + (cfg.obs_per_stage ? 3 * nobs : 0);
+    nself = staged_self_rows(cfg);
+  }
+  int nself;  // self-collision rows per stage (0 in the base-only model)
+  // state error of the cost: component 2 (yaw) of the base-only model goes through angleDiff (controllers/mpc_base.py:129-133)
+  __device__ __forceinline__ double xerr(int i, double x, double xr) const {
+    return (i == 2 && cfg.model == MMPC_MODEL_BASE) ? angle_diff(x, xr) : x - xr;
   }
   int MG;  // offset (second block) of the plane-margin cache of a stage, see staged_marg_doubles
   __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << 5]; }
@@ -251,12 +260,13 @@ struct Inst {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         double v = fmax(fmin(ldg(P.io->x_init + (long long)b * NX + i), cfg.xlim[1][i]), cfg.xlim[0][i]);  // :290-291
+        if (k >= 1 && P.io->x_guess) v = ldg(P.io->x_guess + ((long long)b * (N + 1) + k) * NX + i);       // mpc_base.py:196-201
         if (k >= 1) v = push_in(v, cfg.xlim[0][i], cfg.xlim[1][i]);
         double xr = ldg(xref + k * NX + i);
         x[i] = v; W(k, I_X + i) = v; W(k, I_LAM + i) = 0; W2(k, IN_XREF + i) = xr;
         W(k, I_ZXL + i) = 1; W(k, I_ZXU + i) = 1;
         double Wx = (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-        if (k >= 1) gmax = fmax(gmax, fabs(2 * Wx * (v - xr)));
+        if (k >= 1) gmax = fmax(gmax, fabs(2 * Wx * xerr(i, v, xr)));
       }
       if (k < N) {
 #pragma unroll
@@ -279,7 +289,7 @@ struct Inst {
         W(k, I_T + i) = h; hmax = fmax(hmax, h);
       }
 #pragma unroll 1
-      for (int m = 0; m < 4; ++m) {
+      for (int m = 0; m < nself; ++m) {
         Point p; point_eval(x[0], x[1], f, SELFD[m], p);
         double h = cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]);
         W(k, I_T + nobs + m) = h;
@@ -290,11 +300,11 @@ struct Inst {
         for (int i = 0; i < 6; ++i) {
           Point p; point_eval(x[0], x[1], f, BODY[i], p);
           int jb; double h = plane_row<false>(p, jb);
-          W(k, I_T + nobs + 4 + i) = h; hmax = fmax(hmax, h);
+          W(k, I_T + nobs + nself + i) = h; hmax = fmax(hmax, h);
         }
       }
       if (staged_stale_rows(cfg) > 0) {  // rows with stale plane columns: slack k >= 1, j < npl - 1
-        const int nst = cfg.n_pl - 1, r0 = nobs + 10;
+        const int nst = cfg.n_pl - 1, r0 = nobs + nself + 6;
         for (int r = r0; r < R; ++r) W(k, I_T + r) = 0;
         if (refmode) {
           double pp[NP] = {x[0], x[1], x[2], x[6], x[7], x[8]}; FK ff;
@@ -313,7 +323,7 @@ struct Inst {
       gmax = fmax(gmax, fabs(2 * cfg.S * s));
       for (int r = 0; r < R; ++r) {
         // (x_N = x_{N-1} in the starting point, so s[N-1] already clears the terminal rows by the same 1e-2)
-        const double sr = (k == N && q3() && r >= nobs && r < nobs + 4) ? W(k - 1, I_S) : s;
+        const double sr = (k == N && q3() && r >= nobs && r < nobs + nself) ? W(k - 1, I_S) : s;
         W(k, I_T + r) = sr - W(k, I_T + r); W(k, I_T + R + r) = 1.0;
       }
     }
@@ -443,7 +453,7 @@ struct Inst {
     const int it = J(J_CUR) * ITSZ, jt = (1 - J(J_CUR)) * ITSZ;
     constexpr bool cand = PHASE == 1;
     const double mu = D(D_MU), alpha = cand ? D(D_ALPHA) : 0.0, ad = cand ? D(D_AD) : 0.0;
-    const int nst = cfg.n_pl - 1, r0 = nobs + 10;
+    const int nst = cfg.n_pl - 1, r0 = nobs + nself + 6;
     // Margins and forward kinematics of the stages k-1, k, k+1 at the point this phase works on (the candidate in phase 1,
     // the current iterate otherwise): computed ONCE per stage by pose_pass() in the kernel launched just before, read here,
     // one body point at a time.  The owner of a row and the neighbour that adds its pose terms see the same stored
@@ -639,7 +649,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-      double gr = 2 * Wx * (x[i] - W2(k, IN_XREF + i));
+      double gr = 2 * Wx * xerr(i, x[i], W2(k, IN_XREF + i));
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -713,7 +723,7 @@ struct Inst {
       for (int a = 0; a < NP; ++a) { sv_a[a] = A.a[a]; A.a[a] = 0; }
     }
 #pragma unroll 1
-    for (int m = 0; m < 4; ++m) {  // self collision :219-222
+    for (int m = 0; m < nself; ++m) {  // self collision :219-222
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
       double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsq(d2);
       double h = cfg.self_collision_radius - d2 * inv;
@@ -743,7 +753,7 @@ struct Inst {
       for (int i = 0; i < 6; ++i) {  // obsAvoidConvex :57-89 (proper row)
         Point p; point_eval(x[0], x[1], f, BODY[i], p);
         int jb; double h = plane_row(p, jb);
-        double z, it_, res; row_state(it, nobs + 4 + i, k, h, s, z, it_, res, A);
+        double z, it_, res; row_state(it, nobs + nself + i, k, h, s, z, it_, res, A);
         double sig = z * it_;
         double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)}, g[NP];
         point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g
@@ -1077,7 +1087,7 @@ struct Inst {
     for (int k = 0; k <= N; ++k) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = W(k, it + I_X + i), e = v - W2(k, IN_XREF + i);
+        double v = W(k, it + I_X + i), e = xerr(i, v, W2(k, IN_XREF + i));
         fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
         if (P.io->X) P.io->X[((long long)b * (N + 1) + k) * NX + i] = v;
       }
@@ -1148,7 +1158,7 @@ struct Inst {
     prefetch_stage(k, it, false);
     const double* ci = stage_ptr(k, it); double* c2 = stage_ptr(k, B2);
     // ring items in consumption order: x bounds (zl, zu) x9, u bounds x5, circle rows (t, z, cx, cy, r), other rows (t, z)
-    const int q_circ = NX + NU, q_rows = q_circ + nobs, q_end = q_rows + 4 + (npl > 0 ? 6 : 0);
+    const int q_circ = NX + NU, q_rows = q_circ + nobs, q_end = q_rows + nself + (npl > 0 ? 6 : 0);
     auto ring_issue = [&](int q) {  // one code path (selects, no per-kind branches): the body is inlined at 20 sites
       double* d = ring_slot(q);
       if (q < q_end) {
@@ -1184,7 +1194,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - ldg(&c2[(IN_XREF + i) << 5]);
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], ldg(&c2[(IN_XREF + i) << 5]));
       fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -1254,7 +1264,7 @@ struct Inst {
     }
     if (REF && k == N && q3()) { s_cur = W(N - 1, it + I_S); ds_cur = W2(N - 1, S_DS); }  // terminal rows on s[N-1]
 #pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < nself; ++m) {
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
       double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsq(d2), d = d2 * inv;
       double n[3] = {p.P[0] * inv, p.P[1] * inv, p.P[2] * inv}, g[NP];
@@ -1277,7 +1287,7 @@ struct Inst {
 #pragma unroll
         for (int a = 0; a < NP; ++a) gd_ = fma(g[a], dp[a], gd_);
         const double* rb = ring_pop(); const double rt = rb[0], rz = rb[bs]; ring_next();
-        row_step(nobs + 4 + i, h, gd_, rt, rz);
+        row_step(nobs + nself + i, h, gd_, rt, rz);
       }
     }
     double log_extra = 0;
@@ -1299,7 +1309,7 @@ struct Inst {
     double fsum = 0;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double v = W(k, it + I_X + i), e = v - W2(k, IN_XREF + i);
+      double v = W(k, it + I_X + i), e = xerr(i, v, W2(k, IN_XREF + i));
       fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
       if (P.io->X) P.io->X[((long long)b * (N + 1) + k) * NX + i] = v;
     }
@@ -1381,7 +1391,7 @@ struct Inst {
         double l = W(k, it + I_LAM + i);
         W(k, jt + I_LAM + i) = l + alpha * (W2(k, S_LAMN + i) - l);
       }
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = x[i] - W2(k, IN_XREF + i);
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], W2(k, IN_XREF + i));
       fsum += Wx * e * e;
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -1451,7 +1461,7 @@ struct Inst {
       row_val(i, (circ(k, i, 2) + cfg.base_radius) - sqrt(ddx * ddx + ddy * ddy));
     }
 #pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < nself; ++m) {
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
       row_val(nobs + m, cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]));
     }
@@ -1459,7 +1469,7 @@ struct Inst {
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         Point p; point_eval(x[0], x[1], f, BODY[i], p);
-        int jb; row_val(nobs + 4 + i, plane_row(p, jb));
+        int jb; row_val(nobs + nself + i, plane_row(p, jb));
       }
     }
     bool fin = ok && (fsum == fsum) && (theta == theta);
@@ -1496,7 +1506,7 @@ struct Inst {
 #pragma unroll 1
     for (int f = 0; f < S_DT - IN_XREF; ++f) async_copy8(rb_in + f * bs, &c2[(IN_XREF + f) << 5]);
     async_commit();
-    const int q_end = nobs + 4 + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
+    const int q_end = nobs + nself + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
     auto ring_issue = [&](int q) {
       if (q < q_end) {
         double* d = sm + ((q & (RING_DT - 1)) * RING_W) * bs;
@@ -1607,7 +1617,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-      double e = x[i] - rb_in[(IN_XREF - IN_XREF + i) * bs];
+      double e = xerr(i, x[i], rb_in[(IN_XREF - IN_XREF + i) * bs]);
       fsum += Wx * e * e;
       double gr = 2 * Wx * e;
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
@@ -1703,7 +1713,7 @@ struct Inst {
       for (int a = 0; a < NP; ++a) { sv_a[a] = A.a[a]; A.a[a] = 0; }
     }
 #pragma unroll 1
-    for (int m = 0; m < 4; ++m) {  // self collision :219-222
+    for (int m = 0; m < nself; ++m) {  // self collision :219-222
       Point p; point_eval(x[0], x[1], f, SELFD[m], p);
       double d2 = p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2], inv = rsq(d2);
       double h = cfg.self_collision_radius - d2 * inv;
@@ -1740,11 +1750,11 @@ struct Inst {
         Point p; point_eval(x[0], x[1], f, BODY[i], p);
         int jb; double h = plane_row(p, jb);
         async_wait<RING_DT - 1>();
-        const double* rb = sm + (((nobs + 4 + i) & (RING_DT - 1)) * RING_W) * bs;
+        const double* rb = sm + (((nobs + nself + i) & (RING_DT - 1)) * RING_W) * bs;
         const double rt = rb[0], rdt = rb[2 * bs];
         double z = rb[bs], it_, res;
-        ring_issue(nobs + 4 + i + RING_DT);
-        row_core(nobs + 4 + i, h, rt, rdt, z, it_, res);
+        ring_issue(nobs + nself + i + RING_DT);
+        row_core(nobs + nself + i, h, rt, rdt, z, it_, res);
         double sig = z * it_;
         double n[3] = {PL(6 * jb + 3), PL(6 * jb + 4), PL(6 * jb + 5)}, g[NP];
         point_grad(f, p, n, g);  // the row is  -max c <= s, c = off - n.P  =>  grad h = +g

@@ -212,3 +212,25 @@ def episode_batch(B, seed=7):
         planes[b, pl.shape[0]:] = pl[-1]
         npl[b] = pl.shape[0]
     return xs, gps, np.tile(DEMO_CIRCLES, (B, 1, 1)), planes, npl
+
+
+def make_base_batch(B, N=10, seed=6, n_obs=3, dt=0.1):
+    """Instances of the base-only controller MPCBase (controllers/mpc_base.py), NATIVE layout:
+    x_init [B,6], x_ref [B,N+1,6], u_ref [B,N,2], circles [B,n_obs,3].  Start = a point of the straight-line plan from the
+    origin to (5, 5) plus bounded perturbations (as config 2, base part), window by calcLocalRefTraj semantics; circles: the
+    demo's three, or n_obs random ones as in config 3."""
+    rng = np.random.default_rng(seed)
+    x_start = np.zeros(6)
+    x_target = np.array([5.0, 5.0, -PI, 0, 0, 0])
+    ref = np.linspace(x_start, x_target, 51)
+    uref = np.zeros((50, 2))
+    i0 = rng.integers(0, 31, size=B)
+    x0 = ref[i0] + rng.uniform(-0.3, 0.3, size=(B, 6))
+    lim = np.array([[-100, -100, -np.inf, -2, -2, -PI], [100, 100, np.inf, 2, 2, PI]])
+    x0 = np.clip(x0, lim[0], lim[1])
+    d = np.linalg.norm(ref[None, :, :2] - x0[:, None, :2], axis=2)
+    j0 = np.argmin(d, axis=1)
+    rows = np.minimum(j0[:, None] + np.arange(N + 1)[None, :], 50)
+    urows = np.minimum(j0[:, None] + np.arange(N)[None, :], 49)
+    circ = np.tile(DEMO_CIRCLES, (B, 1, 1)) if n_obs == 3 else _random_circles(rng, x0[:, :2], n_obs)
+    return dict(N=N, dt=dt, n_obs=n_obs, x_init=x0, x_ref=ref[rows].copy(), u_ref=uref[urows].copy(), circles=circ)

@@ -221,6 +221,20 @@ static const double* circle_at(const Work* w, int k, int i) {
 
 static int is_fin(double v) { return v > -1e300 && v < 1e300; }
 
+/* angleDiff (controllers/mpc_base.py:59-84 = mpc_wholebody_qref.py:92-117): a - b folded to the nearest representative */
+static double angle_diff(double a, double b) {
+  const double PI = 3.14159265358979323846;
+  a = fmod(a + PI, 2 * PI) - PI; b = fmod(b + PI, 2 * PI) - PI;
+  double d = a - b;
+  if (a * b >= 0) return d;
+  if (a > b) return d <= PI ? d : d - 2 * PI;
+  return d > -PI ? d : d + 2 * PI;
+}
+/* state error of the cost: the yaw error of MPCBase goes through angleDiff (mpc_base.py:129-133, :146-150) */
+static double xerr(const MmpcConfig* c, int i, double x, double xr) {
+  return (i == 2 && c->model == MMPC_MODEL_BASE) ? angle_diff(x, xr) : x - xr;
+}
+
 static void build_rows(Work* w) {
   int N = w->N;
   for (int m = 0; m <= N; ++m) {
@@ -228,10 +242,11 @@ static void build_rows(Work* w) {
     for (int i = 0; i < w->nobs; ++i) r[n++] = (RowDesc){ROW_CIRCLE, i, 0};
     int term_on_prev = (w->mode == MMPC_MODE_REFERENCE); /* quirk 3, :263-265 */
     if (w->cfg->terminal_rows_on_sN) term_on_prev = 0; /* rows on s_N: the variant the GPU's reference mode solves */
+    const int nself = (w->cfg->model == MMPC_MODEL_BASE) ? 0 : 4; /* MPCBase has no arm (controllers/mpc_base.py) */
     if (m < N || !term_on_prev)
-      for (int i = 0; i < 4; ++i) r[n++] = (RowDesc){ROW_SELF, i, 0};
+      for (int i = 0; i < nself; ++i) r[n++] = (RowDesc){ROW_SELF, i, 0};
     if (m == N - 1 && term_on_prev)
-      for (int i = 0; i < 4; ++i) r[n++] = (RowDesc){ROW_SELF_NEXT, i, 0};
+      for (int i = 0; i < nself; ++i) r[n++] = (RowDesc){ROW_SELF_NEXT, i, 0};
     if (w->npl > 0) {
       for (int i = 0; i < 6; ++i) {
         if (w->mode == MMPC_MODE_REFERENCE && m >= 1) /* quirk 1 (:89 inside the j loop); k=0 rows vacuous (quirk 2) */
@@ -290,7 +305,7 @@ static double cost_eval(const Work* w, const double* x, const double* u, const d
   const MmpcConfig* c = w->cfg; int N = w->N; double J = 0;
   for (int k = 0; k <= N; ++k) {
     const double* Wx = (k < N) ? c->Qd : c->Pd;
-    for (int i = 0; i < NX; ++i) { double e = x[k * NX + i] - w->xref[k * NX + i]; J += Wx[i] * e * e; }
+    for (int i = 0; i < NX; ++i) { double e = xerr(c, i, x[k * NX + i], w->xref[k * NX + i]); J += Wx[i] * e * e; }
     if (k < N)
       for (int j = 0; j < NU; ++j) {
         double e = u[k * NU + j] - w->uref[k * NU + j], dl = u[k * NU + j] - w->ulast[k * NU + j];
@@ -388,7 +403,7 @@ static void evaluate(Work* w, double mu, KktParts* kp) {
     double* H = w->H + (size_t)k * NY * NY; double* g = w->g + k * NY; double* st = stat + k * NY;
     const double* Wx = (k < N) ? c->Qd : c->Pd;
     for (int i = 0; i < NX; ++i) {
-      double gr = 2 * Wx[i] * (XK(w, k)[i] - w->xref[k * NX + i]);
+      double gr = 2 * Wx[i] * xerr(w->cfg, i, XK(w, k)[i], w->xref[k * NX + i]);
       H[i * NY + i] += 2 * Wx[i]; g[i] += gr; st[i] += gr;
       if (k >= 1) {
         double lo = c->xlim[0][i], hi = c->xlim[1][i], v = XK(w, k)[i];
@@ -600,7 +615,7 @@ static void push_in(double* v, double lo, double hi) {
 #define ALLOC(p, n) p = calloc((size_t)(n), sizeof *(p))
 
 static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const double* x_ref, const double* u_ref,
-                     const double* u_last, const double* u_guess, const double* circles, const double* planes,
+                     const double* u_last, const double* u_guess, const double* x_guess, const double* circles, const double* planes,
                      unsigned flags, double* Uo, double* Xo, double* so, double* cost, double* kkt, int32_t* iters) {
   Work W, *w = &W; memset(w, 0, sizeof W);
   int N = cfg->N; const double dt = cfg->dt;
@@ -637,6 +652,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
   for (int k = 0; k <= N; ++k)
     for (int i = 0; i < NX; ++i) {
       double v = w->x0[i];
+      if (k >= 1 && x_guess) v = x_guess[k * NX + i]; /* MPCBase: X <- previous solution (mpc_base.py:196-201) */
       if (k >= 1) push_in(&v, cfg->xlim[0][i], cfg->xlim[1][i]);
       XK(w, k)[i] = v; w->zxl[k * NX + i] = 1; w->zxu[k * NX + i] = 1;
     }
@@ -662,7 +678,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     double gmax = 0;
     for (int k = 1; k <= N; ++k) {
       const double* Wx = (k < N) ? cfg->Qd : cfg->Pd;
-      for (int i = 0; i < NX; ++i) gmax = fmax(gmax, fabs(2 * Wx[i] * (XK(w, k)[i] - x_ref[k * NX + i])));
+      for (int i = 0; i < NX; ++i) gmax = fmax(gmax, fabs(2 * Wx[i] * xerr(cfg, i, XK(w, k)[i], x_ref[k * NX + i])));
     }
     for (int k = 0; k < N; ++k)
       for (int j = 0; j < NU; ++j)
@@ -709,7 +725,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
       const double* Wx = (k < N) ? c->Qd : c->Pd;
       for (int i = 0; i < NX; ++i) {
         double dxi = w->dx[k * NX + i];
-        gphi += 2 * Wx[i] * (XK(w, k)[i] - x_ref[k * NX + i]) * dxi;
+        gphi += 2 * Wx[i] * xerr(c, i, XK(w, k)[i], x_ref[k * NX + i]) * dxi;
         if (k >= 1) {
           double lo = c->xlim[0][i], hi = c->xlim[1][i], v = XK(w, k)[i];
           if (is_fin(lo)) { double d = v - lo, zz = w->zxl[k * NX + i]; double dz = mu / d - zz - zz / d * dxi; w->dzxl[k * NX + i] = dz;
@@ -837,6 +853,7 @@ int mmpc_oracle_solve(const MmpcConfig* cfg, int32_t B, const MmpcBatchIn* in, c
     int st = solve_one(cfg, npl, in->x_init + (size_t)b * NX, in->x_ref + (size_t)b * (N + 1) * NX,
                        in->u_ref + (size_t)b * N * NU, in->u_last + (size_t)b * N * NU,
                        in->u_guess ? in->u_guess + (size_t)b * N * NU : NULL,
+                       in->x_guess ? in->x_guess + (size_t)b * (N + 1) * NX : NULL,
                        in->circles ? in->circles + b * cs : NULL,
                        in->planes ? in->planes + (size_t)b * cfg->n_pl * 6 : NULL,
                        in->flags ? in->flags[b] : 0,

@@ -38,6 +38,12 @@ def config_from_batch(batch, mode=_abi.MODE_REFERENCE, **over):
     cfg.obs_per_stage = int(batch.get("obs_per_stage", 0))
     if "Qd" in batch:
         cfg.Qd[:] = list(batch["Qd"]); cfg.Pd[:] = list(batch.get("Pd", batch["Qd"]))
+    if "Rd" in batch:
+        cfg.Rd[:] = list(batch["Rd"])
+    if "Wd" in batch:
+        cfg.Wd[:] = list(batch["Wd"])
+    if "S" in batch:
+        cfg.S = float(batch["S"])
     for k, v in over.items():
         setattr(cfg, k, v)
     return cfg
@@ -53,8 +59,9 @@ def _solve_chunk(cfg, batch, lo, hi, u_guess):
     npl = None if npl is None else np.ascontiguousarray(npl[lo:hi], dtype=np.int32)
     flags = batch.get("flags")
     flags = None if flags is None else np.ascontiguousarray(flags[lo:hi], dtype=np.uint8)
+    xg = f(batch.get("x_guess"))
     bi = _abi.MmpcBatchIn(*[_abi.ptr(arrs[k]) for k in ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")],
-                          _abi.ptr(npl), _abi.ptr(flags))
+                          _abi.ptr(npl), _abi.ptr(flags), _abi.ptr(xg))
     out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
                kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])

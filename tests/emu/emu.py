@@ -52,7 +52,7 @@ def solve(batch, cfg, kernel="staged"):
     flags = batch.get("flags")
     flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
     bi = _abi.MmpcBatchIn(*[_abi.ptr(arrs[k]) for k in ("x_init", "x_ref", "u_ref", "u_last", "u_guess", "circles", "planes")],
-                          _abi.ptr(npl), _abi.ptr(flags))
+                          _abi.ptr(npl), _abi.ptr(flags), _abi.ptr(f(batch.get("x_guess"))))
     out = dict(U=np.zeros((B, N, 5)), X=np.zeros((B, N + 1, 9)), s=np.zeros((B, N + 1)), cost=np.zeros(B),
                kkt=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     bo = _abi.MmpcBatchOut(*[_abi.ptr(out[k]) for k in ("U", "X", "s", "cost", "kkt", "iters", "status")])

@@ -46,7 +46,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   P.cfg = *cfg; P.B = B;
   SIO io;
   io.x_init = in->x_init; io.x_ref = in->x_ref; io.u_ref = in->u_ref; io.u_last = in->u_last; io.u_guess = in->u_guess;
-  io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags;
+  io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags; io.x_guess = in->x_guess;
   io.U = out->U; io.X = out->X; io.s = out->s; io.cost = out->cost; io.kkt = out->kkt; io.iters = out->iters; io.status = out->status;
   io.B = B;
   P.io = &io;
@@ -63,7 +63,7 @@ extern "C" int mmpc_emu_staged_solve(const MmpcConfig* cfg, int32_t B, const Mmp
   for (int b = 0; b < B; ++b) { body_init(P, b); lists[P.LS + b] = b; }
   cnt[1] = B;
   const bool ref = cfg->mode == MMPC_MODE_REFERENCE;
-  if (ref) parts = 0;  // the part kernels implement the clean NLP only
+  if (ref || cfg->model != MMPC_MODEL_WHOLEBODY) parts = 0;  // the part kernels implement the clean whole-body NLP only
   int N = cfg->N, r = 0;
   for (;; ++r) {
     const int tcur = 1 + (r & 1), tnext = 1 + ((r + 1) & 1);

@@ -33,7 +33,7 @@ REF = os.environ.get("MMPC_REFERENCE", "/root/reference")
 sys.path[:0] = [os.path.join(ROOT, "tests", "refshim"), REF]
 
 sys.path.insert(0, HERE)
-from ref_points import random_points  # noqa: E402
+from ref_points import random_points, random_points_base, input_checksums  # noqa: E402
 import casadi as ca  # noqa: E402  (the stand-in)
 from controllers.mpc_wholebody_qref import MPCWholeBody  # noqa: E402  (reference, unmodified)
 from robot_models.mobile_manipulator import MobileManipulator  # noqa: E402
@@ -177,7 +177,63 @@ def make_model_values(M=1000, seed=11):
     print("model values: %d points" % M)
 
 
+def make_base_case(M_full=16, M_sum=512, seed=201, N=10):
+    """controllers/mpc_base.py::MPCBase.reset() (:114-189) on numbers: SURVEY.md 8(f) row 4."""
+    from controllers.mpc_base import MPCBase          # reference, unmodified
+    from robot_models.base import Base                # reference, unmodified
+    assert REF in sys.modules[MPCBase.__module__].__file__
+    rng = np.random.default_rng(seed)
+    M = M_full + M_sum
+    pts = random_points_base(rng, M, N)
+    Q = np.diag([5., 5., 3.0, 0.5, 0.25, 1.])           # a yaw weight, so that angleDiff (:129-133) shows in the cost
+    ca.Opti.FEED = dict(variable=[pts["X"], pts["U"], pts["s"]], parameter=[pts["X_init"], pts["X_ref"], pts["U_ref"]])
+    ctrl = MPCBase(Base(0.1), [Obstacles(*c) for c in DEMO_CIRCLES], N=N, Q=Q, P=2 * Q)
+    ca.Opti.FEED = None
+    it = iter(ctrl.opti.constraints)
+    s = pts["s"][:, :, 0]
+    vals, tags = [], []
+    bc = lambda a: np.broadcast_to(np.asarray(a), (M,) + np.asarray(a).shape[-2:]).reshape(M, -1)
+
+    def take(kind, k, n, op, i0=0):
+        c = next(it)
+        if op == "bounded":
+            assert c.op == "bounded" and c.mid.shape == (1, n), (c.op, c.mid.shape)
+            v = bc(c.mid.v)
+        else:
+            assert c.op == op and c.lhs.shape == (1, n), (c.op, c.lhs.shape)
+            v = bc(c.lhs.v - c.rhs.v)
+        ks = -1
+        if kind == T_CIRC:
+            rhs = bc(c.rhs.v)[:, 0]
+            (ks,) = [q for q in range(N + 1) if np.array_equal(rhs, s[:, q])]
+        for i in range(n):
+            vals.append(v[:, i]); tags.append((kind, k, i0 + i, -1, ks))
+
+    for k in range(N):
+        take(T_DYN, k, 6, "==")            # :128
+        take(T_BOXU, k, 2, "bounded")      # :139
+        take(T_BOXX, k, 2, "bounded")      # :140  x, y
+        take(T_BOXDU, k, 3, "bounded")     # :141  dx, dy, dpsi  (tag BOXDU reused for the velocity box)
+        for i in range(3):
+            take(T_CIRC, k, 1, "<=", i)    # :142-143
+    take(T_X0, 0, 6, "==")                 # :153
+    take(T_BOXX, N, 2, "bounded"); take(T_BOXDU, N, 3, "bounded")   # :154-155
+    for i in range(3):
+        take(T_CIRC, N, 1, "<=", i)        # :156-157
+    assert next(it, None) is None
+    vals = np.stack(vals, axis=1); tags = np.array(tags, np.int32)
+    cost = np.broadcast_to(ctrl.opti.objective.v, (M, 1, 1)).reshape(-1)
+    wts = rng.uniform(0.5, 1.5, size=vals.shape[1])
+    sums = np.stack([np.where(tags[:, 0] == t, wts, 0.0) @ vals[M_full:].T for t in range(8)], axis=1)
+    np.savez_compressed(os.path.join(HERE, "ref_rows_base.npz"), N=N, dt=0.1, circles=np.array(DEMO_CIRCLES, float), Qd=np.diag(Q), Pd=2 * np.diag(Q),
+                        tags=tags, weights=wts, M_full=M_full, M_sum=M_sum, seed=seed, rows_full=vals[:M_full], cost=cost, row_sums=sums,
+                        input_checksums=input_checksums(pts))
+    print("base     N=%d rows=%d (MPCBase, controllers/mpc_base.py)" % (N, vals.shape[1]))
+    return pts
+
+
 if __name__ == "__main__":
+    make_base_case()
     make_model_values()
     rng = np.random.default_rng(3)
     c16 = [tuple(r) for r in rng.uniform([0.5, 0.5, 0.1], [5.5, 5.5, 0.6], size=(16, 3))]

@@ -19,5 +19,15 @@ def random_points(rng, M, N, npl):
     return dict(X=X, U=U, s=s, free=free, U_last=U_last, X_init=X[:, 0:1, :].copy(), X_ref=X_ref, U_ref=U_ref)
 
 
+def random_points_base(rng, M, N):
+    """evaluation points of the MPCBase rows (6 states, 2 controls)"""
+    lo = np.array([-1, -1, -2 * PI, -2, -2, -PI]); hi = np.array([6, 6, 2 * PI, 2, 2, PI])
+    pts = dict(X=rng.uniform(lo, hi, size=(M, N + 1, 6)), U=rng.uniform([-2, -PI], [2, PI], size=(M, N, 2)),
+               s=rng.uniform(-0.1, 0.5, size=(M, N + 1, 1)), X_ref=rng.uniform(lo, hi, size=(M, N + 1, 6)),
+               U_ref=rng.uniform([-2, -PI], [2, PI], size=(M, N, 2)))
+    pts["X_init"] = pts["X"][:, 0:1, :].copy()
+    return pts
+
+
 def input_checksums(pts):
     return np.array([float(np.sum(pts[k] * np.cos(np.arange(pts[k].size).reshape(pts[k].shape)))) for k in sorted(pts)])

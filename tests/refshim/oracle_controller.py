@@ -24,3 +24,25 @@ class MPCWholeBody(dropin.MPCWholeBody):
                                        U=out["U"][0].copy(), cost=float(out["cost"][0]), status=int(out["status"][0]),
                                        iters=int(out["iters"][0])))
         return out
+
+
+def _weighted_cfg(ctrl):
+    cfg = _abi.MmpcConfig.from_buffer_copy(ctrl._cfg)
+    w = ctrl.weights
+    cfg.Qd[:] = list(w["Qd"]); cfg.Pd[:] = list(w["Pd"]); cfg.Rd[:] = list(w["Rd"]); cfg.Wd[:] = list(w["Wd"]); cfg.S = w["S"]
+    return cfg
+
+
+from mobile_manipulator_mpc_b200.controllers import mpc_base as dropin_base  # noqa: E402
+
+
+class MPCBase(dropin_base.MPCBase):
+    """the drop-in MPCBase with the CPU oracle as its solver; ``BACKEND`` may be replaced by the CPU
+    emulation of the kernel sources (tests/emu)"""
+    BACKEND = staticmethod(lambda b, cfg: osolver.solve(b, cfg=cfg, threads=4))
+
+    def _backend_solve(self, batch, B):
+        cfg = _weighted_cfg(self)
+        b = {k: (None if v is None else np.array(v)) for k, v in batch.items()}
+        b.update(N=cfg.N, dt=cfg.dt, n_obs=cfg.n_obs, n_pl=0)
+        return type(self).BACKEND(b, cfg)

@@ -172,3 +172,36 @@ def test_goldens_are_what_the_reference_code_produces_now():
         sys.path[:] = saved_path
         for k in set(sys.modules) - saved_mods:   # the stand-in `casadi` and the reference packages must not leak into other tests
             del sys.modules[k]
+
+
+def test_oracle_nlp_base_rows_match_reference_mpcbase_reset():
+    """oracle/nlp_base.py against the rows and the cost that the reference's own
+    controllers/mpc_base.py::MPCBase.reset() (:114-189) produced (tests/golden/ref_rows_base.npz): dynamics, boxes, circle rows
+    with their slack, and the cost with its angleDiff yaw error (a yaw weight is set so that it shows)."""
+    from ref_points import random_points_base
+    from oracle.nlp_base import NLPBase
+    g = np.load(os.path.join(GOLD, "ref_rows_base.npz"))
+    N, Mf, Ms = int(g["N"]), int(g["M_full"]), int(g["M_sum"])
+    tags, wts = g["tags"], g["weights"]
+    pts = random_points_base(np.random.default_rng(int(g["seed"])), Mf + Ms, N)
+    assert np.array_equal(input_checksums(pts), g["input_checksums"])
+    sums, scale = np.zeros((Ms, 8)), np.zeros((Ms, 8))
+    for m in range(Mf + Ms):
+        P = NLPBase(N, float(g["dt"]), pts["X"][m, 0], pts["X_ref"][m], pts["U_ref"][m], g["circles"], Qd=g["Qd"], Pd=g["Pd"])
+        X, U, s = pts["X"][m], pts["U"][m], pts["s"][m, :, 0]
+        w = P.pack(X, U, s)
+        e = P.eq(w).reshape(N, 6)
+        gi = P.ineq(w, with_boxes=False).reshape(N + 1, -1)
+        o = np.empty(len(tags))
+        for r, (t, k, i, j, ks) in enumerate(tags):
+            o[r] = {T_DYN: lambda: -e[k, i], T_X0: lambda: 0.0, T_BOXU: lambda: U[k, i], T_BOXX: lambda: X[k, i],
+                    T_BOXDU: lambda: X[k, 3 + i], T_CIRC: lambda: gi[k, i]}[t]()
+            assert t != T_CIRC or ks == k
+        assert close(P.cost(w), g["cost"][m], scale=abs(g["cost"][m])), m
+        if m < Mf:
+            assert close(o, g["rows_full"][m]).all(), m
+        else:
+            for t in range(8):
+                sel = tags[:, 0] == t
+                sums[m - Mf, t] = wts[sel] @ o[sel]; scale[m - Mf, t] = max(1.0, wts[sel] @ np.abs(o[sel]))
+    assert close(sums, g["row_sums"], scale=scale).all()
