@@ -16,13 +16,24 @@ def shard_bounds(B, world, rank):
     return lo, min(B, lo + per)
 
 
-def gather_results(dist, u0, status):
-    """all_gather of the applied controls u0 [B,5] and the per-instance status, rank-major."""
+def gather_results(dist, u0, status, B=None):
+    """all_gather of the applied controls u0 [b,5] and the per-instance status, rank-major.  With ``B`` (the global batch
+    size) the shards may be uneven, as shard_bounds produces them when B % world != 0: every rank pads its shard to the
+    common size ceil(B / world) for the collective and the padding is cut out of the result."""
     world = dist.get_world_size()
-    allu0 = torch.empty((world * u0.shape[0],) + tuple(u0.shape[1:]), dtype=u0.dtype, device=u0.device)
-    allst = torch.empty((world * status.shape[0],), dtype=status.dtype, device=status.device)
+    per = u0.shape[0] if B is None else (B + world - 1) // world
+    if u0.shape[0] < per:   # the last rank(s) of an uneven split
+        pad = per - u0.shape[0]
+        u0 = torch.cat([u0, u0.new_zeros((pad,) + tuple(u0.shape[1:]))])
+        status = torch.cat([status, status.new_full((pad,), -1)])
+    allu0 = torch.empty((world * per,) + tuple(u0.shape[1:]), dtype=u0.dtype, device=u0.device)
+    allst = torch.empty((world * per,), dtype=status.dtype, device=status.device)
     dist.all_gather_into_tensor(allu0, u0.contiguous())
     dist.all_gather_into_tensor(allst, status.contiguous())
+    if B is not None and world * per != B:
+        keep = torch.cat([torch.arange(r * per, r * per + (shard_bounds(B, world, r)[1] - shard_bounds(B, world, r)[0]))
+                          for r in range(world)]).to(allu0.device)
+        allu0, allst = allu0.index_select(0, keep), allst.index_select(0, keep)
     return allu0, allst
 
 

@@ -40,3 +40,31 @@ def test_gloo_world2_gather_order_and_stats():
         assert r[1].shape == (64, 5) and np.array_equal(r[1], x0[:, :5] * 2.0)   # rank-major order
         assert r[2].shape == (64,)
         assert r[3]["seconds_max"] == 0.2 and r[3]["converged_total"] == int((res[0][2] == 0).sum())
+
+
+def _worker_uneven(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mobile_manipulator_mpc_b200 import sharding
+    B = 33                                                   # strong scaling, B % world != 0: shards of 17 and 16
+    lo, hi = sharding.shard_bounds(B, world, rank)
+    idx = torch.arange(lo, hi, dtype=torch.float64)
+    u0 = idx[:, None] * torch.ones(1, 5, dtype=torch.float64)
+    status = torch.arange(lo, hi, dtype=torch.int32) % 3
+    allu0, allst = sharding.gather_results(dist, u0, status, B=B)
+    q.put((rank, allu0.numpy(), allst.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_of_uneven_shards():
+    world, port = 2, 29613
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_uneven, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in ps]
+    for _, u, st in res:
+        assert u.shape == (33, 5) and np.array_equal(u[:, 0], np.arange(33.0)) and np.array_equal(st, np.arange(33) % 3)
