@@ -596,7 +596,7 @@ def main():
                     help="reference = the reference's NLP to the letter (default); clean = the stage-separable variant")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU per step (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--contexts", type=int, default=4, help="concurrent solver contexts (streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=3, help="concurrent solver contexts (streams) per GPU")
     ap.add_argument("--cl-steps", type=int, default=500, help="config 4: closed-loop steps")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--ref-sample", type=int, default=2048)

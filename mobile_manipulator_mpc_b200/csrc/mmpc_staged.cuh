@@ -1837,7 +1837,14 @@ struct Inst {
     if (!ok || dom > 0.5) {
       const int lastf = (ok && dom > 0.5) ? 1 : 0;  // sufficient progress, but the filter said no
       const int nres = (fr >> 8) & 0xff;
-      if (lsn + 1 >= 50) {
+      // IPOPT's minimal step size (IpFilterLSAcceptor::CalculateAlphaMin): below it the line search is given up
+      double alpha_min = 1e-5;
+      if (gphi < 0) {
+        alpha_min = fmin(1e-5, 1e-8 * theta_k / (-gphi));
+        if (theta_k <= D(D_THMIN)) alpha_min = fmin(alpha_min, pow(theta_k, 1.1) / pow(-gphi, 2.3));
+      }
+      alpha_min *= 0.05;
+      if (lsn + 1 >= 50 || alpha * 0.5 <= alpha_min) {
         // IPOPT would enter its restoration phase here; in its place: clear the filter (while resets are left) and search again
         if (nres < MAX_FILTER_RESETS && nfilt > 0) {
           if (lane == 0) { J(J_NFILT) = 0; J(J_FRST) = ((nres + 1) << 8) | (lastf << 16); D(D_ALPHA) = ap0; J(J_LS) = 0; }

@@ -775,6 +775,13 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
       else cnt_frej = 0;
     }
     last_rej_filter = 0;
+    /* IPOPT's minimal step size (IpFilterLSAcceptor::CalculateAlphaMin): below it the line search is given up */
+    double alpha_min = 1e-5;
+    if (gphi < 0) {
+      alpha_min = fmin(1e-5, 1e-8 * theta_k / (-gphi));
+      if (theta_k <= theta_min) alpha_min = fmin(alpha_min, pow(theta_k, 1.1) / pow(-gphi, 2.3));
+    }
+    alpha_min *= 0.05;
     double alpha = ap; int accepted = 0, ftype = 0;
     for (int ls = 0; ls < 50; ++ls) {
       for (int i = 0; i < (N + 1) * NX; ++i) xt[i] = w->x[i] + alpha * w->dx[i];
@@ -797,6 +804,7 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
       if (ok && !dom) { accepted = 1; break; }
       last_rej_filter = ok && dom;
       alpha *= 0.5;
+      if (alpha <= alpha_min) ls = 49;   /* give up (or, below, clear the filter and search once more) */
       if (ls == 49 && n_freset < 5 && nfilt > 0) { nfilt = 0; n_freset++; cnt_frej = 0; alpha = ap; ls = -1; }  /* in place of IPOPT's restoration phase: clear the filter, search again */
     }
     if (accepted && !ftype) {
