@@ -80,15 +80,21 @@ enum {
 enum { MMPC_MODEL_WHOLEBODY = 0, MMPC_MODEL_BASE = 1 };
 
 /* execution strategy of mmpc_solve (same algorithm, same results to the bit):
- *   STAGED batch-synchronous rounds of phase kernels over compacted lists of active instances (stage-parallel
- *          evaluation / step / trial, 16-lane column-parallel Riccati), the whole solve one CUDA graph whose
- *          conditional WHILE nodes loop over the rounds on the device; the default (AUTO)
+ *   STAGED   batch-synchronous rounds of phase kernels over compacted lists of active instances (stage-parallel
+ *            evaluation / step / trial, 16-lane column-parallel Riccati), the whole solve one CUDA graph whose
+ *            conditional WHILE nodes loop over the rounds on the device: the throughput path, AUTO's choice for batches
+ *   RESIDENT the same phase bodies inside one persistent thread block per instance with the state in shared memory: the
+ *            latency path, AUTO's choice for small batches
  * The others are A/B references of single design decisions.  (Values 1 and 2 named two superseded kernels.) */
 enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_STAGED = 3,
        MMPC_KERNEL_STAGED_THREAD = 4,   /* STAGED with the one-thread-per-instance Riccati                         */
        MMPC_KERNEL_STAGED_UNFUSED = 5,  /* STAGED with separate eval and trial kernels (host loop)                 */
        MMPC_KERNEL_STAGED_FAT = 6,      /* STAGED with one thread per (instance, stage) item in the thin rounds too */
-       MMPC_KERNEL_STAGED_HOSTLOOP = 7  /* STAGED with the host sequencing the rounds instead of the CUDA graph    */ };
+       MMPC_KERNEL_STAGED_HOSTLOOP = 7, /* STAGED with the host sequencing the rounds instead of the CUDA graph    */
+       MMPC_KERNEL_RESIDENT = 8         /* one thread block per instance, the whole solver state of the instance in shared memory,
+                                           persistent blocks on an atomic work queue (csrc/mmpc_resident.cu): the latency path.
+                                           AUTO takes it for batches of at most one instance per SM when the state fits
+                                           (N = 20 with 16 circles: 131 KB); MMPC_ERR_UNSUPPORTED if it does not fit */ };
 
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */

@@ -12,7 +12,7 @@ from . import _abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMPC_LIB") or os.path.join(_PKG, "libmmpc_b200.so")  # MMPC_LIB: A/B builds of the same sources
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_parts.cuh", "mmpc_episode.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_resident.cu", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_parts.cuh", "mmpc_episode.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -29,7 +29,7 @@ def build_library(force=False, verbose=False):
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= src_time:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0], SOURCES[1]]   # two translation units: staged + resident
     subprocess.check_call(cmd, cwd=os.path.join(_PKG, "csrc"))
     return LIB_PATH
 

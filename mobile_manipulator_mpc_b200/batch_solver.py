@@ -49,11 +49,12 @@ class BatchSolver:
             self.set_kernel(kernel)
 
     def set_kernel(self, kernel):
-        """'auto' = 'staged' (phase kernels over active lists, one CUDA graph per solve) | A/B references:
+        """'auto' ('resident' for at most one instance per SM, else 'staged') | 'staged' (phase kernels over active lists, one
+        CUDA graph per solve) | 'resident' (one thread block per instance, state in shared memory) | A/B references:
         'staged_hostloop' (the host sequences the rounds), 'staged_thread', 'staged_unfused', 'staged_fat'."""
         k = {"auto": _abi.KERNEL_AUTO, "staged": _abi.KERNEL_STAGED, "staged_thread": _abi.KERNEL_STAGED_THREAD,
              "staged_unfused": _abi.KERNEL_STAGED_UNFUSED, "staged_fat": _abi.KERNEL_STAGED_FAT,
-             "staged_hostloop": _abi.KERNEL_STAGED_HOSTLOOP}.get(kernel, kernel)
+             "staged_hostloop": _abi.KERNEL_STAGED_HOSTLOOP, "resident": _abi.KERNEL_RESIDENT}.get(kernel, kernel)
         check(lib().mmpc_set_kernel(self._h, int(k)))
 
     # -- lifetime -----------------------------------------------------------------------------

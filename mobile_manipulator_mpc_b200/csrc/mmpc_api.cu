@@ -17,6 +17,10 @@
 
 using namespace mmpc;
 
+// csrc/mmpc_resident.cu (its own translation unit: the same phase bodies compiled for a shared-memory workspace)
+extern "C" int mmpc_resident_smem_bytes(const MmpcConfig* cfg);
+extern "C" int mmpc_resident_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream);
+
 struct MmpcHandle {
   MmpcConfig cfg;
   int device, B_max, sm_count;
@@ -28,6 +32,10 @@ struct MmpcHandle {
   // the solve as one CUDA graph (built for a batch size, rebuilt when B, the weights or the kernel selection change)
   struct { struct { cudaGraph_t graph; cudaGraphExec_t exec; int cap, classes; } e[4]; int next, pending_classes; bool pending; } gr;
   int hostloop;  // MMPC_KERNEL_STAGED_HOSTLOOP: the host sequences the rounds
+  int resident;  // MMPC_KERNEL_RESIDENT forced
+  int autosel;   // MMPC_KERNEL_AUTO: resident for small batches, staged otherwise
+  int smem_optin; // largest dynamic shared memory of a block on this device
+  unsigned* queue;  // work queue counter of the resident kernel
   // per-phase device timing of the staged solver (mmpc_set_profile / mmpc_phase_times)
   int profile;
   std::vector<cudaEvent_t>* prof_ev;
@@ -117,13 +125,13 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   MmpcHandle* h = new (std::nothrow) MmpcHandle();
   if (!h) return MMPC_ERR_ARG;
   memset(h, 0, sizeof *h);
-  h->cfg = *cfg; h->device = device; h->B_max = B_max; h->sm_count = prop.multiProcessorCount;
+  h->cfg = *cfg; h->device = device; h->B_max = B_max; h->sm_count = prop.multiProcessorCount; h->smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete h;
     return MMPC_ERR_CUDA;
   }
-  h->kernel = MMPC_KERNEL_AUTO; h->sg_team = 1; h->sg_fused = 1; h->sg_parts = 1;
+  h->kernel = MMPC_KERNEL_AUTO; h->sg_team = 1; h->sg_fused = 1; h->sg_parts = 1; h->autosel = 1;
   {
     int rc = set_kernel_attributes();  // per device (the trial kernels need 81 KB of dynamic shared memory)
     if (rc != MMPC_OK) { cudaStreamDestroy(h->stream); delete h; return rc; }
@@ -147,7 +155,7 @@ extern "C" int mmpc_destroy(MmpcHandle* h) {
   free_staging(h);
   if (h->prof_ev) { for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e); delete h->prof_ev; }
   graph_destroy(h);
-  for (void* q : {(void*)h->sg.ws, (void*)h->sg.qp, (void*)h->sg.rk, (void*)h->sg.gd, (void*)h->sg.gi, (void*)h->sg.lists, (void*)h->sg.cnt, (void*)h->sg.io})
+  for (void* q : {(void*)h->sg.ws, (void*)h->sg.qp, (void*)h->sg.rk, (void*)h->sg.gd, (void*)h->sg.gi, (void*)h->sg.lists, (void*)h->sg.cnt, (void*)h->sg.io, (void*)h->queue})
     if (q) cudaFree(q);
   if (h->sg.pin) cudaFreeHost(h->sg.pin);
   for (int i = 0; i < 8; ++i) if (h->sg.ev[i]) cudaEventDestroy(h->sg.ev[i]);
@@ -169,7 +177,10 @@ extern "C" int mmpc_set_weights(MmpcHandle* h, const double* Qd, const double* P
 }
 
 extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
-  if (!h || (kernel != MMPC_KERNEL_AUTO && (kernel < MMPC_KERNEL_STAGED || kernel > MMPC_KERNEL_STAGED_HOSTLOOP))) return MMPC_ERR_ARG;
+  if (!h || (kernel != MMPC_KERNEL_AUTO && (kernel < MMPC_KERNEL_STAGED || kernel > MMPC_KERNEL_RESIDENT))) return MMPC_ERR_ARG;
+  if (kernel == MMPC_KERNEL_RESIDENT && mmpc_resident_smem_bytes(&h->cfg) > h->smem_optin) return MMPC_ERR_UNSUPPORTED;
+  h->resident = kernel == MMPC_KERNEL_RESIDENT;
+  h->autosel = kernel == MMPC_KERNEL_AUTO;
   cudaSetDevice(h->device);
   graph_destroy(h);
   h->hostloop = kernel == MMPC_KERNEL_STAGED_HOSTLOOP;
@@ -236,6 +247,7 @@ static int ensure_workspace(MmpcHandle* h) {
   CK(cudaMalloc(&h->sg.lists, (size_t)4 * LS * sizeof(int)));   // E, two trial lists, the Riccati's ordering of E
   CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
   CK(cudaMalloc(&h->sg.io, sizeof(SIO)));
+  CK(cudaMalloc(&h->queue, sizeof(unsigned)));
   CK(cudaMallocHost(&h->sg.pin, (8 * 4 + 4) * sizeof(int)));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming | cudaEventBlockingSync));  // the host thread sleeps, it does not spin: several contexts per GPU and ranks per box share the cores
   h->sg.ready = true;
@@ -508,6 +520,17 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   io.B = B;
   staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io);
   CK(cudaGetLastError());
+  // the resident kernel: forced, or AUTO's choice for at most one instance per SM when the instance fits in shared memory
+  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 1;   // A/B: 0 = AUTO never takes it
+  const bool fits = mmpc_resident_smem_bytes(&h->cfg) <= h->smem_optin;
+  if (!h->profile && h->sg_fused && fits && (h->resident || (h->autosel && auto_resident && B <= h->sm_count))) {
+    CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned), st));
+    cudaError_t e = (cudaError_t)mmpc_resident_launch(&h->cfg, B, h->sg.io, h->queue, h->sm_count, st);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "resident kernel launch failed: %s", cudaGetErrorString(e)); return MMPC_ERR_CUDA; }
+    h->launches += 2;
+    h->sg.rounds = 0;
+    return MMPC_OK;
+  }
   static const bool force_hostloop = getenv("MMPC_HOSTLOOP") && atoi(getenv("MMPC_HOSTLOOP")) != 0;
   // (the unfused A/B variant evaluates in every round: host loop only)
   if (h->profile || force_hostloop || h->hostloop || !h->sg_fused) return launch_staged_hostloop(h, B, st);

@@ -41,6 +41,14 @@
 
 namespace mmpc {
 
+// log2 of the lane stride of the per-instance workspace: 32 instances interleaved in HBM (tile-major layout, see Inst), one
+// instance alone in shared memory in the resident build
+#ifdef MMPC_RESIDENT
+constexpr int LSH = 0;
+#else
+constexpr int LSH = 5;
+#endif
+
 // The caller's arrays of one mmpc_solve call (include/mmpc.h: MmpcBatchIn / MmpcBatchOut).  They live in a small block of
 // DEVICE memory that a one-thread kernel rewrites in front of every solve, so the kernel parameters -- and with them the
 // CUDA graph of the solve (mmpc_api.cu) -- do not change when the caller passes other buffers.  Only init() reads the
@@ -138,7 +146,8 @@ struct Inst {
   double* gd;  // this instance's lane in its tile of P.gd
   int* gi;     // this instance's lane in its tile of P.gi
   long long LS;
-  int N, R, STG, ITSZ, B2, nobs, npl, b;
+  int N, R, STG, ITSZ, B2, nobs, npl, b;   // b: index into the workspace
+  int bio;                                  // index into the caller's arrays (P.io); == b except in the resident build
   double dt;
   // Row ring (step and trial kernels): the inputs of the "row-like" items of a stage -- circle rows with their circle,
   // bound multipliers, self-collision and plane rows -- are streamed through a per-thread ring in shared memory
@@ -160,10 +169,18 @@ struct Inst {
     //   ws[((tile*(N+1) + k)*STG + f)*32 + lane]   gd[(tile*ND + f)*32 + lane]   gi[(tile*J_NFIELDS + f)*32 + lane]
     // so a warp of neighbouring instances reads one 256-byte line per field, consecutive fields are
     // consecutive lines (DRAM page locality), and the lane stride is a compile-time constant.
+#ifdef MMPC_RESIDENT
+    // resident build (mmpc_resident.cu): the workspace is ONE instance in shared memory, fields contiguous per stage; b_ only
+    // names the caller's arrays (bio)
+    b = 0; bio = b_;
+    w = p.ws; gd = p.gd; gi = p.gi;
+#else
+    bio = b_;
     const long long tile = b_ >> 5; const int ln = b_ & 31;
     w = p.ws + ((tile * (cfg.N + 1) * p.STG) << 5) + ln;
     gd = p.gd + ((tile * p.ND) << 5) + ln;
     gi = p.gi + ((tile * J_NFIELDS) << 5) + ln;
+#endif
     N = cfg.N; R = p.R; STG = p.STG; ITSZ = p.ITSZ; B2 = 2 * p.ITSZ; nobs = cfg.n_obs; dt = cfg.dt;
     npl = 0;
     MG = S_DT + R + (cfg.obs_per_stage ? 3 * nobs : 0);
@@ -175,15 +192,15 @@ struct Inst {
     return (i == 2 && cfg.model == MMPC_MODEL_BASE) ? angle_diff(x, xr) : x - xr;
   }
   int MG;  // offset (second block) of the plane-margin cache of a stage, see staged_marg_doubles
-  __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << 5]; }
-  __device__ __forceinline__ double& W2(int k, int o) const { return w[(k * STG + B2 + o) << 5]; }
-  // base pointer of a block of fields of stage k (field f of the block is p[f << 5]): with it the field offsets
+  __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << LSH]; }
+  __device__ __forceinline__ double& W2(int k, int o) const { return w[(k * STG + B2 + o) << LSH]; }
+  // base pointer of a block of fields of stage k (field f of the block is p[f << LSH]): with it the field offsets
   // of the hot kernels are compile-time immediates instead of an index computation per access
-  __device__ __forceinline__ double* stage_ptr(int k, int base) const { return w + ((k * STG + base) << 5); }
+  __device__ __forceinline__ double* stage_ptr(int k, int base) const { return w + ((k * STG + base) << LSH); }
   __device__ __forceinline__ double& Qw(int k, int o) const { return P.qp[((long long)k * LS + b) * QS + o]; }
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
-  __device__ __forceinline__ double& D(int o) const { return gd[o << 5]; }
-  __device__ __forceinline__ int& J(int o) const { return gi[o << 5]; }
+  __device__ __forceinline__ double& D(int o) const { return gd[o << LSH]; }
+  __device__ __forceinline__ int& J(int o) const { return gi[o << LSH]; }
   template <bool NC = true>
   __device__ __forceinline__ double circ(int k, int i, int c) const {  // read-only after init: non-coherent load
     const double* p = cfg.obs_per_stage ? &W2(k, S_DT + R + 3 * i + c) : &D(D_CIRC + 3 * i + c);
@@ -201,7 +218,7 @@ struct Inst {
   // plane data (point, normal) of this instance: written by init only, so the phase kernels read it non-coherently
   // (init itself, which has just written it, passes NC = false)
   template <bool NC = true>
-  __device__ __forceinline__ double PL(int o) const { return NC ? ldg(&gd[(D_PL + o) << 5]) : gd[(D_PL + o) << 5]; }
+  __device__ __forceinline__ double PL(int o) const { return NC ? ldg(&gd[(D_PL + o) << LSH]) : gd[(D_PL + o) << LSH]; }
   __device__ __forceinline__ bool term_eq(int k) const { return k == N && (J(J_FLAGS) & 1); }
   // L2 prefetch of every field of stage k this thread is going to read (current iterate, step, references,
   // rows): the loads further down then find their lines in L2 instead of paying a full HBM round trip
@@ -240,27 +257,27 @@ struct Inst {
   // guess (:302-304) + IPOPT bound push; s lifted so every row starts strictly feasible;
   // objective scaling.
   __device__ void init() {
-    const double* xref = P.io->x_ref + (long long)b * (N + 1) * NX;
-    const double* uref = P.io->u_ref + (long long)b * N * NU;
-    const double* ulast = P.io->u_last + (long long)b * N * NU;
-    npl = P.io->n_pl_inst ? ldg(P.io->n_pl_inst + b) : cfg.n_pl;
+    const double* xref = P.io->x_ref + (long long)bio * (N + 1) * NX;
+    const double* uref = P.io->u_ref + (long long)bio * N * NU;
+    const double* ulast = P.io->u_last + (long long)bio * N * NU;
+    npl = P.io->n_pl_inst ? ldg(P.io->n_pl_inst + bio) : cfg.n_pl;
     npl = npl < 0 ? 0 : (npl > cfg.n_pl ? cfg.n_pl : npl);  // a caller's value outside [0, n_pl] must not index past the plane tables
     J(J_NPL) = npl;
     for (int j = 0; j < cfg.n_pl; ++j)
-      for (int c = 0; c < 6; ++c) D(D_PL + 6 * j + c) = ldg(P.io->planes + ((long long)b * cfg.n_pl + j) * 6 + c);
+      for (int c = 0; c < 6; ++c) D(D_PL + 6 * j + c) = ldg(P.io->planes + ((long long)bio * cfg.n_pl + j) * 6 + c);
     if (!cfg.obs_per_stage)
-      for (int i = 0; i < 3 * nobs; ++i) D(D_CIRC + i) = ldg(P.io->circles + (long long)b * 3 * nobs + i);
+      for (int i = 0; i < 3 * nobs; ++i) D(D_CIRC + i) = ldg(P.io->circles + (long long)bio * 3 * nobs + i);
     double gmax = 0;
     const bool refmode = cfg.mode == MMPC_MODE_REFERENCE && npl > 1;
     double cprev[6][MMPC_MAX_PLANES], ccur[6][MMPC_MAX_PLANES];
     for (int k = 0; k <= N; ++k) {
       double x[NX];
       if (cfg.obs_per_stage)
-        for (int i = 0; i < 3 * nobs; ++i) W2(k, S_DT + R + i) = ldg(P.io->circles + ((long long)b * (N + 1) + k) * 3 * nobs + i);
+        for (int i = 0; i < 3 * nobs; ++i) W2(k, S_DT + R + i) = ldg(P.io->circles + ((long long)bio * (N + 1) + k) * 3 * nobs + i);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = fmax(fmin(ldg(P.io->x_init + (long long)b * NX + i), cfg.xlim[1][i]), cfg.xlim[0][i]);  // :290-291
-        if (k >= 1 && P.io->x_guess) v = ldg(P.io->x_guess + ((long long)b * (N + 1) + k) * NX + i);       // mpc_base.py:196-201
+        double v = fmax(fmin(ldg(P.io->x_init + (long long)bio * NX + i), cfg.xlim[1][i]), cfg.xlim[0][i]);  // :290-291
+        if (k >= 1 && P.io->x_guess) v = ldg(P.io->x_guess + ((long long)bio * (N + 1) + k) * NX + i);       // mpc_base.py:196-201
         if (k >= 1) v = push_in(v, cfg.xlim[0][i], cfg.xlim[1][i]);
         double xr = ldg(xref + k * NX + i);
         x[i] = v; W(k, I_X + i) = v; W(k, I_LAM + i) = 0; W2(k, IN_XREF + i) = xr;
@@ -274,7 +291,7 @@ struct Inst {
           double ul = ldg(ulast + k * NU + j), ur = ldg(uref + k * NU + j);
           double lo = fmax(cfg.ulim[0][j], ul + cfg.dulim[0][j]);  // mpc_wholebody_qref.py:203 and :205 merged
           double hi = fmin(cfg.ulim[1][j], ul + cfg.dulim[1][j]);
-          double v = P.io->u_guess ? ldg(P.io->u_guess + ((long long)b * N + k) * NU + j) : ul;
+          double v = P.io->u_guess ? ldg(P.io->u_guess + ((long long)bio * N + k) * NU + j) : ul;
           v = push_in(v, lo, hi);
           W(k, I_U + j) = v; W2(k, IN_UREF + j) = ur; W2(k, IN_ULAST + j) = ul; W2(k, IN_ULO + j) = lo; W2(k, IN_UHI + j) = hi;
           W(k, I_ZUL + j) = 1; W(k, I_ZUU + j) = 1;
@@ -330,7 +347,7 @@ struct Inst {
     D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
     D(D_MU) = cfg.mu_init; D(D_REGLAST) = 0; D(D_THMAX) = -1; D(D_THMIN) = -1; D(D_E0) = 1e300;
     J(J_STATE) = ST_ACTIVE; J(J_IT) = 0; J(J_NFILT) = 0; J(J_LS) = 0; J(J_CUR) = 0; J(J_FRST) = 0; J(J_REGF) = 0;
-    J(J_FLAGS) = P.io->flags ? (int)P.io->flags[b] : 0;
+    J(J_FLAGS) = P.io->flags ? (int)P.io->flags[bio] : 0;
   }
 
   struct RowAcc {
@@ -1089,23 +1106,23 @@ struct Inst {
       for (int i = 0; i < NX; ++i) {
         double v = W(k, it + I_X + i), e = xerr(i, v, W2(k, IN_XREF + i));
         fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
-        if (P.io->X) P.io->X[((long long)b * (N + 1) + k) * NX + i] = v;
+        if (P.io->X) P.io->X[((long long)bio * (N + 1) + k) * NX + i] = v;
       }
       if (k < N)
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           double v = W(k, it + I_U + j), e = v - W2(k, IN_UREF + j), dl = v - W2(k, IN_ULAST + j);
           fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
-          P.io->U[((long long)b * N + k) * NU + j] = v;
+          P.io->U[((long long)bio * N + k) * NU + j] = v;
         }
       double s = W(k, it + I_S);
       fsum += cfg.S * s * s;
-      if (P.io->s) P.io->s[(long long)b * (N + 1) + k] = s;
+      if (P.io->s) P.io->s[(long long)bio * (N + 1) + k] = s;
     }
-    if (P.io->cost) P.io->cost[b] = fsum;
-    if (P.io->kkt) P.io->kkt[b] = D(D_E0);
-    if (P.io->iters) P.io->iters[b] = J(J_IT);
-    P.io->status[b] = status;
+    if (P.io->cost) P.io->cost[bio] = fsum;
+    if (P.io->kkt) P.io->kkt[bio] = D(D_E0);
+    if (P.io->iters) P.io->iters[bio] = J(J_IT);
+    P.io->status[bio] = status;
     J(J_STATE) = ST_DONE;
   }
 
@@ -1166,7 +1183,7 @@ struct Inst {
         const int r = q - q_circ;
         const int oa = isbox ? (q < NX ? I_ZXL + q : I_ZXU + q) : I_T + r;          // I_ZUL + (q - NX) = I_ZXU + q
         const int ob = isbox ? (q < NX ? I_ZXU + q : I_ZUU - NX + q) : I_T + R + r;
-        async_copy8(d, &ci[oa << 5]); async_copy8(d + bs, &ci[ob << 5]);
+        async_copy8(d, &ci[oa << LSH]); async_copy8(d + bs, &ci[ob << LSH]);
         if (!isbox && q < q_rows) { async_copy8(d + 2 * bs, circ_ptr(k, r, 0)); async_copy8(d + 3 * bs, circ_ptr(k, r, 1)); async_copy8(d + 4 * bs, circ_ptr(k, r, 2)); }
       }
       async_commit();
@@ -1183,10 +1200,10 @@ struct Inst {
     LogProd lp; lp.init();
     double x[NX], dxv[NX], u[NU], duv[NU];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = ldg(&ci[(I_X + i) << 5]); dxv[i] = ldg(&c2[(S_DX + i) << 5]); }
-    double s = ldg(&ci[(I_S) << 5]), dsv = ldg(&c2[(S_DS) << 5]);
+    for (int i = 0; i < NX; ++i) { x[i] = ldg(&ci[(I_X + i) << LSH]); dxv[i] = ldg(&c2[(S_DX + i) << LSH]); }
+    double s = ldg(&ci[(I_S) << LSH]), dsv = ldg(&c2[(S_DS) << LSH]);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? ldg(&ci[(I_U + a) << 5]) : 0.0; duv[a] = (k < N) ? ldg(&c2[(S_DU + a) << 5]) : 0.0; }
+    for (int a = 0; a < NU; ++a) { u[a] = (k < N) ? ldg(&ci[(I_U + a) << LSH]) : 0.0; duv[a] = (k < N) ? ldg(&c2[(S_DU + a) << LSH]) : 0.0; }
     double dp[NP];
 #pragma unroll
     for (int a = 0; a < NP; ++a) dp[a] = dxv[POSE2X[a]];
@@ -1194,7 +1211,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], ldg(&c2[(IN_XREF + i) << 5]));
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], ldg(&c2[(IN_XREF + i) << LSH]));
       fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -1219,9 +1236,9 @@ struct Inst {
       const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
       if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - ldg(&c2[(IN_UREF + j) << 5]), dl = u[j] - ldg(&c2[(IN_ULAST + j) << 5]);
+        double e = u[j] - ldg(&c2[(IN_UREF + j) << LSH]), dl = u[j] - ldg(&c2[(IN_ULAST + j) << LSH]);
         fsum += Rj * e * e + Wj * dl * dl; gphi += (2 * Rj * e + 2 * Wj * dl) * duv[j];
-        double lo = ldg(&c2[(IN_ULO + j) << 5]), hi = ldg(&c2[(IN_UHI + j) << 5]);
+        double lo = ldg(&c2[(IN_ULO + j) << LSH]), hi = ldg(&c2[(IN_UHI + j) << LSH]);
         if (is_fin(lo)) {
           double d = u[j] - lo, id = rcp(d), z = zl_c, dz = mu * id - z - z * id * duv[j];
           gphi -= mu * duv[j] * id; lp.mul(d);
@@ -1238,18 +1255,18 @@ struct Inst {
     }
     if (k < N) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) theta += fabs(ldg(&c2[(S_DFC + i) << 5]));
+      for (int i = 0; i < NX; ++i) theta += fabs(ldg(&c2[(S_DFC + i) << LSH]));
     }
-    if (term_eq(k)) theta += fabs(x[0] - ldg(&c2[(IN_XREF + 0) << 5])) + fabs(x[1] - ldg(&c2[(IN_XREF + 1) << 5]));
-    FK f; f.cp = ldg(&c2[(S_FK + 0) << 5]); f.sp = ldg(&c2[(S_FK + 1) << 5]);
+    if (term_eq(k)) theta += fabs(x[0] - ldg(&c2[(IN_XREF + 0) << LSH])) + fabs(x[1] - ldg(&c2[(IN_XREF + 1) << LSH]));
+    FK f; f.cp = ldg(&c2[(S_FK + 0) << LSH]); f.sp = ldg(&c2[(S_FK + 1) << LSH]);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { f.vr[q] = ldg(&c2[(S_FK + 2 + q) << 5]); f.vh[q] = ldg(&c2[(S_FK + 5 + q) << 5]); }
+    for (int q = 0; q < 3; ++q) { f.vr[q] = ldg(&c2[(S_FK + 2 + q) << LSH]); f.vh[q] = ldg(&c2[(S_FK + 5 + q) << LSH]); }
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
     double s_cur = s, ds_cur = dsv;  // slack (and its step) the rows are bounded by
     auto row_step = [&](int r, double h, double gd_, double t, double z) {
       double res = h - s_cur + t;
       double dtv = -res - (gd_ - ds_cur);
-      c2[(S_DT + r) << 5] = dtv;
+      c2[(S_DT + r) << LSH] = dtv;
       double itv = rcp(t), dz = (mu - z * (t + dtv)) * itv;
       theta += fabs(res); gphi -= mu * dtv * itv; lp.mul(t);
       if (dtv < 0) rp.add(t, -dtv);
@@ -1297,8 +1314,8 @@ struct Inst {
       stale_rows<2>(k, Adummy, bvdummy, io);
       theta += io.theta; gphi += io.gphi; log_extra = io.logsum; rp = io.rp; rd = io.rd;
     }
-    c2[(S_PART + 0) << 5] = rp.value(tau); c2[(S_PART + 1) << 5] = rd.value(tau); c2[(S_PART + 2) << 5] = gphi; c2[(S_PART + 3) << 5] = theta;
-    c2[(S_PART + 4) << 5] = fsum; c2[(S_PART + 5) << 5] = lp.value() + log_extra;
+    c2[(S_PART + 0) << LSH] = rp.value(tau); c2[(S_PART + 1) << LSH] = rd.value(tau); c2[(S_PART + 2) << LSH] = gphi; c2[(S_PART + 3) << LSH] = theta;
+    c2[(S_PART + 4) << LSH] = fsum; c2[(S_PART + 5) << LSH] = lp.value() + log_extra;
     async_wait<0>();  // nothing of this item's ring may still be in flight when the thread primes the next one
   }
 
@@ -1311,18 +1328,18 @@ struct Inst {
     for (int i = 0; i < NX; ++i) {
       double v = W(k, it + I_X + i), e = xerr(i, v, W2(k, IN_XREF + i));
       fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
-      if (P.io->X) P.io->X[((long long)b * (N + 1) + k) * NX + i] = v;
+      if (P.io->X) P.io->X[((long long)bio * (N + 1) + k) * NX + i] = v;
     }
     if (k < N)
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
         double v = W(k, it + I_U + j), e = v - W2(k, IN_UREF + j), dl = v - W2(k, IN_ULAST + j);
         fsum += cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl;
-        P.io->U[((long long)b * N + k) * NU + j] = v;
+        P.io->U[((long long)bio * N + k) * NU + j] = v;
       }
     double s = W(k, it + I_S);
     fsum += cfg.S * s * s;
-    if (P.io->s) P.io->s[(long long)b * (N + 1) + k] = s;
+    if (P.io->s) P.io->s[(long long)bio * (N + 1) + k] = s;
     W2(k, S_PART + 0) = fsum;
   }
 
@@ -1338,10 +1355,10 @@ struct Inst {
       for (int k = lane; k <= N; k += NL) fsum += W2(k, S_PART + 0);
       fsum = lanes_sum<NL>(fsum);
       if (lane == 0) {
-        if (P.io->cost) P.io->cost[b] = fsum;
-        if (P.io->kkt) P.io->kkt[b] = D(D_E0);
-        if (P.io->iters) P.io->iters[b] = J(J_IT);
-        P.io->status[b] = J(J_STATUS);
+        if (P.io->cost) P.io->cost[bio] = fsum;
+        if (P.io->kkt) P.io->kkt[bio] = D(D_E0);
+        if (P.io->iters) P.io->iters[bio] = J(J_IT);
+        P.io->status[bio] = J(J_STATUS);
         J(J_STATE) = ST_DONE;
       }
       return false;
@@ -1500,17 +1517,17 @@ struct Inst {
     // LDS at the sites that use them: each of those sites exposed a full HBM round trip (the compiler does not hoist them)
     double* zb = sm + (RING_DT * RING_W) * bs;
 #pragma unroll 1
-    for (int f = 0; f < I_T - I_ZXL; ++f) async_copy8(zb + f * bs, &ci[(I_ZXL + f) << 5]);
+    for (int f = 0; f < I_T - I_ZXL; ++f) async_copy8(zb + f * bs, &ci[(I_ZXL + f) << LSH]);
     // ... and so are the 29 reference / bound inputs of the stage (fields IN_XREF .. S_DT of the second block)
     double* rb_in = zb + (I_T - I_ZXL) * bs;
 #pragma unroll 1
-    for (int f = 0; f < S_DT - IN_XREF; ++f) async_copy8(rb_in + f * bs, &c2[(IN_XREF + f) << 5]);
+    for (int f = 0; f < S_DT - IN_XREF; ++f) async_copy8(rb_in + f * bs, &c2[(IN_XREF + f) << LSH]);
     async_commit();
     const int q_end = nobs + nself + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
     auto ring_issue = [&](int q) {
       if (q < q_end) {
         double* d = sm + ((q & (RING_DT - 1)) * RING_W) * bs;
-        async_copy8(d, &ci[(I_T + q) << 5]); async_copy8(d + bs, &ci[(I_T + R + q) << 5]); async_copy8(d + 2 * bs, &c2[(S_DT + q) << 5]);
+        async_copy8(d, &ci[(I_T + q) << LSH]); async_copy8(d + bs, &ci[(I_T + R + q) << LSH]); async_copy8(d + 2 * bs, &c2[(S_DT + q) << LSH]);
         if (q < nobs) { async_copy8(d + 3 * bs, circ_ptr(k, q, 0)); async_copy8(d + 4 * bs, circ_ptr(k, q, 1)); async_copy8(d + 5 * bs, circ_ptr(k, q, 2)); }
       }
       async_commit();
@@ -1528,32 +1545,32 @@ struct Inst {
     double x[NX], u[NU], lam[NX], lam1[NX], xo[NX], dxo[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      xo[i] = ldg(&ci[(I_X + i) << 5]); dxo[i] = ldg(&c2[(S_DX + i) << 5]);
+      xo[i] = ldg(&ci[(I_X + i) << LSH]); dxo[i] = ldg(&c2[(S_DX + i) << LSH]);
       x[i] = fma(alpha, dxo[i], xo[i]);
-      cj[(I_X + i) << 5] = x[i];
+      cj[(I_X + i) << LSH] = x[i];
       lam[i] = 0;
       if (k >= 1) {
-        double l = ldg(&ci[(I_LAM + i) << 5]);
-        lam[i] = l + alpha * (ldg(&c2[(S_LAMN + i) << 5]) - l);
-        cj[(I_LAM + i) << 5] = lam[i];
+        double l = ldg(&ci[(I_LAM + i) << LSH]);
+        lam[i] = l + alpha * (ldg(&c2[(S_LAMN + i) << LSH]) - l);
+        cj[(I_LAM + i) << LSH] = lam[i];
       }
     }
-    const double s = fma(alpha, ldg(&c2[(S_DS) << 5]), ldg(&ci[(I_S) << 5]));
-    cj[(I_S) << 5] = s;
+    const double s = fma(alpha, ldg(&c2[(S_DS) << LSH]), ldg(&ci[(I_S) << LSH]));
+    cj[(I_S) << LSH] = s;
     double uo[NU], duo[NU];
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
-      uo[j] = (k < N) ? ldg(&ci[(I_U + j) << 5]) : 0.0; duo[j] = (k < N) ? ldg(&c2[(S_DU + j) << 5]) : 0.0;
+      uo[j] = (k < N) ? ldg(&ci[(I_U + j) << LSH]) : 0.0; duo[j] = (k < N) ? ldg(&c2[(S_DU + j) << LSH]) : 0.0;
       u[j] = fma(alpha, duo[j], uo[j]);
-      if (k < N) cj[(I_U + j) << 5] = u[j];
+      if (k < N) cj[(I_U + j) << LSH] = u[j];
     }
     FK f;
     if (REF) load_fk(k, f);  // the pose kernel has just evaluated the candidate's forward kinematics
     else {
       fk_eval(x[2], x[6], x[7], x[8], f);
-      c2[(S_FK + 0) << 5] = f.cp; c2[(S_FK + 1) << 5] = f.sp;
+      c2[(S_FK + 0) << LSH] = f.cp; c2[(S_FK + 1) << LSH] = f.sp;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) { c2[(S_FK + 2 + q) << 5] = f.vr[q]; c2[(S_FK + 5 + q) << 5] = f.vh[q]; }
+      for (int q = 0; q < 3; ++q) { c2[(S_FK + 2 + q) << LSH] = f.vr[q]; c2[(S_FK + 5 + q) << LSH] = f.vh[q]; }
     }
     double es = 0, hpp = 0, sum_lam = 0;
     int n_eq = 0;
@@ -1568,11 +1585,11 @@ struct Inst {
       dyn_f(x, u, dt, f.cp, f.sp, xn);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double l1 = ldg(&ni[(I_LAM + i) << 5]);
-        lam1[i] = l1 + alpha * (ldg(&n2[(S_LAMN + i) << 5]) - l1);
-        double x1 = fma(alpha, ldg(&n2[(S_DX + i) << 5]), ldg(&ni[(I_X + i) << 5]));
+        double l1 = ldg(&ni[(I_LAM + i) << LSH]);
+        lam1[i] = l1 + alpha * (ldg(&n2[(S_LAMN + i) << LSH]) - l1);
+        double x1 = fma(alpha, ldg(&n2[(S_DX + i) << LSH]), ldg(&ni[(I_X + i) << LSH]));
         double d = xn[i] - x1;
-        c2[(S_DFC + i) << 5] = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
+        c2[(S_DFC + i) << LSH] = d; A.prim = fmax(A.prim, fabs(d)); sum_lam += fabs(lam1[i]);
         theta += fabs(d);
       }
       n_eq = NX;
@@ -1675,7 +1692,7 @@ struct Inst {
       double dz = (mu - z * (t + dtv)) * rcp(t);
       it_ = rcp(tt);
       z = zclamp(z + ad * dz, mu, it_);
-      cj[(I_T + r) << 5] = tt; cj[(I_T + R + r) << 5] = z;
+      cj[(I_T + r) << LSH] = tt; cj[(I_T + R + r) << LSH] = z;
       res = h - s_cur + tt;
       theta += fabs(res);
       if (tt <= 0) ok = false; else lp.mul(tt);
@@ -1792,11 +1809,11 @@ struct Inst {
       if (k == N) { W2(N, S_DFC + 0) = q3_z; es = fmax(es, fabs(S2 * s - A.zrows)); }
       else W2(N, S_DFC + 1) = S2 * s - A.zrows;
     } else es = fmax(es, fabs(S2 * s - A.zrows));
-    c2[(S_PART + 0) << 5] = es; c2[(S_PART + 1) << 5] = A.prim; c2[(S_PART + 2) << 5] = A.chi; c2[(S_PART + 3) << 5] = A.clo;
-    c2[(S_PART + 4) << 5] = sum_lam; c2[(S_PART + 5) << 5] = A.sumz; c2[(S_PART + 6) << 5] = (double)A.nz; c2[(S_PART + 7) << 5] = (double)n_eq;
+    c2[(S_PART + 0) << LSH] = es; c2[(S_PART + 1) << LSH] = A.prim; c2[(S_PART + 2) << LSH] = A.chi; c2[(S_PART + 3) << LSH] = A.clo;
+    c2[(S_PART + 4) << LSH] = sum_lam; c2[(S_PART + 5) << LSH] = A.sumz; c2[(S_PART + 6) << LSH] = (double)A.nz; c2[(S_PART + 7) << LSH] = (double)n_eq;
     bool fin = ok && (fsum == fsum) && (theta == theta);
-    c2[(S_PART + PT_MERIT + 0) << 5] = theta; c2[(S_PART + PT_MERIT + 1) << 5] = fsum; c2[(S_PART + PT_MERIT + 2) << 5] = fin ? lp.value() + log_extra : 0.0;
-    c2[(S_PART + PT_MERIT + 3) << 5] = fin ? 1.0 : 0.0;
+    c2[(S_PART + PT_MERIT + 0) << LSH] = theta; c2[(S_PART + PT_MERIT + 1) << LSH] = fsum; c2[(S_PART + PT_MERIT + 2) << LSH] = fin ? lp.value() + log_extra : 0.0;
+    c2[(S_PART + PT_MERIT + 3) << LSH] = fin ? 1.0 : 0.0;
     async_wait<0>();  // nothing of this item's ring may still be in flight when the thread primes the next one
   }
 
@@ -1929,7 +1946,7 @@ inline void compact_list(const SParams& P, int dst, int src, int want) {
   P.cnt[dst] = n;
   if (dst == 0) for (int i = 0; i < n; ++i) list_S(P)[i] = out[i];  // (the order of the Riccati's list does not change any result)
 }
-#else
+#elif !defined(MMPC_RESIDENT)   // (the resident build has its own single kernel, mmpc_resident.cu)
 // Ordered compaction  list dst <- { b in list src : state(b) == want }  by one block of 1024 threads: warp w
 // scans a contiguous chunk of the source list 32 entries at a time (coalesced), counts with ballots, the warp
 // totals are scanned through shared memory, and the second pass writes the survivors in order.  Every

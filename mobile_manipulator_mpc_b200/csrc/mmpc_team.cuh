@@ -375,7 +375,7 @@ struct Team {
 #pragma unroll
         for (int j = 0; j < NX; ++j) mine = fma(r0[R_K + c * NX + j], dxv[j], mine);
         if (q3 && k == N - 1) mine = fma(S.Rw(N, R_K + c), ds_in, mine);  // u[N-1] also answers to ds[N-1] (terminal rows)
-        w2k[(S_DU + c) << 5] = mine;
+        w2k[(S_DU + c) << LSH] = mine;
       }
       double duv[NU];
 #pragma unroll
@@ -399,7 +399,7 @@ struct Team {
         double mx = 0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) mx = (i == c) ? dxv[i] : mx;
-        w2n[(S_DX + c) << 5] = mx;
+        w2n[(S_DX + c) << LSH] = mx;
         double v = r1[R_PV + c];
 #pragma unroll
         for (int j = 0; j < NX; ++j) v = fma(r1[R_P + (c <= j ? c * 9 - c * (c - 1) / 2 + (j - c) : j * 9 - j * (j - 1) / 2 + (c - j))], dxv[j], v);
@@ -409,9 +409,9 @@ struct Team {
           if (c >= 6) v = fma(r1[RO_A + (c - 3)], dsv, v);
         }
         if (q3 && k + 1 == N && (c < 3 || c >= 6)) v = fma(S.Qw(N, Q_BV + (c < 3 ? c : c - 3)), ds_in, v);  // abar ds[N-1]
-        w2n[(S_LAMN + c) << 5] = v;
+        w2n[(S_LAMN + c) << LSH] = v;
       }
-      if (c == 14) w2n[S_DS << 5] = dsv;
+      if (c == 14) w2n[S_DS << LSH] = dsv;
       team_sync();  // slot k & 3 is free
       ro_issue(k + 4, it);
     }
@@ -493,7 +493,7 @@ __device__ inline void body_solve_team(const SParams& P, int j, int c, double* s
   T.template solve<Q3>();
 }
 
-#if !defined(MMPC_EMULATE) && !defined(MMPC_EMULATE_LANE)
+#if !defined(MMPC_EMULATE_LANE) && !defined(MMPC_RESIDENT)
 // threads per block of the team kernel, 16 lanes per instance.  A/B on B200 (solve phase of a 65,536 batch): 128 -> 162.5 ms,
 // 64 -> 155.5 ms, 32 -> 153.3 ms: a block leaves when its slowest warp (most delta_w retries) does, smaller blocks free their
 // registers sooner

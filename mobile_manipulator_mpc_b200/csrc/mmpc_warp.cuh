@@ -27,20 +27,35 @@ __device__ __forceinline__ unsigned next_instance(unsigned* counter) {
   return __shfl_sync(FULL, v, 0);
 }
 __device__ __forceinline__ unsigned lane_next_instance(unsigned* counter) { return atomicAdd(counter, 1u); }
+#ifdef MMPC_RESIDENT
+__device__ __forceinline__ double ldg(const double* p) { return *p; }   // may point into shared memory: generic load
+__device__ __forceinline__ int ldg(const int* p) { return *p; }
+#else
 __device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
 __device__ __forceinline__ int ldg(const int* p) { return __ldg(p); }
+#endif
 // teams: the two 16-lane halves of a warp run in lock step (full-warp mask, width-16 shuffles): half-warp
 // masks make the hardware issue every shuffle once per team (measured: 17.5 of 32 lanes active)
 __device__ __forceinline__ double shfl16(double v, int src) { return __shfl_sync(FULL, v, src, 16); }
 __device__ __forceinline__ double shfl16_xor(double v, int m) { return __shfl_xor_sync(FULL, v, m, 16); }
 __device__ __forceinline__ void team_sync() { __syncwarp(); }
 __device__ __forceinline__ bool warp_all(bool p) { return __all_sync(FULL, p); }
+#ifdef MMPC_RESIDENT
+// resident build (mmpc_resident.cu): the workspace the phase bodies read IS shared memory, so the staging rings are filled
+// by plain copies (cp.async needs a global source) and there is nothing to wait for
+__device__ __forceinline__ void async_copy8(double* smem_dst, const double* src) { smem_dst[0] = src[0]; }
+__device__ __forceinline__ void async_copy16(double* smem_dst, const double* src) { smem_dst[0] = src[0]; smem_dst[1] = src[1]; }
+__device__ __forceinline__ void async_commit() {}
+template <int PENDING> __device__ __forceinline__ void async_wait() {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 // cp.async: global -> shared without passing through registers (LDGSTS), grouped per commit
 __device__ __forceinline__ void async_copy8(double* smem_dst, const double* src) { __pipeline_memcpy_async(smem_dst, src, 8); }
 __device__ __forceinline__ void async_copy16(double* smem_dst, const double* src) { __pipeline_memcpy_async(smem_dst, src, 16); }
 __device__ __forceinline__ void async_commit() { __pipeline_commit(); }
 template <int PENDING> __device__ __forceinline__ void async_wait() { __pipeline_wait_prior(PENDING); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 // compiler-only fence: memory operations are not moved across it (no instruction is emitted)
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 }  // namespace mmpc
