@@ -29,8 +29,15 @@ def build_library(force=False, verbose=False):
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= src_time:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0], SOURCES[1]]   # two translation units: staged + resident
-    subprocess.check_call(cmd, cwd=os.path.join(_PKG, "csrc"))
+    extra = os.environ.get("MMPC_NVCC_EXTRA", "").split()   # A/B builds: -D switches
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + extra
+    # two translation units (staged + resident), compiled side by side, then linked
+    objs = [LIB_PATH + "." + os.path.basename(s)[:-3] + ".o" for s in SOURCES[:2]]
+    procs = [subprocess.Popen([nvcc] + flags + ["-c", "-o", o, s], cwd=os.path.join(_PKG, "csrc")) for o, s in zip(objs, SOURCES[:2])]
+    for pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, pr.args)
+    subprocess.check_call([nvcc] + NVCC_FLAGS[:2] + ["-shared", "-o", LIB_PATH] + objs, cwd=os.path.join(_PKG, "csrc"))
     return LIB_PATH
 
 

@@ -27,11 +27,49 @@ using namespace mmpc_res;
 
 namespace mmpc_res {
 
+// ---- TMA (1-D bulk copy) + mbarrier: the instance's inputs come into shared memory by cp.async.bulk, issued by one thread ----
+__device__ __forceinline__ unsigned sptr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy accesses of shared memory before, async-proxy (bulk copy) writes after
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sptr(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(sptr(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// A caller's array holds n doubles per instance, so an instance's slice starts on an 8-byte boundary and a bulk copy wants 16:
+// element i of the slice goes to region[off + i] with off = 1 when the slice starts on an odd double -- then the 16-byte
+// aligned middle of the slice lands 16-byte aligned in the (16-byte aligned) region and goes by ONE bulk copy; the odd
+// double in front and / or behind it goes by a plain copy of the issuing thread (released by its mbarrier arrive).
+__device__ __forceinline__ int slice_off(const double* src) { return (int)(((unsigned long long)src >> 3) & 1ull); }
+__device__ __forceinline__ unsigned slice_in(double* region, const double* src, int n, unsigned long long* bar) {
+  const int head = slice_off(src);
+  const int mid = (n - head) & ~1;
+  if (head) region[1] = src[0];
+  if (n - head - mid) region[head + n - 1] = src[n - 1];
+  if (mid > 0) bulk_g2s(region + 2 * head, src + head, (unsigned)mid * 8u, bar);
+  return (unsigned)mid * 8u;
+}
+
 // shared-memory plan of one block, in doubles
 struct ResPlan {
   int STGp;        // stage stride, padded to an odd number of doubles: stage threads hit different banks
-  int o_ws, o_qp, o_rk, o_gd, o_gi, o_team, o_ring, total;
+  int o_ws, o_qp, o_rk, o_rk1, o_gd, o_gi, o_team, o_ring, total;
   int stage_threads, threads;
+  // input staging (aliases the Riccati records, which are dead while an instance is set up): regions of n + 2 doubles
+  int i_xinit, i_xref, i_uref, i_ulast, i_uguess, i_circ, i_planes, i_xguess, i_total;
 };
 __host__ __device__ inline ResPlan res_plan(const MmpcConfig& c) {
   ResPlan p;
@@ -39,10 +77,18 @@ __host__ __device__ inline ResPlan res_plan(const MmpcConfig& c) {
   p.STGp = staged_stage_doubles(c) | 1;
   p.stage_threads = (K1 + 31) / 32 * 32;
   p.threads = 32 + p.stage_threads;
+  int i = 0;
+  auto region = [&](int n) { int at = i; i += (n + 3) & ~1; return at; };
+  p.i_xinit = region(NX); p.i_xref = region(K1 * NX); p.i_uref = region(c.N * NU); p.i_ulast = region(c.N * NU);
+  p.i_uguess = region(c.N * NU); p.i_circ = region((c.obs_per_stage ? K1 : 1) * 3 * c.n_obs); p.i_planes = region(6 * c.n_pl);
+  p.i_xguess = region(K1 * NX); p.i_total = i;
   int o = 0;
   p.o_ws = o; o += K1 * p.STGp;
+  o = (o + 1) & ~1;
+  p.o_rk = o; o += (K1 * RS > p.i_total ? K1 * RS : p.i_total);   // 16-byte aligned: bulk copy destination
+  o = (o + 1) & ~1;
+  p.o_rk1 = o; o += K1 * RS;                           // the second set of Riccati records (speculative delta_w)
   p.o_qp = o; o += K1 * QS;
-  p.o_rk = o; o += K1 * RS;
   p.o_gd = o; o += staged_inst_doubles(c);
   p.o_gi = o; o += (J_NFIELDS + 1) / 2 + 1;          // ints, two per double
   o = (o + 1) & ~1;                                   // the team ring is read in 16-byte pieces
@@ -52,10 +98,157 @@ __host__ __device__ inline ResPlan res_plan(const MmpcConfig& c) {
   return p;
 }
 
+// One thread: bulk copies of instance b's inputs into the staging regions, then its arrive with the byte count.
+__device__ inline void inputs_issue(const SParams& P, const ResPlan& pl, double* in, int b, unsigned long long* bar) {
+  const MmpcConfig& c = P.cfg; const SIO& io = *P.io;
+  const int K1 = c.N + 1;
+  unsigned bytes = 0;
+  bytes += slice_in(in + pl.i_xinit, io.x_init + (long long)b * NX, NX, bar);
+  bytes += slice_in(in + pl.i_xref, io.x_ref + (long long)b * K1 * NX, K1 * NX, bar);
+  bytes += slice_in(in + pl.i_uref, io.u_ref + (long long)b * c.N * NU, c.N * NU, bar);
+  bytes += slice_in(in + pl.i_ulast, io.u_last + (long long)b * c.N * NU, c.N * NU, bar);
+  if (io.u_guess) bytes += slice_in(in + pl.i_uguess, io.u_guess + (long long)b * c.N * NU, c.N * NU, bar);
+  const int ncirc = (c.obs_per_stage ? K1 : 1) * 3 * c.n_obs;
+  if (ncirc > 0) bytes += slice_in(in + pl.i_circ, io.circles + (long long)b * ncirc, ncirc, bar);
+  if (c.n_pl > 0) bytes += slice_in(in + pl.i_planes, io.planes + (long long)b * 6 * c.n_pl, 6 * c.n_pl, bar);
+  if (io.x_guess) bytes += slice_in(in + pl.i_xguess, io.x_guess + (long long)b * K1 * NX, K1 * NX, bar);
+  mbar_arrive_expect(bar, bytes);
+}
+
+// ---- stage-parallel set-up of an instance: Inst::init() (mmpc_staged.cuh, one thread per instance) split into three passes
+// of one thread per stage; the values, and the order of the operations that produce each of them, are init()'s.  Reads the
+// staged inputs; pass A also leaves the stage's plane margins in the margin cache for pass B's stale-column rows.
+struct InPtr { const double *xinit, *xref, *uref, *ulast, *uguess, *circ, *xguess; };
+__device__ __forceinline__ InPtr in_ptrs(const SParams& P, const ResPlan& pl, const double* in, int b) {
+  const MmpcConfig& c = P.cfg; const SIO& io = *P.io;
+  const int K1 = c.N + 1;
+  InPtr q;
+  q.xinit = in + pl.i_xinit + slice_off(io.x_init + (long long)b * NX);
+  q.xref = in + pl.i_xref + slice_off(io.x_ref + (long long)b * K1 * NX);
+  q.uref = in + pl.i_uref + slice_off(io.u_ref + (long long)b * c.N * NU);
+  q.ulast = in + pl.i_ulast + slice_off(io.u_last + (long long)b * c.N * NU);
+  q.uguess = io.u_guess ? in + pl.i_uguess + slice_off(io.u_guess + (long long)b * c.N * NU) : nullptr;
+  q.circ = in + pl.i_circ + slice_off(io.circles + (long long)b * (c.obs_per_stage ? K1 : 1) * 3 * c.n_obs);
+  q.xguess = io.x_guess ? in + pl.i_xguess + slice_off(io.x_guess + (long long)b * K1 * NX) : nullptr;
+  return q;
+}
+// per-instance tables (planes, static circles): any thread t of nt
+__device__ inline void init_tables(Inst& S, const ResPlan& pl, const double* in, const InPtr& q, int t, int nt) {
+  const MmpcConfig& cfg = S.cfg;
+  const double* planes = in + pl.i_planes + slice_off(S.P.io->planes + (long long)S.bio * 6 * cfg.n_pl);
+  for (int i = t; i < 6 * cfg.n_pl; i += nt) S.D(D_PL + i) = planes[i];
+  if (!cfg.obs_per_stage)
+    for (int i = t; i < 3 * S.nobs; i += nt) S.D(D_CIRC + i) = q.circ[i];
+}
+__device__ inline void init_pass_a(Inst& S, const InPtr& q, int k) {
+  const MmpcConfig& cfg = S.cfg;
+  const int N = S.N, R = S.R, nobs = S.nobs, nself = S.nself, npl = S.npl;
+  double gmax = 0;
+  const bool refmode = cfg.mode == MMPC_MODE_REFERENCE && npl > 1;
+  double x[NX];
+  if (cfg.obs_per_stage)
+    for (int i = 0; i < 3 * nobs; ++i) S.W2(k, S_DT + R + i) = q.circ[k * 3 * nobs + i];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double v = fmax(fmin(q.xinit[i], cfg.xlim[1][i]), cfg.xlim[0][i]);
+    if (k >= 1 && q.xguess) v = q.xguess[k * NX + i];
+    if (k >= 1) v = push_in(v, cfg.xlim[0][i], cfg.xlim[1][i]);
+    double xr = q.xref[k * NX + i];
+    x[i] = v; S.W(k, I_X + i) = v; S.W(k, I_LAM + i) = 0; S.W2(k, IN_XREF + i) = xr;
+    S.W(k, I_ZXL + i) = 1; S.W(k, I_ZXU + i) = 1;
+    double Wx = (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+    if (k >= 1) gmax = fmax(gmax, fabs(2 * Wx * S.xerr(i, v, xr)));
+  }
+  if (k < N) {
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      double ul = q.ulast[k * NU + j], ur = q.uref[k * NU + j];
+      double lo = fmax(cfg.ulim[0][j], ul + cfg.dulim[0][j]);
+      double hi = fmin(cfg.ulim[1][j], ul + cfg.dulim[1][j]);
+      double v = q.uguess ? q.uguess[k * NU + j] : ul;
+      v = push_in(v, lo, hi);
+      S.W(k, I_U + j) = v; S.W2(k, IN_UREF + j) = ur; S.W2(k, IN_ULAST + j) = ul; S.W2(k, IN_ULO + j) = lo; S.W2(k, IN_UHI + j) = hi;
+      S.W(k, I_ZUL + j) = 1; S.W(k, I_ZUU + j) = 1;
+      gmax = fmax(gmax, fabs(2 * cfg.Rd[j] * (v - ur) + 2 * cfg.Wd[j] * (v - ul)));
+    }
+  }
+  FK f; fk_eval(x[2], x[6], x[7], x[8], f);
+  double hmax = -1e300;
+  for (int i = 0; i < nobs; ++i) {
+    double ddx = x[0] - S.circ<false>(k, i, 0), ddy = x[1] - S.circ<false>(k, i, 1);
+    double h = (S.circ<false>(k, i, 2) + cfg.base_radius) - sqrt(ddx * ddx + ddy * ddy);
+    S.W(k, I_T + i) = h; hmax = fmax(hmax, h);
+  }
+#pragma unroll 1
+  for (int m = 0; m < nself; ++m) {
+    Point p; point_eval(x[0], x[1], f, SELFD[m], p);
+    double h = cfg.self_collision_radius - sqrt(p.P[0] * p.P[0] + p.P[1] * p.P[1] + p.P[2] * p.P[2]);
+    S.W(k, I_T + nobs + m) = h;
+    if (!(k == N && S.q3())) hmax = fmax(hmax, h);
+  }
+  if (npl > 0) {
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+      Point p; point_eval(x[0], x[1], f, BODY[i], p);
+      int jb; double h = S.plane_row<false>(p, jb);
+      S.W(k, I_T + nobs + nself + i) = h; hmax = fmax(hmax, h);
+    }
+  }
+  if (staged_stale_rows(cfg) > 0 && refmode) {
+    double pp[NP] = {x[0], x[1], x[2], x[6], x[7], x[8]}; FK ff;
+    double c[6][MMPC_MAX_PLANES];
+    S.margins(pp, ff, c);
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < npl; ++j) S.W2(k, S.MG + i * cfg.n_pl + j) = c[i][j];
+  }
+  S.W2(k, S_PART + 0) = hmax; S.W2(k, S_PART + 1) = gmax;
+}
+__device__ inline void init_pass_b(Inst& S, int k) {
+  const MmpcConfig& cfg = S.cfg;
+  const int R = S.R, nobs = S.nobs, nself = S.nself, npl = S.npl;
+  const bool refmode = cfg.mode == MMPC_MODE_REFERENCE && npl > 1;
+  double hmax = S.W2(k, S_PART + 0), gmax = S.W2(k, S_PART + 1);
+  if (staged_stale_rows(cfg) > 0) {
+    const int nst = cfg.n_pl - 1, r0 = nobs + nself + 6;
+    for (int r = r0; r < R; ++r) S.W(k, I_T + r) = 0;
+    if (refmode && k >= 1) {
+      double ccur[6][MMPC_MAX_PLANES], cprev[6][MMPC_MAX_PLANES];
+      S.load_margins(k, ccur); S.load_margins(k - 1, cprev);
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < npl - 1; ++j) {
+          int jb; double h = S.stale_max(ccur, cprev, i, j, jb);
+          S.W(k, I_T + r0 + i * nst + j) = h; hmax = fmax(hmax, h);
+        }
+    }
+  }
+  double s = fmax(0.0, hmax + 1e-2);
+  S.W(k, I_S) = s;
+  gmax = fmax(gmax, fabs(2 * cfg.S * s));
+  S.W2(k, S_PART + 1) = gmax;
+}
+__device__ inline void init_pass_c(Inst& S, int k) {
+  const int N = S.N, R = S.R, nobs = S.nobs, nself = S.nself;
+  const double s = S.W(k, I_S);
+  for (int r = 0; r < R; ++r) {
+    const double sr = (k == N && S.q3() && r >= nobs && r < nobs + nself) ? S.W(k - 1, I_S) : s;
+    S.W(k, I_T + r) = sr - S.W(k, I_T + r); S.W(k, I_T + R + r) = 1.0;
+  }
+  if (k == 0) {
+    const MmpcConfig& cfg = S.cfg;
+    double gmax = 0;
+    for (int kk = 0; kk <= N; ++kk) gmax = fmax(gmax, S.W2(kk, S_PART + 1));
+    S.D(D_OS) = (gmax > 100.0) ? fmax(100.0 / gmax, 1e-8) : 1.0;
+    S.D(D_MU) = cfg.mu_init; S.D(D_REGLAST) = 0; S.D(D_THMAX) = -1; S.D(D_THMIN) = -1; S.D(D_E0) = 1e300;
+    S.J(J_NPL) = S.npl;
+    S.J(J_STATE) = ST_ACTIVE; S.J(J_IT) = 0; S.J(J_NFILT) = 0; S.J(J_LS) = 0; S.J(J_CUR) = 0; S.J(J_FRST) = 0; S.J(J_REGF) = 0;
+    S.J(J_FLAGS) = S.P.io->flags ? (int)S.P.io->flags[S.bio] : 0;
+  }
+}
+
 template <bool REF, bool Q3>
 __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_constant__ SParams P0, unsigned* queue) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_b;
+  __shared__ __align__(8) unsigned long long s_bar;   // mbarrier: the inputs of the block's next instance have landed
   const ResPlan pl = res_plan(P0.cfg);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = P0.cfg.N;
@@ -64,44 +257,82 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
   SParams P = P0;
   P.ws = smem + pl.o_ws; P.qp = smem + pl.o_qp; P.rk = smem + pl.o_rk; P.gd = smem + pl.o_gd; P.gi = (int*)(smem + pl.o_gi);
   P.LS = 1; P.STG = pl.STGp;
+  double* const in = smem + pl.o_rk;            // input staging: the Riccati records are dead while an instance is set up
   double* team_ring = smem + pl.o_team + (lane >> 4) * Team::SMEM_DOUBLES;
   double* ring = smem + pl.o_ring + (tid - 32);
   const int B = P.io->B;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  unsigned parity = 0;
+#ifdef MMPC_RES_PROF   // A/B build: cycles per phase of block 0, printed at the end (a clock read right behind a barrier
+                       // captures the barrier's ISSUE, so a phase's wait shows up in the next bucket: read the buckets in pairs)
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
+#define RES_TICK(i) { t1 = clock64(); pc[i] += t1 - t0; t0 = t1; }
+#else
+#define RES_TICK(i)
+#endif
   for (;;) {
     __syncthreads();                            // everybody is done with the previous instance (and with s_b)
-    if (tid == 0) s_b = (int)atomicAdd(queue, 1u);
+    if (tid == 0) {
+      const int nb = (int)atomicAdd(queue, 1u);
+      s_b = nb;
+      if (nb < B) { fence_async_smem(); inputs_issue(P, pl, in, nb, &s_bar); }
+    }
     __syncthreads();
     const int b = s_b;
     if (b >= B) break;
     Inst S(P, b); S.sm = ring; S.bs = pl.stage_threads;
-    if (tid == 0) S.init();                     // the starting point (:302-304), bound push, slack lift, objective scaling
+    S.npl = P.io->n_pl_inst ? P.io->n_pl_inst[b] : P.cfg.n_pl;
+    S.npl = S.npl < 0 ? 0 : (S.npl > P.cfg.n_pl ? P.cfg.n_pl : S.npl);
+    const InPtr q = in_ptrs(P, pl, in, b);
+    RES_TICK(7)
+    mbar_wait(&s_bar, parity); parity ^= 1;     // the bulk copies have landed (and the issuing thread's odd doubles with them)
+    // ---- the starting point (:302-304), bound push, slack lift, objective scaling: Inst::init(), one thread per stage ----
+    init_tables(S, pl, in, q, tid, blockDim.x);
     __syncthreads();
+    if (stage) init_pass_a(S, q, k);
+    __syncthreads();
+    if (stage) init_pass_b(S, k);
+    __syncthreads();
+    if (stage) init_pass_c(S, k);
+    __syncthreads();
+    RES_TICK(0)
     if (REF) { if (stage) S.pose_pass(k, false); __syncthreads(); }
     if (stage) S.template eval<REF>(k);
     __syncthreads();
+    RES_TICK(1)
     for (;;) {
-      // ---- KKT test, barrier update, Riccati factorisation, roll-out of the Newton step ----
-      if (warp == 0) { Team T(P, b, lane & 15, team_ring); T.template solve<Q3>(); }
+      // ---- KKT test, barrier update, Riccati factorisation (two delta_w at a time), roll-out of the Newton step ----
+      if (warp == 0) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, smem + pl.o_rk1); }
       __syncthreads();
+      RES_TICK(2)
       const int st = S.J(J_STATE);
       // ---- slack / multiplier steps, fraction to the boundary (or: the results of an instance that has just finished) ----
       if (stage) { if (st == ST_FINISH) S.finish_stage(k); else if (st == ST_ACTIVE) S.template step<REF>(k); }
       __syncthreads();
+      RES_TICK(3)
       if (warp == 0) S.template ctrl_step<32>(lane);
       __syncthreads();
+      RES_TICK(4)
       if (S.J(J_STATE) != ST_TRIAL) break;      // finished: the outputs are written
       // ---- filter line search: candidate + evaluation of the next iteration at the candidate ----
       for (;;) {
         if (REF) { if (stage) S.pose_pass(k, true); __syncthreads(); }
         if (stage) S.template trial_eval<REF>(k);
         __syncthreads();
+        RES_TICK(5)
         if (warp == 0) S.template ctrl_trial<32>(lane);
         __syncthreads();
+        RES_TICK(6)
         if (S.J(J_STATE) != ST_TRIAL) break;    // accepted (ST_ACTIVE) or given up (ST_DONE)
       }
       if (S.J(J_STATE) != ST_ACTIVE) break;
     }
   }
+#ifdef MMPC_RES_PROF
+  if (blockIdx.x == 0 && tid == 0)
+    printf("resident cycles: init %lld eval0 %lld team %lld step %lld ctrl_step %lld pose+trial %lld ctrl_trial %lld other %lld\n",
+           pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
+#endif
 }
 
 }  // namespace mmpc_res

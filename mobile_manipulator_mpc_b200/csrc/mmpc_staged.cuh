@@ -173,7 +173,7 @@ struct Inst {
     // resident build (mmpc_resident.cu): the workspace is ONE instance in shared memory, fields contiguous per stage; b_ only
     // names the caller's arrays (bio)
     b = 0; bio = b_;
-    w = p.ws; gd = p.gd; gi = p.gi;
+    w = p.ws; gd = p.gd; gi = p.gi; rkp = p.rk;
 #else
     bio = b_;
     const long long tile = b_ >> 5; const int ln = b_ & 31;
@@ -198,7 +198,12 @@ struct Inst {
   // of the hot kernels are compile-time immediates instead of an index computation per access
   __device__ __forceinline__ double* stage_ptr(int k, int base) const { return w + ((k * STG + base) << LSH); }
   __device__ __forceinline__ double& Qw(int k, int o) const { return P.qp[((long long)k * LS + b) * QS + o]; }
+#ifdef MMPC_RESIDENT
+  double* rkp;   // the Riccati records this thread works on: the resident kernel keeps two sets (speculative delta_w, mmpc_team.cuh)
+  __device__ __forceinline__ double& Rw(int k, int o) const { return rkp[k * RS + o]; }
+#else
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
+#endif
   __device__ __forceinline__ double& D(int o) const { return gd[o << LSH]; }
   __device__ __forceinline__ int& J(int o) const { return gi[o << LSH]; }
   template <bool NC = true>

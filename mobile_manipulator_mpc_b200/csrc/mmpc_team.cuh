@@ -484,6 +484,74 @@ struct Team {
     rollout<Q3>(mu, it);
     if (fin >= 0 && c == 0) { S.J(J_STATUS) = fin; S.J(J_STATE) = ST_FINISH; }
   }
+
+#ifdef MMPC_RESIDENT
+  // Resident build (mmpc_resident.cu): the warp works on ONE instance, so the second half-warp has nothing of its own to do.
+  // Instead of mirroring the first it factorises, at the same time and into its own set of Riccati records (rk1), with the
+  // NEXT delta_w of IPOPT's inertia-correction sequence.  The sequence is known up front (0, then reg_last/3 or 1e-4, then
+  // x8 or x100), the first success in sequence order wins, so the accepted factorisation -- and every number after it -- is
+  // the one the serial retry loop of solve() arrives at; 26 % of the iterations of config 3 need delta_w > 0 and save one
+  // full sweep or more.  An instance that leaves (converged, max_iter, NaN) skips factorisation and roll-out altogether:
+  // nothing reads the step of a finished instance.
+  template <bool Q3>
+  __device__ void solve_spec(int half, double* rk1) {
+    const MmpcConfig& cfg = S.cfg;
+    const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5;
+    const double tol = cfg.tol;
+    const int N = S.N;
+    const int it = S.J(J_CUR) * S.ITSZ;
+    KktParts kp;
+    kp.e_stat = 0; kp.e_prim = 0; kp.c_hi = -1e300; kp.c_lo = 1e300; kp.sum_lam = 0; kp.sum_z = 0;
+    double nz = 0, neq = 0;
+    for (int k = c; k <= N; k += 16) {
+      kp.e_stat = fmax(kp.e_stat, S.W2(k, S_PART + 0)); kp.e_prim = fmax(kp.e_prim, S.W2(k, S_PART + 1));
+      kp.c_hi = fmax(kp.c_hi, S.W2(k, S_PART + 2)); kp.c_lo = fmin(kp.c_lo, S.W2(k, S_PART + 3));
+      kp.sum_lam += S.W2(k, S_PART + 4); kp.sum_z += S.W2(k, S_PART + 5); nz += S.W2(k, S_PART + 6); neq += S.W2(k, S_PART + 7);
+    }
+    kp.e_stat = tmax(kp.e_stat); kp.e_prim = tmax(kp.e_prim); kp.c_hi = tmax(kp.c_hi); kp.c_lo = tmin(kp.c_lo);
+    kp.sum_lam = tsum(kp.sum_lam); kp.sum_z = tsum(kp.sum_z); nz = tsum(nz); neq = tsum(neq);
+    kp.n_z = (int)nz; kp.n_eq = (int)neq;
+    if (Q3) kp.e_stat = fmax(kp.e_stat, fabs(S.W2(N, S_DFC + 1) - S.W2(N, S_DFC + 0)));
+    const double E0 = kkt_error(kp, 0.0);
+    const int iter = S.J(J_IT);
+    double mu = S.D(D_MU);
+    const double reg_last = S.D(D_REGLAST);
+    team_sync();
+    const bool writer = c == 0 && half == 0;
+    if (writer) S.D(D_E0) = E0;
+    int fin = -1;
+    if (!(E0 == E0)) fin = MMPC_STATUS_NAN;
+    else if (E0 <= tol) fin = MMPC_STATUS_CONVERGED;
+    else if (iter >= cfg.max_iter) fin = MMPC_STATUS_MAX_ITER;
+    if (fin >= 0) { if (writer) { S.J(J_STATUS) = fin; S.J(J_STATE) = ST_FINISH; } return; }
+    bool mu_changed = false;
+    while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
+      mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
+    }
+    if (mu_changed && writer) { S.J(J_NFILT) = 0; S.J(J_FRST) = S.J(J_FRST) & 0xff00; S.D(D_MU) = mu; }
+    auto next_reg = [&](double r) { return r == 0 ? ((reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3)) : r * (reg_last == 0 ? 100 : 8); };
+    double* const rk0 = S.rkp;
+    S.rkp = half ? rk1 : rk0;
+    double r_a = 0, reg = 0;   // attempt number ia of the serial sequence runs in half 0, ia + 1 in half 1
+    int ia = 0, win = -1;
+    for (;;) {
+      const double r_b = next_reg(r_a);
+      const int fail = riccati<Q3>(half ? r_b : r_a, mu, it);
+      const int fail_a = __shfl_sync(FULL, fail, 0), fail_b = __shfl_sync(FULL, fail, 16);
+      if (!fail_a) { win = 0; reg = r_a; break; }
+      if (ia + 1 > 40 || r_b > 1e20) break;      // the serial loop gives up after attempt ia (MMPC_STATUS_FACTOR)
+      if (!fail_b) { win = 1; reg = r_b; break; }
+      r_a = next_reg(r_b); ia += 2;
+      if (ia > 40 || r_a > 1e20) break;
+    }
+    if (win < 0) { if (writer) { S.J(J_STATUS) = MMPC_STATUS_FACTOR; S.J(J_STATE) = ST_FINISH; } S.rkp = rk0; return; }
+    if (writer) { if (reg > 0) S.D(D_REGLAST) = reg; S.J(J_REGF) = reg > 0; }
+    S.rkp = win ? rk1 : rk0;
+    team_sync();
+    rollout<Q3>(mu, it);
+    S.rkp = rk0;
+  }
+#endif
 };
 
 // Q3: the literal reference NLP (Inst::q3) -- the host picks the instantiation from the configuration
