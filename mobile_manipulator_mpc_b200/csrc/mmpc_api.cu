@@ -520,10 +520,13 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   io.B = B;
   staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io);
   CK(cudaGetLastError());
-  // the resident kernel: forced, or AUTO's choice for at most one instance per SM when the instance fits in shared memory
-  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 1;   // A/B: 0 = AUTO never takes it
+  // the resident kernel: forced, or AUTO's choice for small batches when the instance fits in shared memory.  Measured on a
+  // B200 (config 3, reference NLP, resident / staged ms): B = 1 4.0 / 5.2, 148 14.5 / 31.8, 592 19.1 / 39.4, 1,024 32.4 / 47.7,
+  // 2,048 50.4 / 51.5 -- the staged solver's floor is the launch latency of its ~270 rounds, the resident kernel's slope is
+  // one instance (two at a time) per SM.  MMPC_AUTO_RESIDENT = largest batch, in instances per SM, AUTO sends there (0: never).
+  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 10;
   const bool fits = mmpc_resident_smem_bytes(&h->cfg) <= h->smem_optin;
-  if (!h->profile && h->sg_fused && fits && (h->resident || (h->autosel && auto_resident && B <= h->sm_count))) {
+  if (!h->profile && h->sg_fused && fits && (h->resident || (h->autosel && (long long)B <= (long long)auto_resident * h->sm_count))) {
     CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned), st));
     cudaError_t e = (cudaError_t)mmpc_resident_launch(&h->cfg, B, h->sg.io, h->queue, h->sm_count, st);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "resident kernel launch failed: %s", cudaGetErrorString(e)); return MMPC_ERR_CUDA; }

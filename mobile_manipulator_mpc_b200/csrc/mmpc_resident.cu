@@ -5,7 +5,7 @@
 // atomic work queue, so there are no lists, no compaction, no rounds, and no host in the loop: one launch per solve.
 //
 // It is the LATENCY path (small batches: a single controller, closed loops of a few hundred robots).  A B200 SM holds one
-// instance of this NLP in shared memory (about 127 KB at N = 20 with 16 circles), so 148 instances are in flight and an
+// or two instances of this NLP in shared memory (112 KB each at N = 20 with 16 circles), so 148 .. 296 instances are in flight and an
 // iteration costs its dependent-instruction latency; batches beyond a few hundred instances are faster through the streaming
 // "staged" kernels, which keep 24 instances per SM in flight.  mmpc_api.cu picks by batch size.
 //
@@ -65,8 +65,9 @@ __device__ __forceinline__ unsigned slice_in(double* region, const double* src, 
 
 // shared-memory plan of one block, in doubles
 struct ResPlan {
+  int ITSZ;        // doubles of one copy of a stage's iterate, at least RS: the dead copy doubles as the second set of Riccati records
   int STGp;        // stage stride, padded to an odd number of doubles: stage threads hit different banks
-  int o_ws, o_qp, o_rk, o_rk1, o_gd, o_gi, o_team, o_ring, total;
+  int o_ws, o_qp, o_rk, o_gd, o_gi, o_team, o_ring, total;
   int stage_threads, threads;
   // input staging (aliases the Riccati records, which are dead while an instance is set up): regions of n + 2 doubles
   int i_xinit, i_xref, i_uref, i_ulast, i_uguess, i_circ, i_planes, i_xguess, i_total;
@@ -74,7 +75,8 @@ struct ResPlan {
 __host__ __device__ inline ResPlan res_plan(const MmpcConfig& c) {
   ResPlan p;
   const int K1 = c.N + 1;
-  p.STGp = staged_stage_doubles(c) | 1;
+  p.ITSZ = staged_itsz(c) > RS ? staged_itsz(c) : RS;
+  p.STGp = (staged_stage_doubles(c) + 2 * (p.ITSZ - staged_itsz(c))) | 1;
   p.stage_threads = (K1 + 31) / 32 * 32;
   p.threads = 32 + p.stage_threads;
   int i = 0;
@@ -86,14 +88,12 @@ __host__ __device__ inline ResPlan res_plan(const MmpcConfig& c) {
   p.o_ws = o; o += K1 * p.STGp;
   o = (o + 1) & ~1;
   p.o_rk = o; o += (K1 * RS > p.i_total ? K1 * RS : p.i_total);   // 16-byte aligned: bulk copy destination
-  o = (o + 1) & ~1;
-  p.o_rk1 = o; o += K1 * RS;                           // the second set of Riccati records (speculative delta_w)
   p.o_qp = o; o += K1 * QS;
   p.o_gd = o; o += staged_inst_doubles(c);
   p.o_gi = o; o += (J_NFIELDS + 1) / 2 + 1;          // ints, two per double
   o = (o + 1) & ~1;                                   // the team ring is read in 16-byte pieces
-  p.o_team = o; o += 2 * Team::SMEM_DOUBLES;          // one ring per half-warp
-  p.o_ring = o; o += STAGED_TRIAL_RING_DOUBLES * p.stage_threads;   // the per-thread row rings of the step / trial bodies
+  p.o_team = o; o += Team::SMEM_DOUBLES;              // the team's ring: two backward-sweep rings (one per half-warp) or one roll-out ring
+  p.o_ring = o; o += Inst::RING_D * Inst::RING_W * p.stage_threads;   // the per-thread row rings of the step / trial bodies
   p.total = o;
   return p;
 }
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
   P.ws = smem + pl.o_ws; P.qp = smem + pl.o_qp; P.rk = smem + pl.o_rk; P.gd = smem + pl.o_gd; P.gi = (int*)(smem + pl.o_gi);
   P.LS = 1; P.STG = pl.STGp;
   double* const in = smem + pl.o_rk;            // input staging: the Riccati records are dead while an instance is set up
-  double* team_ring = smem + pl.o_team + (lane >> 4) * Team::SMEM_DOUBLES;
+  double* team_ring = smem + pl.o_team;
   double* ring = smem + pl.o_ring + (tid - 32);
   const int B = P.io->B;
   if (tid == 0) mbar_init(&s_bar, 1);
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
     RES_TICK(1)
     for (;;) {
       // ---- KKT test, barrier update, Riccati factorisation (two delta_w at a time), roll-out of the Newton step ----
-      if (warp == 0) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, smem + pl.o_rk1); }
+      if (warp == 0) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, &S.W(0, (1 - S.J(J_CUR)) * pl.ITSZ), pl.STGp); }
       __syncthreads();
       RES_TICK(2)
       const int st = S.J(J_STATE);
@@ -350,14 +350,17 @@ extern "C" int mmpc_resident_launch(const MmpcConfig* cfg, int B, const void* io
   SParams P; memset(&P, 0, sizeof P);
   P.cfg = c; P.B = B; P.io = (const SIO*)io_dev;
   P.team = 1; P.fused = 1; P.parts = 0;
-  P.R = staged_rows(c); P.ITSZ = staged_itsz(c); P.STG = pl.STGp; P.ND = staged_inst_doubles(c); P.LS = 1;
+  P.R = staged_rows(c); P.ITSZ = pl.ITSZ; P.STG = pl.STGp; P.ND = staged_inst_doubles(c); P.LS = 1;
   const bool ref = c.mode == MMPC_MODE_REFERENCE, q3 = ref && c.terminal_rows_on_sN == 0;
   const void* fn = ref ? (q3 ? (const void*)resident_solve_kernel<true, true> : (const void*)resident_solve_kernel<true, false>)
                        : (const void*)resident_solve_kernel<false, false>;
   const int smem = (int)(pl.total * sizeof(double));
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  const int grid = B < max_blocks ? B : max_blocks;
+  cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int per_sm = 1;   // blocks (= instances) an SM holds: 2 at N = 20 with 16 circles (112 KB each)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl.threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = B < max_blocks * per_sm ? B : max_blocks * per_sm;
   void* args[] = {&P, &queue};
   return (int)cudaLaunchKernel(fn, dim3(grid), dim3(pl.threads), args, smem, (cudaStream_t)stream);
 }

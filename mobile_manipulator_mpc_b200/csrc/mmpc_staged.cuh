@@ -173,7 +173,7 @@ struct Inst {
     // resident build (mmpc_resident.cu): the workspace is ONE instance in shared memory, fields contiguous per stage; b_ only
     // names the caller's arrays (bio)
     b = 0; bio = b_;
-    w = p.ws; gd = p.gd; gi = p.gi; rkp = p.rk;
+    w = p.ws; gd = p.gd; gi = p.gi; rkp = p.rk; rks = RS;
 #else
     bio = b_;
     const long long tile = b_ >> 5; const int ln = b_ & 31;
@@ -199,8 +199,9 @@ struct Inst {
   __device__ __forceinline__ double* stage_ptr(int k, int base) const { return w + ((k * STG + base) << LSH); }
   __device__ __forceinline__ double& Qw(int k, int o) const { return P.qp[((long long)k * LS + b) * QS + o]; }
 #ifdef MMPC_RESIDENT
-  double* rkp;   // the Riccati records this thread works on: the resident kernel keeps two sets (speculative delta_w, mmpc_team.cuh)
-  __device__ __forceinline__ double& Rw(int k, int o) const { return rkp[k * RS + o]; }
+  double* rkp;   // the Riccati records this thread works on and their stage stride: the resident kernel keeps two sets
+  int rks;       // (speculative delta_w, mmpc_team.cuh), the second one inside the dead copy of the iterate
+  __device__ __forceinline__ double& Rw(int k, int o) const { return rkp[k * rks + o]; }
 #else
   __device__ __forceinline__ double& Rw(int k, int o) const { return P.rk[((long long)k * LS + b) * RS + o]; }
 #endif
@@ -1520,6 +1521,10 @@ struct Inst {
     // issue sites: instruction-cache misses) nor parked in shared memory up front (L1, where the spills live, shrinks) paid.
     // the 28 bound multipliers (fields I_ZXL .. I_T) are parked in shared memory by one group of copies and read back as plain
     // LDS at the sites that use them: each of those sites exposed a full HBM round trip (the compiler does not hoist them)
+#ifdef MMPC_RESIDENT
+    // (resident build: the workspace is shared memory already, the parked values are read where they lie)
+    const double* zb = &ci[I_ZXL]; const double* rb_in = &c2[IN_XREF]; constexpr int ps = 1;
+#else
     double* zb = sm + (RING_DT * RING_W) * bs;
 #pragma unroll 1
     for (int f = 0; f < I_T - I_ZXL; ++f) async_copy8(zb + f * bs, &ci[(I_ZXL + f) << LSH]);
@@ -1528,6 +1533,8 @@ struct Inst {
 #pragma unroll 1
     for (int f = 0; f < S_DT - IN_XREF; ++f) async_copy8(rb_in + f * bs, &c2[(IN_XREF + f) << LSH]);
     async_commit();
+    const int ps = bs;
+#endif
     const int q_end = nobs + nself + (npl > 0 ? 6 : 0);  // ring items = the rows in evaluation order: circles, self-collision, planes
     auto ring_issue = [&](int q) {
       if (q < q_end) {
@@ -1639,18 +1646,18 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
-      double e = xerr(i, x[i], rb_in[(IN_XREF - IN_XREF + i) * bs]);
+      double e = xerr(i, x[i], rb_in[(IN_XREF - IN_XREF + i) * ps]);
       fsum += Wx * e * e;
       double gr = 2 * Wx * e;
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
         if (is_fin(lo)) {
-          double d = x[i] - lo, id, z = box(zb[i * bs], xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
+          double d = x[i] - lo, id, z = box(zb[i * ps], xo[i] - lo, d, dxo[i], jt + I_ZXL + i, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - x[i], id, z = box(zb[(I_ZXU - I_ZXL + i) * bs], hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
+          double d = hi - x[i], id, z = box(zb[(I_ZXU - I_ZXL + i) * ps], hi - xo[i], d, -dxo[i], jt + I_ZXU + i, id);
           Hd += z * id; gB += id; st += z;
         }
       }
@@ -1672,18 +1679,18 @@ struct Inst {
       double Hd = 0, gA = 0, gB = 0;
       if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - rb_in[(IN_UREF - IN_XREF + j) * bs], dl = u[j] - rb_in[(IN_ULAST - IN_XREF + j) * bs];
+        double e = u[j] - rb_in[(IN_UREF - IN_XREF + j) * ps], dl = u[j] - rb_in[(IN_ULAST - IN_XREF + j) * ps];
         fsum += os * (cfg.Rd[j] * e * e + cfg.Wd[j] * dl * dl);
         double gr = 2 * Rj * e + 2 * Wj * dl;
         Hd = 2 * Rj + 2 * Wj; gA = gr;
         double st = gr + stu[j];
-        double lo = rb_in[(IN_ULO - IN_XREF + j) * bs], hi = rb_in[(IN_UHI - IN_XREF + j) * bs];
+        double lo = rb_in[(IN_ULO - IN_XREF + j) * ps], hi = rb_in[(IN_UHI - IN_XREF + j) * ps];
         if (is_fin(lo)) {
-          double d = u[j] - lo, id, z = box(zb[(I_ZUL - I_ZXL + j) * bs], uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
+          double d = u[j] - lo, id, z = box(zb[(I_ZUL - I_ZXL + j) * ps], uo[j] - lo, d, duo[j], jt + I_ZUL + j, id);
           Hd += z * id; gB -= id; st -= z;
         }
         if (is_fin(hi)) {
-          double d = hi - u[j], id, z = box(zb[(I_ZUU - I_ZXL + j) * bs], hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
+          double d = hi - u[j], id, z = box(zb[(I_ZUU - I_ZXL + j) * ps], hi - uo[j], d, -duo[j], jt + I_ZUU + j, id);
           Hd += z * id; gB += id; st += z;
         }
         es = fmax(es, fabs(st));

@@ -491,10 +491,11 @@ struct Team {
   // NEXT delta_w of IPOPT's inertia-correction sequence.  The sequence is known up front (0, then reg_last/3 or 1e-4, then
   // x8 or x100), the first success in sequence order wins, so the accepted factorisation -- and every number after it -- is
   // the one the serial retry loop of solve() arrives at; 26 % of the iterations of config 3 need delta_w > 0 and save one
-  // full sweep or more.  An instance that leaves (converged, max_iter, NaN) skips factorisation and roll-out altogether:
+  // full sweep or more.  rk1 lies inside the copy of the iterate that is dead between an accepted trial and the next one
+  // (stage stride rk1_stride), so the second set costs no shared memory.  An instance that leaves (converged, max_iter, NaN) skips factorisation and roll-out altogether:
   // nothing reads the step of a finished instance.
   template <bool Q3>
-  __device__ void solve_spec(int half, double* rk1) {
+  __device__ void solve_spec(int half, double* rk1, int rk1_stride) {
     const MmpcConfig& cfg = S.cfg;
     const double kap_eps = 10, kap_mu = 0.2, th_mu = 1.5;
     const double tol = cfg.tol;
@@ -530,8 +531,9 @@ struct Team {
     }
     if (mu_changed && writer) { S.J(J_NFILT) = 0; S.J(J_FRST) = S.J(J_FRST) & 0xff00; S.D(D_MU) = mu; }
     auto next_reg = [&](double r) { return r == 0 ? ((reg_last == 0) ? 1e-4 : fmax(1e-20, reg_last / 3)) : r * (reg_last == 0 ? 100 : 8); };
-    double* const rk0 = S.rkp;
-    S.rkp = half ? rk1 : rk0;
+    double* const rk0 = S.rkp; double* const ring0 = sm;
+    S.rkp = half ? rk1 : rk0; S.rks = half ? rk1_stride : RS;
+    sm = ring0 + half * (BW_SZ * BW_SLOTS);   // backward sweeps: a ring per half (each adds its own delta_w to the diagonals)
     double r_a = 0, reg = 0;   // attempt number ia of the serial sequence runs in half 0, ia + 1 in half 1
     int ia = 0, win = -1;
     for (;;) {
@@ -544,12 +546,13 @@ struct Team {
       r_a = next_reg(r_b); ia += 2;
       if (ia > 40 || r_a > 1e20) break;
     }
-    if (win < 0) { if (writer) { S.J(J_STATUS) = MMPC_STATUS_FACTOR; S.J(J_STATE) = ST_FINISH; } S.rkp = rk0; return; }
+    sm = ring0;                                // roll-out: both halves do the same, one ring
+    if (win < 0) { if (writer) { S.J(J_STATUS) = MMPC_STATUS_FACTOR; S.J(J_STATE) = ST_FINISH; } S.rkp = rk0; S.rks = RS; return; }
     if (writer) { if (reg > 0) S.D(D_REGLAST) = reg; S.J(J_REGF) = reg > 0; }
-    S.rkp = win ? rk1 : rk0;
+    S.rkp = win ? rk1 : rk0; S.rks = win ? rk1_stride : RS;
     team_sync();
     rollout<Q3>(mu, it);
-    S.rkp = rk0;
+    S.rkp = rk0; S.rks = RS;
   }
 #endif
 };

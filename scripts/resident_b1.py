@@ -7,7 +7,7 @@ import torch
 from mobile_manipulator_mpc_b200 import scenarios, _abi
 from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
 kern = sys.argv[1] if len(sys.argv) > 1 else "resident"
-for cfg, B in ((1, 1), (3, 148), (3, 296)):
+for cfg, B in ((1, 1), (3, 148), (3, 296), (3, 592), (3, 1024), (3, 2048), (2, 1024)):
     b = scenarios.make_batch(cfg, B)
     S = BatchSolver(N=b["N"], dt=b["dt"], n_obs=b["n_obs"], n_pl=b["n_pl"], B_max=B, kernel=kern)
     d = S.to_device(b); o = S.solve_device(d); torch.cuda.synchronize()

@@ -14,13 +14,35 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+KERNEL = "staged"
+
+
+@pytest.fixture(autouse=True, params=["staged", "resident"])
+def _kernel(request):
+    """Every test of this module runs twice: on the staged solver (phase kernels over active lists, one CUDA graph) and on the
+    resident kernel (one thread block per instance, state in shared memory; csrc/mmpc_resident.cu).  Where the resident kernel
+    does not fit (N = 40, 63) the second run falls back to the staged solver."""
+    global KERNEL
+    KERNEL = request.param
+    yield
+    KERNEL = "staged"
+
+
 def _solver(batch, B=None, **kw):
     """mode defaults to the stage-separable NLP HERE (these tests name the oracle's mode explicitly); the product's default is
     MMPC_MODE_REFERENCE."""
     from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    from mobile_manipulator_mpc_b200._lib import MmpcError
     kw.setdefault("mode", _abi.MODE_CLEAN)
-    return BatchSolver(N=batch["N"], dt=batch["dt"], n_obs=batch["n_obs"], n_pl=batch["n_pl"],
-                       B_max=B or batch["x_init"].shape[0], obs_per_stage=batch["obs_per_stage"], **kw)
+    kern = kw.pop("kernel", KERNEL)
+    S = BatchSolver(N=batch["N"], dt=batch["dt"], n_obs=batch["n_obs"], n_pl=batch["n_pl"],
+                    B_max=B or batch["x_init"].shape[0], obs_per_stage=batch["obs_per_stage"], **kw)
+    try:
+        S.set_kernel(kern)
+    except MmpcError:
+        assert kern == "resident" and batch["N"] >= 30, (kern, batch["N"])   # MMPC_ERR_UNSUPPORTED: the instance does not fit in shared memory
+        S.set_kernel("staged")
+    return S
 
 
 def _parity_counts(name, batch, o, ref, nlp_mode, max_unconverged, max_outliers):
@@ -472,3 +494,52 @@ def test_graph_solve_equals_host_sequenced_solve_bitwise(mode):
         assert (a["status"] == 0).mean() >= 0.95
     assert Sg.launch_count() > 0
     Sg.close(); Sh.close()
+
+
+@pytest.mark.parametrize("mode,q3", [(_abi.MODE_REFERENCE, 0), (_abi.MODE_REFERENCE, 1), (_abi.MODE_CLEAN, 0)])
+def test_resident_kernel_equals_staged_solver(mode, q3):
+    """The resident kernel compiles the staged solver's phase bodies for a shared-memory workspace, sets an instance up with
+    one thread per stage from inputs staged by cp.async.bulk, and factorises with two delta_w at a time: on the reference NLP
+    (the product's default) every output must equal the staged solver's to the bit -- ragged batch sizes (odd instance offsets: the bulk copies' head
+    and tail doubles), per-instance plane counts, a warm start, the terminal-equality flag, moving obstacles."""
+    rng = np.random.default_rng(5)
+    for cid, B, per_stage in ((3, 301, False), (2, 77, False), (1, 1, False), (3, 40, True)):
+        batch = scenarios.make_batch(cid, B)
+        if per_stage:   # moving obstacles: circles[B, N+1, n_obs, 3]
+            c = np.repeat(batch["circles"][:, None], batch["N"] + 1, axis=1).copy()
+            c[..., :2] += 0.02 * np.arange(batch["N"] + 1)[None, :, None, None]
+            batch["circles"] = c; batch["obs_per_stage"] = True
+        batch["u_guess"] = batch["u_last"] + 0.01 * rng.standard_normal(batch["u_last"].shape)
+        batch["n_pl_inst"] = rng.integers(0, batch["n_pl"] + 1, size=B).astype(np.int32)
+        batch["flags"] = (rng.random(B) < 0.3).astype(np.uint8)
+        kw = dict(mode=mode, terminal_rows_on_sN=q3) if mode == _abi.MODE_REFERENCE else dict(mode=mode)
+        # (clean NLP: 'staged_fat' = the staged solver without the warp-specialised part kernels, which sum in another order)
+        Ss = _solver(batch, kernel="staged" if mode == _abi.MODE_REFERENCE else "staged_fat", **kw)
+        Sr = _solver(batch, kernel="resident", **kw)
+        for n in sorted({B, max(1, B - 3), min(B, 2)}):
+            b = {k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in batch.items()}
+            a, r = Ss.solve_host(b), Sr.solve_host(b)
+            if mode == _abi.MODE_REFERENCE:
+                for k in ("status", "U", "X", "s", "cost", "kkt", "iters"):
+                    assert np.array_equal(a[k], r[k]), (cid, n, k)
+            else:
+                # clean NLP: the two builds inline forward kinematics into different surroundings and the compiler contracts
+                # other multiply-adds: the iterates agree to rounding (measured: 4e-11 on U), not to the bit
+                same = a["status"] == r["status"]
+                assert same.mean() >= 0.97, (cid, n, same.mean())
+                ok = same & (a["status"] == 0)
+                if ok.any():
+                    assert (np.abs(a["iters"] - r["iters"])[ok] <= 1).mean() >= 0.95, (cid, n)
+                    assert (np.abs(a["cost"] - r["cost"])[ok] <= 1e-8 * np.maximum(1, np.abs(a["cost"][ok]))).mean() >= 0.97, (cid, n)
+                    assert np.median(np.abs(a["U"] - r["U"])[ok].max(axis=(1, 2))) < 1e-7, (cid, n)
+        Ss.close(); Sr.close()
+
+
+def test_auto_picks_the_resident_kernel_for_small_batches():
+    """MMPC_KERNEL_AUTO (the default): one launch sequence of three (resident) for a small batch, the graph for a large one."""
+    batch = scenarios.make_batch(3, 2048)
+    S = _solver(batch, kernel="auto", mode=_abi.MODE_REFERENCE)
+    small = {k: (v[:64] if isinstance(v, np.ndarray) else v) for k, v in batch.items()}
+    n0 = S.launch_count(); S.solve_host(small); n1 = S.launch_count(); S.solve_host(batch); n2 = S.launch_count()
+    assert n1 - n0 == 2 and n2 - n1 > 2, (n0, n1, n2)
+    S.close()

@@ -91,12 +91,15 @@ def test_kernel_sources_match_oracle_emulated(n_obs):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["staged", "resident"])
 @pytest.mark.parametrize("n_obs,B", [(3, 256), (16, 256)])
-def test_gpu_mpc_base_matches_oracle(n_obs, B):
+def test_gpu_mpc_base_matches_oracle(n_obs, B, kernel):
     from mobile_manipulator_mpc_b200.controllers.mpc_base import MPCBase
     b = scenarios.make_base_batch(B, n_obs=n_obs, seed=9)
     ref = _ctrl(OC.MPCBase, b).solve_batch(b["x_init"], b["x_ref"], b["u_ref"], circles=b["circles"])
     c = _ctrl(MPCBase, b, batch=B)
+    c.solve_batch(b["x_init"][:1], b["x_ref"][:1], b["u_ref"][:1], circles=b["circles"][:1])   # creates the solver
+    c._solver.set_kernel(kernel)
     out = c.solve_batch(b["x_init"], b["x_ref"], b["u_ref"], circles=b["circles"])
     both = _check_against_oracle(out, ref, b, max_unconverged=1, max_outliers=1)
     assert both.sum() >= B - 1
