@@ -87,13 +87,20 @@ struct MinRatio {
   __device__ __forceinline__ double value(double tau) const { return den > 0 ? fmin(1.0, tau * num / den) : 1.0; }
 };
 
-// log of a running product without one log() per factor
+// log of a running product without one log() per factor.  The rare renormalisation calls log() OUT OF LINE: inlined, its
+// ~60 instructions sat behind every one of the ~100 mul() sites of the trial kernel (31 % of the kernel's code, 6.7 % of its
+// stall samples "no instruction": the taken branch around each copy runs past the fetched lines).
+#if defined(MMPC_EMULATE) || defined(MMPC_EMULATE_LANE) || defined(MMPC_LOG_INLINE)
+__device__ __forceinline__ double log_renorm(double p) { return log(p); }
+#else
+__device__ __noinline__ double log_renorm(double p) { return log(p); }
+#endif
 struct LogProd {
   double prod, acc;
   __device__ __forceinline__ void init() { prod = 1.0; acc = 0.0; }
   __device__ __forceinline__ void mul(double v) {
     prod *= v;
-    if (prod < 1e-120 || prod > 1e120) { acc += log(prod); prod = 1.0; }
+    if (prod < 1e-120 || prod > 1e120) { acc += log_renorm(prod); prod = 1.0; }
   }
   __device__ __forceinline__ double value() const { return acc + log(prod); }
 };
