@@ -139,6 +139,14 @@ __host__ __device__ inline int staged_inst_doubles(const MmpcConfig& c) { return
 __host__ __device__ constexpr int ssidx(int i, int j) { return i <= j ? i * 9 - i * (i - 1) / 2 + (j - i) : j * 9 - j * (j - 1) / 2 + (i - j); }
 struct SACoef { double dt, a32, a42, a34, a43, a35, a45, cp, sp; };
 
+// step kernel: what is parked in shared memory next to the row ring (A/B): 0 nothing, 1 the 29 stage inputs, 2 also the FK
+// cache and the defect (17)
+#ifndef MMPC_STEP_PARK
+#define MMPC_STEP_PARK 1
+#endif
+constexpr int STEP_PARK = MMPC_STEP_PARK;
+constexpr int STAGED_STEP_PARKED = (STEP_PARK >= 1 ? S_DT - IN_XREF : 0) + (STEP_PARK >= 2 ? S_PART - S_FK : 0);
+
 struct Inst {
   const SParams& P;
   const MmpcConfig& cfg;
@@ -374,9 +382,9 @@ struct Inst {
   //   phase 0: evaluation of the current iterate   1: trial + evaluation of the candidate   2: step
   // (Quirk 3, the terminal self-collision rows bounded by s_{N-1}, is handled where those rows are evaluated: see q3().)
   struct StaleIO {
-    double theta, logsum; bool ok;           // merit ingredients (phase 1, 2)
+    double theta; LogProd lp; bool ok;       // merit ingredients (phase 1, 2); lp: the barrier's log of the product of the slacks
     MinRatio rp, rd; double gphi;            // phase 2
-    __device__ __forceinline__ void reset() { theta = 0; logsum = 0; ok = true; gphi = 0; }
+    __device__ __forceinline__ void reset() { theta = 0; lp.init(); ok = true; gphi = 0; }
   };
   __device__ __forceinline__ void pose_at(int kk, int it, bool cand, double alpha, double (&p)[NP]) const {
 #pragma unroll
@@ -457,9 +465,38 @@ struct Inst {
     }
     return -cb;
   }
-  __device__ __forceinline__ void load_margins1(int kk, int i, double (&c)[MMPC_MAX_PLANES]) const {
+  // Where stale_rows() reads the margin caches of the stages k-1, k, k+1 (st = 0, 1, 2) from: the workspace, or a copy the
+  // step / trial kernel has prefetched into its shared-memory slots (margins_prefetch).
+  const double* mg_b[3] = {nullptr, nullptr, nullptr};
+  int mg_s = 1;
+  __device__ __forceinline__ void margins_in_place(int k) {
 #pragma unroll
-    for (int j = 0; j < MMPC_MAX_PLANES; ++j) c[j] = j < npl ? W2(kk, MG + i * cfg.n_pl + j) : 0.0;
+    for (int st = 0; st < 3; ++st) { const int kk = k - 1 + st; mg_b[st] = (kk >= 0 && kk <= N) ? stage_ptr(kk, B2 + MG) : nullptr; }
+    mg_s = 1 << LSH;
+  }
+  // cp.async of the margin caches of NST stages from k-1 on into per-thread slots at dst (6 n_pl slots per stage, stride
+  // bs); one commit group.  The caller waits for it (async_wait) before stale_rows().
+  template <int NST>
+  __device__ __forceinline__ void margins_prefetch(int k, double* dst) {
+    const int nm = 6 * cfg.n_pl;
+    margins_in_place(k);
+#pragma unroll
+    for (int st = 0; st < NST; ++st) {   // (unrolled: mg_b stays in registers)
+      const double* src = mg_b[st];
+      double* d = dst + st * nm * bs;
+      if (src) {
+#pragma unroll 1
+        for (int f = 0; f < nm; ++f) async_copy8(d + f * bs, src + (f << LSH));
+        mg_b[st] = d;
+      }
+    }
+    async_commit();
+    mg_s = bs;
+  }
+  __device__ __forceinline__ void load_margins1(int st, int i, double (&c)[MMPC_MAX_PLANES]) const {
+    const double* p = mg_b[st] + (i * cfg.n_pl) * mg_s;
+#pragma unroll
+    for (int j = 0; j < MMPC_MAX_PLANES; ++j) c[j] = j < npl ? p[j * mg_s] : 0.0;
   }
   __device__ __forceinline__ static void pick_fk(bool first, const FK& a, const FK& b, FK& o) {
     o.cp = first ? a.cp : b.cp; o.sp = first ? a.sp : b.sp;
@@ -497,7 +534,7 @@ struct Inst {
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         double ck[MMPC_MAX_PLANES], cm[MMPC_MAX_PLANES];
-        load_margins1(k, i, ck); load_margins1(k - 1, i, cm);
+        load_margins1(1, i, ck); load_margins1(0, i, cm);
 #pragma unroll 1
         for (int j = 0; j < npl - 1; ++j) {
           const int r = r0 + i * nst + j;
@@ -515,7 +552,7 @@ struct Inst {
             double res = h - s_k + t, dtv = -res - (gd_ - dsk);
             W2(k, S_DT + r) = dtv;
             double itv = rcp(t), dz = (mu - z * (t + dtv)) * itv;
-            io.theta += fabs(res); io.gphi -= mu * dtv * itv; io.logsum += log(t);
+            io.theta += fabs(res); io.gphi -= mu * dtv * itv; io.lp.mul(t);
             if (dtv < 0) io.rp.add(t, -dtv);
             if (dz < 0) io.rd.add(z, -dz);
             continue;
@@ -529,7 +566,7 @@ struct Inst {
             z = zclamp(z + ad * dz, mu, it_);
             W(k, jt + I_T + r) = tt; W(k, jt + I_T + R + r) = z;
             t = tt;
-            if (tt <= 0) io.ok = false; else io.logsum += log(tt);
+            if (tt <= 0) io.ok = false; else io.lp.mul(tt);
           } else it_ = 1.0 / t;
           const double res = h - s_k + t;
           io.theta += fabs(res);
@@ -557,7 +594,7 @@ struct Inst {
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         double ck[MMPC_MAX_PLANES], cn[MMPC_MAX_PLANES];
-        load_margins1(k, i, ck); load_margins1(k + 1, i, cn);
+        load_margins1(1, i, ck); load_margins1(2, i, cn);
 #pragma unroll 1
         for (int j = 0; j < npl - 1; ++j) {
           const int r = r0 + i * nst + j;
@@ -793,6 +830,7 @@ struct Inst {
     double bv[NP] = {0, 0, 0, 0, 0, 0};
     if (REF) {  // compiled out of the clean-mode kernels
       StaleIO io; io.reset(); io.rp.init(); io.rd.init();
+      margins_in_place(k);
       stale_rows<0>(k, A, bv, io);
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
@@ -1197,6 +1235,28 @@ struct Inst {
     int rq = 0;  // next ring item
     auto ring_pop = [&]() -> const double* { async_wait<RING_D - 1>(); return ring_slot(rq); };
     auto ring_next = [&]() { ring_issue(rq + RING_D); ++rq; };
+    // The 29 reference / bound inputs of the stage (IN_XREF .. S_DT) and its FK cache + defect (S_FK .. S_DFC + 9) are parked
+    // in shared memory by one group of copies in front of the ring (so the first ring_pop also waits for it): read one at a
+    // time where they are used, each of those loads exposed a full HBM round trip (34 % of the kernel's stall samples)
+#if defined(MMPC_RESIDENT)
+    const double* pk_in = &c2[IN_XREF]; const double* pk_fk = &c2[S_FK]; constexpr int ps = 1, pf = 1;   // shared memory already
+#else
+    const int ps = STEP_PARK >= 1 ? bs : (1 << LSH), pf = STEP_PARK >= 2 ? bs : (1 << LSH);
+    const double* pk_in = &c2[IN_XREF << LSH]; const double* pk_fk = &c2[S_FK << LSH];
+    if (STEP_PARK >= 1) {
+      double* d = sm + (RING_D * RING_W) * bs;
+#pragma unroll 1
+      for (int f = 0; f < S_DT - IN_XREF; ++f) async_copy8(d + f * bs, &c2[(IN_XREF + f) << LSH]);
+      pk_in = d;
+      if (STEP_PARK >= 2) {
+        d += (S_DT - IN_XREF) * bs;
+#pragma unroll 1
+        for (int f = 0; f < S_PART - S_FK; ++f) async_copy8(d + f * bs, &c2[(S_FK + f) << LSH]);
+        pk_fk = d;
+      }
+      async_commit();
+    }
+#endif
 #pragma unroll
     for (int q = 0; q < RING_D; ++q) ring_issue(q);
     const double os = D(D_OS), mu = D(D_MU);
@@ -1217,7 +1277,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], ldg(&c2[(IN_XREF + i) << LSH]));
+      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], pk_in[i * ps]);
       fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -1242,9 +1302,9 @@ struct Inst {
       const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
       if (k < N) {
         double Rj = os * cfg.Rd[j], Wj = os * cfg.Wd[j];
-        double e = u[j] - ldg(&c2[(IN_UREF + j) << LSH]), dl = u[j] - ldg(&c2[(IN_ULAST + j) << LSH]);
+        double e = u[j] - pk_in[(IN_UREF - IN_XREF + j) * ps], dl = u[j] - pk_in[(IN_ULAST - IN_XREF + j) * ps];
         fsum += Rj * e * e + Wj * dl * dl; gphi += (2 * Rj * e + 2 * Wj * dl) * duv[j];
-        double lo = ldg(&c2[(IN_ULO + j) << LSH]), hi = ldg(&c2[(IN_UHI + j) << LSH]);
+        double lo = pk_in[(IN_ULO - IN_XREF + j) * ps], hi = pk_in[(IN_UHI - IN_XREF + j) * ps];
         if (is_fin(lo)) {
           double d = u[j] - lo, id = rcp(d), z = zl_c, dz = mu * id - z - z * id * duv[j];
           gphi -= mu * duv[j] * id; lp.mul(d);
@@ -1261,12 +1321,18 @@ struct Inst {
     }
     if (k < N) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) theta += fabs(ldg(&c2[(S_DFC + i) << LSH]));
+      for (int i = 0; i < NX; ++i) theta += fabs(pk_fk[(S_DFC - S_FK + i) * pf]);
     }
-    if (term_eq(k)) theta += fabs(x[0] - ldg(&c2[(IN_XREF + 0) << LSH])) + fabs(x[1] - ldg(&c2[(IN_XREF + 1) << LSH]));
-    FK f; f.cp = ldg(&c2[(S_FK + 0) << LSH]); f.sp = ldg(&c2[(S_FK + 1) << LSH]);
+    if (term_eq(k)) theta += fabs(x[0] - pk_in[0]) + fabs(x[1] - pk_in[ps]);
+    FK f; f.cp = pk_fk[0]; f.sp = pk_fk[pf];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { f.vr[q] = ldg(&c2[(S_FK + 2 + q) << LSH]); f.vh[q] = ldg(&c2[(S_FK + 5 + q) << LSH]); }
+    for (int q = 0; q < 3; ++q) { f.vr[q] = pk_fk[(2 + q) * pf]; f.vh[q] = pk_fk[(5 + q) * pf]; }
+#if !defined(MMPC_RESIDENT) && !defined(MMPC_NO_MARGIN_PREFETCH)
+    // (reference NLP) the margin caches of stages k-1 and k for the stale-column rows at the end: prefetched into the parked
+    // slots, which are free from here on, while the rows below are worked through
+    const bool mg_pref = REF && npl >= 2 && k >= 1 && 2 * 6 * cfg.n_pl <= STAGED_STEP_PARKED;
+    if (mg_pref) margins_prefetch<2>(k, sm + (RING_D * RING_W) * bs);
+#endif
     // rows: dt_i = -res_i - (grad h_i . dx - ds)
     double s_cur = s, ds_cur = dsv;  // slack (and its step) the rows are bounded by
     auto row_step = [&](int r, double h, double gd_, double t, double z) {
@@ -1317,8 +1383,13 @@ struct Inst {
     if (REF) {  // compiled out of the clean-mode kernels
       StaleIO io; io.reset(); io.rp = rp; io.rd = rd;
       RowAcc Adummy; double bvdummy[NP];   // phase 2 touches neither
+#if defined(MMPC_RESIDENT) || defined(MMPC_NO_MARGIN_PREFETCH)
+      margins_in_place(k);
+#else
+      if (mg_pref) async_wait<0>(); else margins_in_place(k);
+#endif
       stale_rows<2>(k, Adummy, bvdummy, io);
-      theta += io.theta; gphi += io.gphi; log_extra = io.logsum; rp = io.rp; rd = io.rd;
+      theta += io.theta; gphi += io.gphi; log_extra = io.lp.value(); rp = io.rp; rd = io.rd;
     }
     c2[(S_PART + 0) << LSH] = rp.value(tau); c2[(S_PART + 1) << LSH] = rd.value(tau); c2[(S_PART + 2) << LSH] = gphi; c2[(S_PART + 3) << LSH] = theta;
     c2[(S_PART + 4) << LSH] = fsum; c2[(S_PART + 5) << LSH] = lp.value() + log_extra;
@@ -1697,6 +1768,13 @@ struct Inst {
       }
       Qw(k, Q_HUU + j) = Hd; Qw(k, Q_GA + SGY_U + j) = gA; Qw(k, Q_GB + SGY_U + j) = gB;
     }
+#if !defined(MMPC_RESIDENT) && !defined(MMPC_NO_MARGIN_PREFETCH)
+    // (reference NLP) the margin caches of stages k-1, k, k+1 for the stale-column rows at the end: prefetched into the slots
+    // of the parked multipliers and inputs, which are free from here on, while the rows below are worked through (the
+    // margin loads of stale_rows() were 10 % of the kernel's stall samples)
+    const bool mg_pref = REF && npl >= 2 && 3 * 6 * cfg.n_pl <= (I_T - I_ZXL) + (S_DT - IN_XREF);
+    if (mg_pref) margins_prefetch<3>(k, sm + (RING_DT * RING_W) * bs);
+#endif
     // one slack row  h - s + t = 0 : candidate (t, z) with slack reset, merit and KKT bookkeeping
     double s_cur = s;  // slack the rows are bounded by (s[N-1] for the terminal self-collision rows of the literal reference NLP)
     auto row_core = [&](int r, double h, double t, double dtv, double& z, double& it_, double& res) {  // z: in = current multiplier
@@ -1800,8 +1878,13 @@ struct Inst {
     double bv[NP] = {0, 0, 0, 0, 0, 0}, log_extra = 0;
     if (REF) {  // compiled out of the clean-mode kernels
       StaleIO io; io.reset(); io.rp.init(); io.rd.init();
+#if defined(MMPC_RESIDENT) || defined(MMPC_NO_MARGIN_PREFETCH)
+      margins_in_place(k);
+#else
+      if (mg_pref) async_wait<0>(); else margins_in_place(k);
+#endif
       stale_rows<1>(k, A, bv, io);
-      theta += io.theta; log_extra = io.logsum; ok = ok && io.ok;
+      theta += io.theta; log_extra = io.lp.value(); ok = ok && io.ok;
     }
     // slack column of the stage Hessian: H[s][s] = 2S + sum sigma, H[pose][s] = -sum sigma grad h
     double S2 = 2 * os * cfg.S;
@@ -1926,7 +2009,7 @@ template <bool REF>
 __device__ inline void body_eval(const SParams& P, int j, int k) { Inst S(P, list_E(P)[j]); S.template eval<REF>(k); }
 __device__ inline void body_solve(const SParams& P, int j) { Inst S(P, list_E(P)[j]); S.solve(); }
 // doubles of shared memory one thread of the step / trial kernels needs for its row ring
-constexpr int STAGED_RING_DOUBLES = Inst::RING_D * Inst::RING_W;
+constexpr int STAGED_RING_DOUBLES = Inst::RING_D * Inst::RING_W + STAGED_STEP_PARKED;  // row ring + parked stage inputs, FK cache and defect
 constexpr int STAGED_TRIAL_RING_DOUBLES = Inst::RING_DT * Inst::RING_W + (I_T - I_ZXL) + (S_DT - IN_XREF);  // row ring + 28 bound multipliers + 29 stage inputs
 template <bool REF>
 __device__ inline void body_step(const SParams& P, int j, int k, double* sm, int bs) {

@@ -36,8 +36,21 @@ __device__ __forceinline__ int ldg(const int* p) { return __ldg(p); }
 #endif
 // teams: the two 16-lane halves of a warp run in lock step (full-warp mask, width-16 shuffles): half-warp
 // masks make the hardware issue every shuffle once per team (measured: 17.5 of 32 lanes active)
+// (the halves of a double go through the non-volatile conversion intrinsics: CUDA's own __shfl_sync(double) splits and joins
+// them with `asm volatile mov.b64`, which ptxas keeps as real moves -- 12 % of the team kernel's instructions)
+#ifdef MMPC_SHFL_PLAIN
 __device__ __forceinline__ double shfl16(double v, int src) { return __shfl_sync(FULL, v, src, 16); }
 __device__ __forceinline__ double shfl16_xor(double v, int m) { return __shfl_xor_sync(FULL, v, m, 16); }
+#else
+__device__ __forceinline__ double shfl16(double v, int src) {
+  const int lo = __shfl_sync(FULL, __double2loint(v), src, 16), hi = __shfl_sync(FULL, __double2hiint(v), src, 16);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl16_xor(double v, int m) {
+  const int lo = __shfl_xor_sync(FULL, __double2loint(v), m, 16), hi = __shfl_xor_sync(FULL, __double2hiint(v), m, 16);
+  return __hiloint2double(hi, lo);
+}
+#endif
 __device__ __forceinline__ void team_sync() { __syncwarp(); }
 __device__ __forceinline__ bool warp_all(bool p) { return __all_sync(FULL, p); }
 #ifdef MMPC_RESIDENT
