@@ -257,6 +257,10 @@ int mmpc_workspace_bytes(const MmpcHandle* h, int64_t* bytes);
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t mmpc_launch_count(const MmpcHandle* h);
 
+/* Which execution strategy the last mmpc_solve of this handle took: MMPC_KERNEL_RESIDENT or MMPC_KERNEL_STAGED (any of the
+ * staged variants); MMPC_KERNEL_AUTO before the first solve. */
+int mmpc_last_solver(const MmpcHandle* h);
+
 /* sizeof() of the three ABI structs, for binding self-checks. */
 int mmpc_struct_sizes(int32_t* cfg_bytes, int32_t* in_bytes, int32_t* out_bytes);
 

@@ -73,6 +73,7 @@ def lib():
     L.mmpc_episode_update.argtypes = [vp, i32, i32, i32, C.POINTER(_abi.MmpcEpisodeIO), vp]
     L.mmpc_launch_count.argtypes = [vp]
     L.mmpc_launch_count.restype = i64
+    L.mmpc_last_solver.argtypes = [vp]
     L.mmpc_occupancy.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.mmpc_bench_fp64.argtypes = [i32, C.POINTER(C.c_double)]
     a, b, c = i32(), i32(), i32()
@@ -90,4 +91,4 @@ def check(rc):
 
 EXPORTS = ("mmpc_version", "mmpc_error_string", "mmpc_default_config", "mmpc_create", "mmpc_destroy",
            "mmpc_set_weights", "mmpc_set_kernel", "mmpc_set_profile", "mmpc_phase_times", "mmpc_workspace_bytes", "mmpc_solve", "mmpc_solve_host", "mmpc_eval_model", "mmpc_shift",
-           "mmpc_plant_step", "mmpc_window", "mmpc_ik", "mmpc_episode_update", "mmpc_launch_count", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")
+           "mmpc_plant_step", "mmpc_window", "mmpc_ik", "mmpc_episode_update", "mmpc_launch_count", "mmpc_last_solver", "mmpc_struct_sizes", "mmpc_occupancy", "mmpc_bench_fp64")

@@ -99,6 +99,10 @@ class BatchSolver:
     def launch_count(self):
         return int(lib().mmpc_launch_count(self._h))
 
+    def last_solver(self):
+        """'resident' or 'staged': what the last solve ran on (AUTO picks by batch size); None before the first solve."""
+        return {_abi.KERNEL_RESIDENT: "resident", _abi.KERNEL_STAGED: "staged"}.get(int(lib().mmpc_last_solver(self._h)))
+
     # -- weights: MPCWholeBody.setWeight (:119-139) ----------------------------------------------
     def set_weights(self, Q=None, R=None, P=None, S=None, W=None):
         ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)

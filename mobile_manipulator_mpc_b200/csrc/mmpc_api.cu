@@ -36,6 +36,7 @@ struct MmpcHandle {
   int autosel;   // MMPC_KERNEL_AUTO: resident for small batches, staged otherwise
   int smem_optin; // largest dynamic shared memory of a block on this device
   unsigned* queue;  // work queue counter of the resident kernel
+  int last_solver;  // MMPC_KERNEL_RESIDENT / MMPC_KERNEL_STAGED: what the last solve ran on
   // per-phase device timing of the staged solver (mmpc_set_profile / mmpc_phase_times)
   int profile;
   std::vector<cudaEvent_t>* prof_ev;
@@ -532,8 +533,10 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "resident kernel launch failed: %s", cudaGetErrorString(e)); return MMPC_ERR_CUDA; }
     h->launches += 2;
     h->sg.rounds = 0;
+    h->last_solver = MMPC_KERNEL_RESIDENT;
     return MMPC_OK;
   }
+  h->last_solver = MMPC_KERNEL_STAGED;
   static const bool force_hostloop = getenv("MMPC_HOSTLOOP") && atoi(getenv("MMPC_HOSTLOOP")) != 0;
   // (the unfused A/B variant evaluates in every round: host loop only)
   if (h->profile || force_hostloop || h->hostloop || !h->sg_fused) return launch_staged_hostloop(h, B, st);
@@ -824,6 +827,8 @@ extern "C" int64_t mmpc_launch_count(const MmpcHandle* h) {
   graph_account(const_cast<MmpcHandle*>(h));  // rounds of the last graph solve (the caller has synchronised its stream)
   return h->launches;
 }
+
+extern "C" int mmpc_last_solver(const MmpcHandle* h) { return h ? h->last_solver : MMPC_KERNEL_AUTO; }
 
 extern "C" int mmpc_occupancy(const MmpcHandle* h, int32_t* sm_count, int32_t* blocks_per_sm, int32_t* smem_bytes) {
   if (!h) return MMPC_ERR_ARG;
