@@ -149,6 +149,58 @@ def cpu_baseline(batch, sample, threads, nlp):
     return conv / dt, conv, dt, o
 
 
+def demo_episode_latency(mode, device, nlp, with_cpu=True):
+    """BASELINE config 1 in its natural habitat: the 198 MPCWholeBody.solve calls the reference's own Interface made in its demo
+    episode (scenario 1; recorded by tests/golden/make_interface_golden.py with the unmodified interface_wholebody_qref.py), each
+    solved alone (B = 1) with the recorded inputs, weights and warm start.  Latency per call on the GPU (device-resident
+    inputs, CUDA events) and through the host API (mmpc_solve_host), and of the CPU port on one core on the same calls."""
+    import torch
+    from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    from mobile_manipulator_mpc_b200 import scenarios
+    g = np.load(os.path.join(ROOT, "tests", "golden", "interface_demo1.npz"))
+    _, _, planes = scenarios.demo_scenario(1)
+    n = len(g["call_cost"])
+    N, dt = int(g["N"]), float(g["dt"])
+    S = BatchSolver(N=N, dt=dt, n_obs=3, n_pl=3, B_max=1, device=device, mode=mode)
+
+    def call(i):
+        return dict(N=N, dt=dt, n_obs=3, n_pl=3, obs_per_stage=0, x_init=g["call_x_init"][i][None], x_ref=g["call_x_ref"][i][None],
+                    u_ref=g["call_u_ref"][i][None], u_last=g["call_u_last"][i][None], circles=scenarios.DEMO_CIRCLES[None].copy(),
+                    planes=planes[None].copy(), n_pl_inst=np.full(1, 3, np.int32), flags=np.full(1, int(g["call_flag"][i]), np.uint8))
+    dev_ms, host_ms, iters, ok = [], [], [], 0
+    out = None
+    for rep in range(2):   # first pass warms up
+        dev_ms, host_ms, iters, ok = [], [], [], 0
+        for i in range(n):
+            if i == 0 or not np.array_equal(g["call_Qd"][i], g["call_Qd"][i - 1]):
+                S.set_weights(Q=np.diag(g["call_Qd"][i]), P=np.diag(g["call_Pd"][i]))
+            b = call(i)
+            d = S.to_device(b)
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); out = S.solve_device(d, out=out); e.record(); torch.cuda.synchronize()
+            dev_ms.append(a.elapsed_time(e))
+            t = time.perf_counter(); oh = S.solve_host(b); host_ms.append((time.perf_counter() - t) * 1e3)
+            iters.append(int(oh["iters"][0])); ok += int(oh["status"][0] == 0)
+            assert abs(float(oh["cost"][0]) - float(g["call_cost"][i])) <= 1e-5 * max(1e-12, abs(float(g["call_cost"][i]))), i
+    res = dict(calls=n, converged=ok, solver=S.last_solver(), mean_iterations=float(np.mean(iters)), median_iterations=float(np.median(iters)),
+               device_p50_ms=float(np.median(dev_ms)), device_p99_ms=float(np.percentile(dev_ms, 99)), device_mean_ms=float(np.mean(dev_ms)),
+               host_api_p50_ms=float(np.median(host_ms)), host_api_p99_ms=float(np.percentile(host_ms, 99)), host_api_mean_ms=float(np.mean(host_ms)),
+               ms_per_iteration=float(np.sum(dev_ms) / np.sum(iters)),
+               note="every call's optimal cost equals the recorded one to 1e-5 relative (asserted)")
+    S.close()
+    if with_cpu:
+        from oracle import solver as osolver
+        osolver.lib()
+        cpu_ms = []
+        for i in range(n):
+            b = call(i)
+            cfg = osolver.config_from_batch(b, mode)
+            cfg.Qd[:] = list(g["call_Qd"][i]); cfg.Pd[:] = list(g["call_Pd"][i])
+            t = time.perf_counter(); osolver.solve(b, cfg=cfg, mode=mode, threads=1); cpu_ms.append((time.perf_counter() - t) * 1e3)
+        res.update(cpu_port_p50_ms=float(np.median(cpu_ms)), cpu_port_p99_ms=float(np.percentile(cpu_ms, 99)), cpu_port_mean_ms=float(np.mean(cpu_ms)))
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference path on the host cores.  CasADi/IPOPT cannot be installed in this image (no wheel, no
     network), so this arm times the oracle port -- the same interior-point algorithm on the same NLP -- with every host thread."""
@@ -370,6 +422,9 @@ def run_batched(args):
             l1.append(a.elapsed_time(b))
         lat1 = dict(p50_ms=float(np.median(l1)), p99_ms=float(np.percentile(l1, 99)), iterations=int(o1["iters"][0]))
         S1.close()
+    demo = None
+    if rank == 0 and cid == 1:
+        demo = demo_episode_latency(mode, local, nlp, with_cpu=not args.no_cpu_baseline)
     # side figure: the same batch as the other NLP variant, one context, two timed solves
     other = None
     if rank == 0 and not args.no_side:
@@ -469,7 +524,7 @@ def run_batched(args):
                                 converged_fraction=conv_all / solved_all, mean_iterations=iters_all / solved_all,
                                 status_histogram={n: int(v) for n, v in zip(STATUS_NAMES, hh.tolist())},
                                 rounds=rounds, single_context_ms_per_step=step_ms,
-                                p50_batched_solve_latency_ms=step_ms, single_instance_latency=lat1, other_nlp=other,
+                                p50_batched_solve_latency_ms=step_ms, single_instance_latency=lat1, demo_episode_latency=demo, other_nlp=other,
                                 single_context_value=conv0 / (step_ms * 1e-3), wall_ms_timed_region=wall_ms),
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
