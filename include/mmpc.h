@@ -77,7 +77,12 @@ enum {
  *              controls are unbounded, carry a unit control weight and no state weight, so they stay at their initial
  *              values and do not interact with the base (no FK row exists: no self-collision rows, n_pl must be 0, mode
  *              MMPC_MODE_CLEAN).  S plays the role of M.  Host class: mobile_manipulator_mpc_b200/controllers/mpc_base.py. */
-enum { MMPC_MODEL_WHOLEBODY = 0, MMPC_MODEL_BASE = 1 };
+enum { MMPC_MODEL_WHOLEBODY = 0, MMPC_MODEL_BASE = 1,
+       MMPC_MODEL_POSEREF = 2   /* controllers/mpc_wholebody.py:49-128: the whole-body model with the tracking cost on the END-POINT
+                                   POSE (x, y, z, psi) = forward_tranformation(x)[0] instead of on the state; circle rows only (no
+                                   self-collision rows, n_pl must be 0).  x_ref[B, N+1, 9] carries the pose reference in its first
+                                   four columns, Qd[0..3] / Pd[0..3] are the pose weights (the other entries must be 0), x_guess
+                                   warm-starts X (:138-141).  Runs on the resident kernel (any batch size) */ };
 
 /* execution strategy of mmpc_solve (same algorithm, same results to the bit):
  *   STAGED   batch-synchronous rounds of phase kernels over compacted lists of active instances (stage-parallel

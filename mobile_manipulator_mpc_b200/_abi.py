@@ -14,7 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_LINESEARCH, STATUS_FACTOR, STATUS_NAN, STATUS_ACCEPTABLE = range(6)
 STATUS_NAMES = ("converged", "max_iter", "linesearch", "factor", "nan", "acceptable")
 MODE_REFERENCE, MODE_CLEAN = 0, 1
-MODEL_WHOLEBODY, MODEL_BASE = 0, 1
+MODEL_WHOLEBODY, MODEL_BASE, MODEL_POSEREF = 0, 1, 2
 KERNEL_AUTO, KERNEL_STAGED, KERNEL_STAGED_THREAD, KERNEL_STAGED_UNFUSED, KERNEL_STAGED_FAT, KERNEL_STAGED_HOSTLOOP, KERNEL_RESIDENT = 0, 3, 4, 5, 6, 7, 8
 
 _d = C.c_double

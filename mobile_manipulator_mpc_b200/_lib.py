@@ -12,7 +12,7 @@ from . import _abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMPC_LIB") or os.path.join(_PKG, "libmmpc_b200.so")  # MMPC_LIB: A/B builds of the same sources
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_resident.cu", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_parts.cuh", "mmpc_episode.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("mmpc_api.cu", "mmpc_resident.cu", "mmpc_resident_pose.cu", "mmpc_staged.cuh", "mmpc_team.cuh", "mmpc_parts.cuh", "mmpc_episode.cuh", "mmpc_ipm.cuh", "mmpc_model.cuh", "mmpc_warp.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -31,9 +31,9 @@ def build_library(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("MMPC_NVCC_EXTRA", "").split()   # A/B builds: -D switches
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + extra
-    # two translation units (staged + resident), compiled side by side, then linked
-    objs = [LIB_PATH + "." + os.path.basename(s)[:-3] + ".o" for s in SOURCES[:2]]
-    procs = [subprocess.Popen([nvcc] + flags + ["-c", "-o", o, s], cwd=os.path.join(_PKG, "csrc")) for o, s in zip(objs, SOURCES[:2])]
+    # three translation units (staged, resident, resident with the pose-reference cost), compiled side by side, then linked
+    objs = [LIB_PATH + "." + os.path.basename(s)[:-3] + ".o" for s in SOURCES[:3]]
+    procs = [subprocess.Popen([nvcc] + flags + ["-c", "-o", o, s], cwd=os.path.join(_PKG, "csrc")) for o, s in zip(objs, SOURCES[:3])]
     for pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, pr.args)

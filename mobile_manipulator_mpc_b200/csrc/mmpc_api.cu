@@ -20,6 +20,9 @@ using namespace mmpc;
 // csrc/mmpc_resident.cu (its own translation unit: the same phase bodies compiled for a shared-memory workspace)
 extern "C" int mmpc_resident_smem_bytes(const MmpcConfig* cfg);
 extern "C" int mmpc_resident_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream);
+// csrc/mmpc_resident_pose.cu (the same kernel with the end-point pose cost of MMPC_MODEL_POSEREF compiled in)
+extern "C" int mmpc_resident_pose_smem_bytes(const MmpcConfig* cfg);
+extern "C" int mmpc_resident_pose_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream);
 
 struct MmpcHandle {
   MmpcConfig cfg;
@@ -107,7 +110,9 @@ extern "C" int mmpc_create(const MmpcConfig* cfg, int32_t B_max, int32_t device,
   if (!cfg || !out || B_max < 1) return MMPC_ERR_ARG;
   if (cfg->N < 1 || cfg->N > 63 || cfg->n_obs < 0 || cfg->n_pl < 0 || cfg->n_pl > MMPC_MAX_PLANES) return MMPC_ERR_ARG;
   if (cfg->mode != MMPC_MODE_CLEAN && cfg->mode != MMPC_MODE_REFERENCE) return MMPC_ERR_ARG;
-  if (cfg->model != MMPC_MODEL_WHOLEBODY && cfg->model != MMPC_MODEL_BASE) return MMPC_ERR_ARG;
+  if (cfg->model != MMPC_MODEL_WHOLEBODY && cfg->model != MMPC_MODEL_BASE && cfg->model != MMPC_MODEL_POSEREF) return MMPC_ERR_ARG;
+  // the pose-reference controller (controllers/mpc_wholebody.py) has ground circles only; it runs on the resident kernel
+  if (cfg->model == MMPC_MODEL_POSEREF && (cfg->n_pl != 0 || cfg->mode != MMPC_MODE_CLEAN)) return MMPC_ERR_UNSUPPORTED;
   // the base-only controller (controllers/mpc_base.py) has no arm: no plane rows, no bug-for-bug rows
   if (cfg->model == MMPC_MODEL_BASE && (cfg->n_pl != 0 || cfg->mode != MMPC_MODE_CLEAN)) return MMPC_ERR_UNSUPPORTED;
   // the literal reference NLP bounds the terminal self-collision rows by s[N-1]: the starting point relies on x_N = x_{N-1},
@@ -526,10 +531,12 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   // 2,048 50.4 / 51.5 -- the staged solver's floor is the launch latency of its ~270 rounds, the resident kernel's slope is
   // one instance (two at a time) per SM.  MMPC_AUTO_RESIDENT = largest batch, in instances per SM, AUTO sends there (0: never).
   static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 10;
-  const bool fits = mmpc_resident_smem_bytes(&h->cfg) <= h->smem_optin;
-  if (!h->profile && h->sg_fused && fits && (h->resident || (h->autosel && (long long)B <= (long long)auto_resident * h->sm_count))) {
+  const bool pose = h->cfg.model == MMPC_MODEL_POSEREF;   // compiled into the pose build of the resident kernel only
+  const bool fits = (pose ? mmpc_resident_pose_smem_bytes(&h->cfg) : mmpc_resident_smem_bytes(&h->cfg)) <= h->smem_optin;
+  if (pose && !fits) { snprintf(g_err, sizeof g_err, "MMPC_MODEL_POSEREF runs on the resident kernel; this horizon does not fit in shared memory"); return MMPC_ERR_UNSUPPORTED; }
+  if (pose || (!h->profile && h->sg_fused && fits && (h->resident || (h->autosel && (long long)B <= (long long)auto_resident * h->sm_count)))) {
     CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned), st));
-    cudaError_t e = (cudaError_t)mmpc_resident_launch(&h->cfg, B, h->sg.io, h->queue, h->sm_count, st);
+    cudaError_t e = (cudaError_t)(pose ? mmpc_resident_pose_launch : mmpc_resident_launch)(&h->cfg, B, h->sg.io, h->queue, h->sm_count, st);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "resident kernel launch failed: %s", cudaGetErrorString(e)); return MMPC_ERR_CUDA; }
     h->launches += 2;
     h->sg.rounds = 0;

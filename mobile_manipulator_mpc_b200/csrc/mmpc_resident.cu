@@ -156,9 +156,18 @@ __device__ inline void init_pass_a(Inst& S, const InPtr& q, int k) {
     double xr = q.xref[k * NX + i];
     x[i] = v; S.W(k, I_X + i) = v; S.W(k, I_LAM + i) = 0; S.W2(k, IN_XREF + i) = xr;
     S.W(k, I_ZXL + i) = 1; S.W(k, I_ZXU + i) = 1;
-    double Wx = (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+    double Wx = S.xweight(k, i);
     if (k >= 1) gmax = fmax(gmax, fabs(2 * Wx * S.xerr(i, v, xr)));
   }
+#ifdef MMPC_POSEREF
+  if (S.pose_model() && k >= 1) {   // gradient of the end-point pose cost at the starting point (objective scaling)
+    FK fp; fk_eval(x[2], x[6], x[7], x[8], fp);
+    const double r[4] = {q.xref[k * NX + 0], q.xref[k * NX + 1], q.xref[k * NX + 2], q.xref[k * NX + 3]};
+    double g[NP];
+    S.pose_cost(k, 1.0, x[0], x[1], x[2], fp, r, g, nullptr);
+    for (int a = 0; a < NP; ++a) gmax = fmax(gmax, fabs(g[a]));
+  }
+#endif
   if (k < N) {
 #pragma unroll
     for (int j = 0; j < NU; ++j) {

@@ -124,8 +124,9 @@ constexpr int NPART = 8;
 __host__ __device__ inline int staged_stale_rows(const MmpcConfig& c) {
   return (c.mode == MMPC_MODE_REFERENCE && c.n_pl > 1) ? 6 * (c.n_pl - 1) : 0;
 }
-// self-collision rows of a stage: 4, none in the base-only model (controllers/mpc_base.py has no arm)
-__host__ __device__ inline int staged_self_rows(const MmpcConfig& c) { return c.model == MMPC_MODEL_BASE ? 0 : 4; }
+// self-collision rows of a stage: 4; none in the base-only model (controllers/mpc_base.py has no arm) and in the pose-reference
+// model (controllers/mpc_wholebody.py:100 "onstacles 3D: TODO")
+__host__ __device__ inline int staged_self_rows(const MmpcConfig& c) { return c.model == MMPC_MODEL_WHOLEBODY ? 4 : 0; }
 __host__ __device__ inline int staged_rows(const MmpcConfig& c) { return c.n_obs + staged_self_rows(c) + (c.n_pl > 0 ? 6 : 0) + staged_stale_rows(c); }
 __host__ __device__ inline int staged_itsz(const MmpcConfig& c) { return I_T + 2 * staged_rows(c); }
 // MMPC_MODE_REFERENCE: the plane margins c[i][j] of the stage's six body points (6 x n_pl, i-major), written once per
@@ -199,6 +200,56 @@ struct Inst {
   __device__ __forceinline__ double xerr(int i, double x, double xr) const {
     return (i == 2 && cfg.model == MMPC_MODEL_BASE) ? angle_diff(x, xr) : x - xr;
   }
+  // MMPC_MODEL_POSEREF (controllers/mpc_wholebody.py:79-86, :104-107; compiled into the pose build of the resident kernel only,
+  // mmpc_resident_pose.cu): the tracking cost is  e^T diag(W) e  on the end-point pose  e = forward_tranformation(x)[0] - X_ref[k]
+  // = (P_e - r_xyz, psi - r_psi), W = Qd[0..3] (Pd at k = N); the states carry no tracking weight of their own.
+#ifdef MMPC_POSEREF
+  __device__ __forceinline__ bool pose_model() const { return cfg.model == MMPC_MODEL_POSEREF; }
+#else
+  __device__ __forceinline__ constexpr bool pose_model() const { return false; }
+#endif
+  __device__ __forceinline__ double xweight(int k, int i) const { return pose_model() ? 0.0 : (k < N ? cfg.Qd[i] : cfg.Pd[i]); }
+#ifdef MMPC_POSEREF
+  // value of the pose cost of stage k (weights times `scale`), its gradient g wrt the pose (x, y, psi, q1, q2, q3) and -- if H
+  // is given -- its exact Hessian added to the packed pose block H[21]:  2 J^T W J + sum_c 2 W_c e_c Hess(P_c)
+  __device__ __forceinline__ double pose_cost(int k, double scale, double px, double py, double psi, const FK& f, const double (&r)[4],
+                                              double (&g)[NP], double* H) const {
+    const double* Wv = k < N ? cfg.Qd : cfg.Pd;
+    Point p; point_eval(px, py, f, BODY[5], p);   // the end point
+    double n[3], val = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const double e = p.P[c] - r[c], w = scale * Wv[c]; n[c] = 2 * w * e; val += w * e * e; }
+    const double ep = psi - r[3], w3 = scale * Wv[3];
+    val += w3 * ep * ep;
+    point_grad(f, p, n, g);
+    g[2] += 2 * w3 * ep;
+    if (H) {
+      point_hess_acc(f, p, n, 1.0, H);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double u[3] = {c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0};
+        double gc[NP]; point_grad(f, p, u, gc);
+        const double w2 = 2 * scale * Wv[c];
+#pragma unroll
+        for (int a = 0; a < NP; ++a)
+#pragma unroll
+          for (int b = a; b < NP; ++b) H[pidx(a, b)] += w2 * gc[a] * gc[b];
+      }
+      H[pidx(2, 2)] += 2 * w3;
+    }
+    return val;
+  }
+#endif
+#ifdef MMPC_POSEREF
+  // unscaled pose cost of stage k at the iterate `it` (results: sol.value of the objective)
+  __device__ __forceinline__ double pose_cost_value(int k, int it) const {
+    const double px = W(k, it + I_X + 0), py = W(k, it + I_X + 1), psi = W(k, it + I_X + 2);
+    FK f; fk_eval(psi, W(k, it + I_X + 6), W(k, it + I_X + 7), W(k, it + I_X + 8), f);
+    const double r[4] = {W2(k, IN_XREF + 0), W2(k, IN_XREF + 1), W2(k, IN_XREF + 2), W2(k, IN_XREF + 3)};
+    double g[NP];
+    return pose_cost(k, 1.0, px, py, psi, f, r, g, nullptr);
+  }
+#endif
   int MG;  // offset (second block) of the plane-margin cache of a stage, see staged_marg_doubles
   __device__ __forceinline__ double& W(int k, int o) const { return w[(k * STG + o) << LSH]; }
   __device__ __forceinline__ double& W2(int k, int o) const { return w[(k * STG + B2 + o) << LSH]; }
@@ -296,7 +347,7 @@ struct Inst {
         double xr = ldg(xref + k * NX + i);
         x[i] = v; W(k, I_X + i) = v; W(k, I_LAM + i) = 0; W2(k, IN_XREF + i) = xr;
         W(k, I_ZXL + i) = 1; W(k, I_ZXU + i) = 1;
-        double Wx = (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+        double Wx = xweight(k, i);
         if (k >= 1) gmax = fmax(gmax, fabs(2 * Wx * xerr(i, v, xr)));
       }
       if (k < N) {
@@ -708,7 +759,7 @@ struct Inst {
     // others are final here.
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+      double Wx = os * xweight(k, i);
       double gr = 2 * Wx * xerr(i, x[i], W2(k, IN_XREF + i));
       double Hd = 2 * Wx, gA = gr, gB = 0, st = gr + stx[i] - lam[i];
       if (k >= 1) {
@@ -737,6 +788,15 @@ struct Inst {
         if (k >= 1) es = fmax(es, fabs(st));
       }
     }
+#ifdef MMPC_POSEREF
+    if (pose_model()) {  // the end-point pose cost: gradient and exact Hessian into the pose block
+      const double r[4] = {W2(k, IN_XREF + 0), W2(k, IN_XREF + 1), W2(k, IN_XREF + 2), W2(k, IN_XREF + 3)};
+      double g[NP];
+      pose_cost(k, os, x[0], x[1], x[2], f, r, g, A.H);
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { A.gA[a] += g[a]; A.st[a] += g[a]; }
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
       double Hd = 0, gA = 0, gB = 0;
@@ -1149,9 +1209,12 @@ struct Inst {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         double v = W(k, it + I_X + i), e = xerr(i, v, W2(k, IN_XREF + i));
-        fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
+        fsum += xweight(k, i) * e * e;
         if (P.io->X) P.io->X[((long long)bio * (N + 1) + k) * NX + i] = v;
       }
+#ifdef MMPC_POSEREF
+      if (pose_model()) fsum += pose_cost_value(k, it);
+#endif
       if (k < N)
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
@@ -1277,7 +1340,7 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       const double* rb = ring_pop(); const double zl_c = rb[0], zu_c = rb[bs]; ring_next();
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], pk_in[i * ps]);
+      double Wx = os * xweight(k, i), e = xerr(i, x[i], pk_in[i * ps]);
       fsum += Wx * e * e; gphi += 2 * Wx * e * dxv[i];
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -1327,6 +1390,15 @@ struct Inst {
     FK f; f.cp = pk_fk[0]; f.sp = pk_fk[pf];
 #pragma unroll
     for (int q = 0; q < 3; ++q) { f.vr[q] = pk_fk[(2 + q) * pf]; f.vh[q] = pk_fk[(5 + q) * pf]; }
+#ifdef MMPC_POSEREF
+    if (pose_model()) {  // the end-point pose cost: value and directional derivative along the step
+      const double r[4] = {pk_in[0], pk_in[ps], pk_in[2 * ps], pk_in[3 * ps]};
+      double g[NP];
+      fsum += pose_cost(k, os, x[0], x[1], x[2], f, r, g, nullptr);
+#pragma unroll
+      for (int a = 0; a < NP; ++a) gphi = fma(g[a], dp[a], gphi);
+    }
+#endif
 #if !defined(MMPC_RESIDENT) && !defined(MMPC_NO_MARGIN_PREFETCH)
     // (reference NLP) the margin caches of stages k-1 and k for the stale-column rows at the end: prefetched into the parked
     // slots, which are free from here on, while the rows below are worked through
@@ -1404,9 +1476,12 @@ struct Inst {
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double v = W(k, it + I_X + i), e = xerr(i, v, W2(k, IN_XREF + i));
-      fsum += (k < N ? cfg.Qd[i] : cfg.Pd[i]) * e * e;
+      fsum += xweight(k, i) * e * e;
       if (P.io->X) P.io->X[((long long)bio * (N + 1) + k) * NX + i] = v;
     }
+#ifdef MMPC_POSEREF
+    if (pose_model()) fsum += pose_cost_value(k, it);
+#endif
     if (k < N)
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
@@ -1485,7 +1560,7 @@ struct Inst {
         double l = W(k, it + I_LAM + i);
         W(k, jt + I_LAM + i) = l + alpha * (W2(k, S_LAMN + i) - l);
       }
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]), e = xerr(i, x[i], W2(k, IN_XREF + i));
+      double Wx = os * xweight(k, i), e = xerr(i, x[i], W2(k, IN_XREF + i));
       fsum += Wx * e * e;
       if (k >= 1) {
         double lo = cfg.xlim[0][i], hi = cfg.xlim[1][i];
@@ -1716,7 +1791,7 @@ struct Inst {
     async_wait<RING_DT>();  // the bound multipliers have landed (the row ring's RING_DT groups were committed after them)
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double Wx = os * (k < N ? cfg.Qd[i] : cfg.Pd[i]);
+      double Wx = os * xweight(k, i);
       double e = xerr(i, x[i], rb_in[(IN_XREF - IN_XREF + i) * ps]);
       fsum += Wx * e * e;
       double gr = 2 * Wx * e;
@@ -1744,6 +1819,15 @@ struct Inst {
         if (k >= 1) es = fmax(es, fabs(st));
       }
     }
+#ifdef MMPC_POSEREF
+    if (pose_model()) {  // the end-point pose cost at the candidate: value, gradient and exact Hessian into the pose block
+      const double r[4] = {rb_in[0], rb_in[ps], rb_in[2 * ps], rb_in[3 * ps]};
+      double g[NP];
+      fsum += pose_cost(k, os, x[0], x[1], x[2], f, r, g, A.H);
+#pragma unroll
+      for (int a = 0; a < NP; ++a) { A.gA[a] += g[a]; A.st[a] += g[a]; }
+    }
+#endif
     fsum += os * cfg.S * s * s;
 #pragma unroll
     for (int j = 0; j < NU; ++j) {

@@ -234,3 +234,30 @@ def make_base_batch(B, N=10, seed=6, n_obs=3, dt=0.1):
     urows = np.minimum(j0[:, None] + np.arange(N)[None, :], 49)
     circ = np.tile(DEMO_CIRCLES, (B, 1, 1)) if n_obs == 3 else _random_circles(rng, x0[:, :2], n_obs)
     return dict(N=N, dt=dt, n_obs=n_obs, x_init=x0, x_ref=ref[rows].copy(), u_ref=uref[urows].copy(), circles=circ)
+
+
+POSE_XLIM = np.array([[-100, -100, -np.inf, -2, -2, -PI, -PI / 2, -PI * 3 / 4, 0],
+                      [100, 100, np.inf, 2, 2, PI, PI / 2, 0, PI]])            # controllers/mpc_wholebody.py:17-20
+
+
+def make_pose_batch(B, N=10, seed=8, n_obs=3, dt=0.1):
+    """Instances of the pose-reference whole-body controller (controllers/mpc_wholebody.py): x_init [B,9],
+    x_ref [B,N+1,9] with the END-POINT pose reference (x, y, z, psi) in the first four columns (the rest zero), u_ref [B,N,5],
+    u_last [B,N,5], circles [B,n_obs,3].  The pose reference is the end-point pose along a straight-line plan of the state from a
+    perturbed start towards a goal near the demo's table, so it is reachable; circles: the demo's three or n_obs random ones."""
+    from .robot_models import MobileManipulator
+    rng = np.random.default_rng(seed)
+    x_start = np.array([0, 0, 0, 0, 0, 0, -PI / 4, -PI / 2, PI / 2])
+    x_goal = np.array([4.0, 4.5, 0.8, 0, 0, 0, 0.2, -1.2, 0.9])
+    plan = np.linspace(x_start, x_goal, 51)
+    i0 = rng.integers(0, 31, size=B)
+    x0 = plan[i0] + rng.uniform(-0.2, 0.2, size=(B, 9)) * np.array([1, 1, 1, 0.5, 0.5, 0.5, 0.3, 0.3, 0.3])
+    x0 = np.clip(x0, POSE_XLIM[0] + 1e-3, POSE_XLIM[1] - 1e-3)
+    rows = np.minimum(i0[:, None] + 2 + np.arange(N + 1)[None, :], 50)
+    robot = MobileManipulator(dt)
+    pose = np.array([np.asarray(robot.forward_tranformation(p)[0], float).reshape(4) for p in plan])     # [51, 4]
+    x_ref = np.zeros((B, N + 1, 9)); x_ref[:, :, :4] = pose[rows]
+    circ = np.tile(DEMO_CIRCLES, (B, 1, 1)) if n_obs == 3 else _random_circles(rng, x0[:, :2], n_obs)
+    return dict(N=N, dt=dt, n_obs=n_obs, n_pl=0, obs_per_stage=0, x_init=x0, x_ref=x_ref, u_ref=np.zeros((B, N, 5)),
+                u_last=np.zeros((B, N, 5)), circles=circ, planes=None, n_pl_inst=None,
+                Qd=np.array([5., 5, 5, 5, 0, 0, 0, 0, 0]), Pd=np.array([50., 50, 50, 50, 0, 0, 0, 0, 0]))

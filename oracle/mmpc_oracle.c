@@ -117,6 +117,29 @@ static void point_hess(const FK* f, const Point* p, const double n[3], double G[
   G[4][4] = g23;  G[4][5] = G[5][4] = gam[2]; G[5][5] = gam[2];
 }
 
+/* ---- MMPC_MODEL_POSEREF (controllers/mpc_wholebody.py:79-86, :104-107): the tracking cost  e^T diag(W) e  on the end-point pose
+ * e = forward_tranformation(x)[0] - X_ref[k] = (P_e - r_xyz, psi - r_psi); value, gradient and exact Hessian wrt the 6 pose
+ * variables (x, y, psi, q1, q2, q3).  Wp: 4 weights; r: 4 reference values. ---- */
+static double pose_cost(const double* x, const FK* f, const double* Wp, const double* r, double g[NP], double H[NP][NP]) {
+  Point p; point_eval(x, f, BODY[5], &p);
+  double e[3], n[3], val = 0;
+  for (int c = 0; c < 3; ++c) { e[c] = p.P[c] - r[c]; n[c] = 2 * Wp[c] * e[c]; val += Wp[c] * e[c] * e[c]; }
+  const double ep = x[2] - r[3];
+  val += Wp[3] * ep * ep;
+  if (g) {
+    for (int a = 0; a < NP; ++a) { g[a] = 0; for (int c = 0; c < 3; ++c) g[a] += n[c] * p.J[c][a]; }
+    g[2] += 2 * Wp[3] * ep;
+  }
+  if (H) {
+    point_hess(f, &p, n, H);
+    for (int a = 0; a < NP; ++a)
+      for (int b = 0; b < NP; ++b)
+        for (int c = 0; c < 3; ++c) H[a][b] += 2 * Wp[c] * p.J[c][a] * p.J[c][b];
+    H[2][2] += 2 * Wp[3];
+  }
+  return val;
+}
+
 /* ---- row evaluation: value, gradient and Hessian wrt the 6 pose variables ---- */
 static void row_circle(const double* x, const double* c, double base_r, double* h, double g[NP], double H[NP][NP]) {
   double dx = x[0] - c[0], dy = x[1] - c[1];
@@ -242,7 +265,7 @@ static void build_rows(Work* w) {
     for (int i = 0; i < w->nobs; ++i) r[n++] = (RowDesc){ROW_CIRCLE, i, 0};
     int term_on_prev = (w->mode == MMPC_MODE_REFERENCE); /* quirk 3, :263-265 */
     if (w->cfg->terminal_rows_on_sN) term_on_prev = 0; /* rows on s_N: the variant the GPU's reference mode solves */
-    const int nself = (w->cfg->model == MMPC_MODEL_BASE) ? 0 : 4; /* MPCBase has no arm (controllers/mpc_base.py) */
+    const int nself = (w->cfg->model == MMPC_MODEL_WHOLEBODY) ? 4 : 0; /* MPCBase has no arm (controllers/mpc_base.py); the pose-reference controller no self-collision rows (controllers/mpc_wholebody.py:100 "TODO") */
     if (m < N || !term_on_prev)
       for (int i = 0; i < nself; ++i) r[n++] = (RowDesc){ROW_SELF, i, 0};
     if (m == N - 1 && term_on_prev)
@@ -305,7 +328,8 @@ static double cost_eval(const Work* w, const double* x, const double* u, const d
   const MmpcConfig* c = w->cfg; int N = w->N; double J = 0;
   for (int k = 0; k <= N; ++k) {
     const double* Wx = (k < N) ? c->Qd : c->Pd;
-    for (int i = 0; i < NX; ++i) { double e = xerr(c, i, x[k * NX + i], w->xref[k * NX + i]); J += Wx[i] * e * e; }
+    if (c->model == MMPC_MODEL_POSEREF) { FK f; fk_eval(x + k * NX, &f); J += pose_cost(x + k * NX, &f, Wx, w->xref + k * NX, NULL, NULL); }
+    else for (int i = 0; i < NX; ++i) { double e = xerr(c, i, x[k * NX + i], w->xref[k * NX + i]); J += Wx[i] * e * e; }
     if (k < N)
       for (int j = 0; j < NU; ++j) {
         double e = u[k * NU + j] - w->uref[k * NU + j], dl = u[k * NU + j] - w->ulast[k * NU + j];
@@ -402,9 +426,18 @@ static void evaluate(Work* w, double mu, KktParts* kp) {
   for (int k = 0; k <= N; ++k) {
     double* H = w->H + (size_t)k * NY * NY; double* g = w->g + k * NY; double* st = stat + k * NY;
     const double* Wx = (k < N) ? c->Qd : c->Pd;
+    const int pose = c->model == MMPC_MODEL_POSEREF;
+    if (pose) {
+      double gp[NP], Hp[NP][NP];
+      pose_cost(XK(w, k), w->fk + k, Wx, w->xref + k * NX, gp, Hp);
+      for (int a = 0; a < NP; ++a) {
+        g[POSE2X[a]] += gp[a]; st[POSE2X[a]] += gp[a];
+        for (int b = 0; b < NP; ++b) H[POSE2X[a] * NY + POSE2X[b]] += Hp[a][b];
+      }
+    }
     for (int i = 0; i < NX; ++i) {
-      double gr = 2 * Wx[i] * xerr(w->cfg, i, XK(w, k)[i], w->xref[k * NX + i]);
-      H[i * NY + i] += 2 * Wx[i]; g[i] += gr; st[i] += gr;
+      double gr = pose ? 0.0 : 2 * Wx[i] * xerr(w->cfg, i, XK(w, k)[i], w->xref[k * NX + i]);
+      H[i * NY + i] += pose ? 0.0 : 2 * Wx[i]; g[i] += gr; st[i] += gr;
       if (k >= 1) {
         double lo = c->xlim[0][i], hi = c->xlim[1][i], v = XK(w, k)[i];
         if (is_fin(lo)) { double d = v - lo, zz = w->zxl[k * NX + i]; H[i * NY + i] += zz / d; g[i] -= mu / d; st[i] -= zz;
@@ -678,6 +711,10 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     double gmax = 0;
     for (int k = 1; k <= N; ++k) {
       const double* Wx = (k < N) ? cfg->Qd : cfg->Pd;
+      if (cfg->model == MMPC_MODEL_POSEREF) {
+        double gp[NP]; pose_cost(XK(w, k), w->fk + k, Wx, x_ref + k * NX, gp, NULL);
+        for (int a = 0; a < NP; ++a) gmax = fmax(gmax, fabs(gp[a]));
+      } else
       for (int i = 0; i < NX; ++i) gmax = fmax(gmax, fabs(2 * Wx[i] * xerr(cfg, i, XK(w, k)[i], x_ref[k * NX + i])));
     }
     for (int k = 0; k < N; ++k)
@@ -723,9 +760,13 @@ static int solve_one(const MmpcConfig* cfg, int npl, const double* x_init, const
     for (int k = 0; k <= N; ++k) {
       const MmpcConfig* c = w->cfg;
       const double* Wx = (k < N) ? c->Qd : c->Pd;
+      if (c->model == MMPC_MODEL_POSEREF) {
+        double gp[NP]; pose_cost(XK(w, k), w->fk + k, Wx, x_ref + k * NX, gp, NULL);
+        for (int a = 0; a < NP; ++a) gphi += gp[a] * w->dx[k * NX + POSE2X[a]];
+      }
       for (int i = 0; i < NX; ++i) {
         double dxi = w->dx[k * NX + i];
-        gphi += 2 * Wx[i] * xerr(c, i, XK(w, k)[i], x_ref[k * NX + i]) * dxi;
+        if (c->model != MMPC_MODEL_POSEREF) gphi += 2 * Wx[i] * xerr(c, i, XK(w, k)[i], x_ref[k * NX + i]) * dxi;
         if (k >= 1) {
           double lo = c->xlim[0][i], hi = c->xlim[1][i], v = XK(w, k)[i];
           if (is_fin(lo)) { double d = v - lo, zz = w->zxl[k * NX + i]; double dz = mu / d - zz - zz / d * dxi; w->dzxl[k * NX + i] = dz;

@@ -232,8 +232,72 @@ def make_base_case(M_full=16, M_sum=512, seed=201, N=10):
     return pts
 
 
+def make_pose_case(M_full=16, M_sum=512, seed=301, N=10):
+    """controllers/mpc_wholebody.py::MPCWholeBody.reset() (:49-128), the pose-reference sibling (end-point pose in the cost), on
+    numbers: SURVEY.md 8(f) row 4."""
+    import importlib
+    mod = importlib.import_module("controllers.mpc_wholebody")     # reference, unmodified
+    assert REF in mod.__file__
+    rng = np.random.default_rng(seed)
+    M = M_full + M_sum
+    pts = random_points(rng, M, N, 0)
+    pts = {k: v for k, v in pts.items() if k != "free"}
+    pts["X_ref"] = np.ascontiguousarray(pts["X_ref"][:, :, :4])                     # x y z psi of the end point (:66)
+    pts["X_ref"][:, :, 2] = rng.uniform(0.6, 1.8, size=(M, N + 1))                   # a reachable height
+    Q = np.diag([5., 4., 3., 2.]); P = np.diag([50., 40., 30., 20.])                # distinct weights: every component shows in the cost
+    ca.Opti.FEED = dict(variable=[pts["X"], pts["U"], pts["s"]], parameter=[pts["U_last"], pts["X_init"], pts["X_ref"], pts["U_ref"]])
+    ctrl = mod.MPCWholeBody(MobileManipulator(0.1), [Obstacles(*c) for c in DEMO_CIRCLES], N=N, Q=Q, P=P)
+    ca.Opti.FEED = None
+    it = iter(ctrl.opti.constraints)
+    s = pts["s"][:, :, 0]
+    vals, tags, blo, bhi = [], [], [], []
+    bc = lambda a: np.broadcast_to(np.asarray(a), (M,) + np.asarray(a).shape[-2:]).reshape(M, -1)
+
+    def take(kind, k, n, op, i0=0):
+        c = next(it)
+        lo = hi = None
+        if op == "bounded":
+            assert c.op == "bounded" and c.mid.shape == (1, n), (c.op, c.mid.shape)
+            v, lo, hi = bc(c.mid.v), bc(c.lhs.v), bc(c.rhs.v)
+        else:
+            assert c.op == op and c.lhs.shape == (1, n), (c.op, c.lhs.shape)
+            v = bc(c.lhs.v - c.rhs.v)
+        ks = -1
+        if kind == T_CIRC:
+            rhs = bc(c.rhs.v)[:, 0]
+            (ks,) = [q for q in range(N + 1) if np.array_equal(rhs, s[:, q])]
+        for i in range(n):
+            vals.append(v[:, i]); tags.append((kind, k, i0 + i, -1, ks))
+            blo.append(np.nan if lo is None else lo[0, i]); bhi.append(np.nan if hi is None else hi[0, i])
+
+    for k in range(N):
+        take(T_DYN, k, 9, "==")            # :76
+        take(T_BOXU, k, 5, "bounded")      # :91
+        take(T_BOXX, k, 9, "bounded")      # :92
+        take(T_BOXDU, k, 5, "bounded")     # :93
+        for i in range(3):
+            take(T_CIRC, k, 1, "<=", i)    # :96-97
+    take(T_X0, 0, 9, "==")                 # :108
+    take(T_BOXX, N, 9, "bounded")          # :109
+    for i in range(3):
+        take(T_CIRC, N, 1, "<=", i)        # :112-113
+    assert next(it, None) is None
+    vals = np.stack(vals, axis=1); tags = np.array(tags, np.int32)
+    cost = np.broadcast_to(ctrl.opti.objective.v, (M, 1, 1)).reshape(-1)
+    wts = rng.uniform(0.5, 1.5, size=vals.shape[1])
+    sums = np.stack([np.where(tags[:, 0] == t, wts, 0.0) @ vals[M_full:].T for t in range(8)], axis=1)
+    np.savez_compressed(os.path.join(HERE, "ref_rows_pose.npz"), N=N, dt=0.1, circles=np.array(DEMO_CIRCLES, float), Qd=np.diag(Q), Pd=np.diag(P),
+                        tags=tags, box_lo=np.array(blo), box_hi=np.array(bhi), weights=wts, M_full=M_full, M_sum=M_sum, seed=seed,
+                        rows_full=vals[:M_full], cost=cost, row_sums=sums, x_ref_z=pts["X_ref"][:, :, 2], input_checksums=input_checksums(pts))
+    print("pose     N=%d rows=%d (pose-reference MPCWholeBody, controllers/mpc_wholebody.py)" % (N, vals.shape[1]))
+    return pts
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pose":
+        make_pose_case(); sys.exit(0)
     make_base_case()
+    make_pose_case()
     make_model_values()
     rng = np.random.default_rng(3)
     c16 = [tuple(r) for r in rng.uniform([0.5, 0.5, 0.1], [5.5, 5.5, 0.6], size=(16, 3))]
