@@ -4,16 +4,22 @@
 // inputs once and its outputs once: the algorithmic traffic of section 8(d).  Blocks are persistent and pull instances from an
 // atomic work queue, so there are no lists, no compaction, no rounds, and no host in the loop: one launch per solve.
 //
-// It is the LATENCY path (small batches: a single controller, closed loops of a few hundred robots).  A B200 SM holds one
-// or two instances of this NLP in shared memory (112 KB each at N = 20 with 16 circles), so 148 .. 296 instances are in flight and an
-// iteration costs its dependent-instruction latency; batches beyond a few hundred instances are faster through the streaming
-// "staged" kernels, which keep 24 instances per SM in flight.  mmpc_api.cu picks by batch size.
+// It is the LATENCY path (a single controller, closed loops of up to a couple of thousand robots).  A B200 SM holds two
+// instances of this NLP in shared memory (112 KB each at N = 20 with 16 circles), so 296 instances are in flight and an
+// iteration costs its dependent-instruction latency (about 115 us); batches beyond ~2,000 instances are faster through the
+// streaming "staged" kernels, which keep 24 instances per SM in flight.  mmpc_api.cu picks by batch size.
+//
+// The inputs of an instance (6.2 KB) come in by TMA: cp.async.bulk + mbarrier into a staging area that aliases the Riccati
+// records (dead while an instance is set up), see slice_in() / inputs_issue().
 //
 // The arithmetic is the staged solver's, literally: this file compiles the same phase bodies (mmpc_staged.cuh, mmpc_team.cuh)
 // with MMPC_RESIDENT defined, which turns the tile-major HBM layout into a stride-1 layout (LSH = 0), global-memory loads
-// and cp.async staging into plain shared-memory accesses, and gives Inst a separate index for the caller's arrays.  Thread
-// roles inside the block: warp 0 = the 16-lane Riccati team (its second half-warp mirrors the first) and the per-instance
-// control steps; threads 32 .. 32 + N = one per stage (evaluation, step, trial).  Phases are separated by __syncthreads().
+// and cp.async staging into plain shared-memory accesses, and gives Inst a separate index for the caller's arrays.  On the
+// reference NLP the results equal the staged solver's to the bit (tests/test_gpu_parity.py).  Thread roles inside the block:
+// warp 0 = the 16-lane Riccati team -- its second half-warp factorises with the NEXT delta_w of the inertia-correction
+// sequence at the same time (Team::solve_spec) -- and the per-instance control steps; threads 32 .. 32 + N = one per stage
+// (set-up, evaluation, step, trial).  Phases are separated by __syncthreads().
+// mmpc_resident_pose.cu compiles this file a second time with the pose-reference controller's cost (MMPC_POSEREF).
 #define MMPC_RESIDENT 1
 #define mmpc mmpc_res   // its own namespace: the same inline function names are compiled differently in mmpc_api.cu
 #include <cuda_runtime.h>
