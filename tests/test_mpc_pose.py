@@ -127,5 +127,19 @@ def test_gpu_pose_controller_matches_oracle(n_obs, B):
     i = int(np.nonzero(both)[0][0])
     u = c1.solve(b["x_init"][i].copy(), b["x_ref"][i, :, :4], b["u_ref"][i])
     assert np.abs(u - ref["U"][i, 0]).max() < 1e-4 and c1.x_guess.shape == (b["N"] + 1, 9)
+    xg, ul = c1.x_guess.copy(), c1.u_latest.copy()
     u2 = c1.solve(b["x_init"][i].copy(), b["x_ref"][i, :, :4], b["u_ref"][i])
     assert c1.last_info["status"][0] == 0 and np.isfinite(u2).all()
+    # the same warm-started problem on the oracle: U_last = U guess = previous U*, X guess = previous X*
+    b2 = {k: (v[i:i + 1] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == B else v) for k, v in b.items()}
+    b2["u_last"] = ul[None]; b2["x_guess"] = xg[None]
+    r2 = _oracle_solve(b2)
+    assert r2["status"][0] == 0
+    assert abs(c1.cost - r2["cost"][0]) <= 1e-5 * max(1.0, abs(r2["cost"][0])) and np.abs(u2 - r2["U"][0, 0]).max() < 1e-4
+    # the model is refused where it cannot run: planes, or the literal-reference NLP mode
+    from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
+    from mobile_manipulator_mpc_b200._lib import MmpcError
+    with pytest.raises(MmpcError):
+        BatchSolver(N=10, n_obs=3, n_pl=2, mode=_abi.MODE_CLEAN, model=_abi.MODEL_POSEREF)
+    with pytest.raises(MmpcError):
+        BatchSolver(N=10, n_obs=3, n_pl=0, mode=_abi.MODE_REFERENCE, model=_abi.MODEL_POSEREF)
