@@ -265,7 +265,11 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
   __shared__ int s_b;
   __shared__ __align__(8) unsigned long long s_bar;   // mbarrier: the inputs of the block's next instance have landed
   const ResPlan pl = res_plan(P0.cfg);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp 0 is the team.  The role predicate is a VOTE, not tid >> 5: a branch on threadIdx is "divergent" to the compiler,
+  // which then brackets every shuffle under it with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE (439 brackets in this kernel); a vote
+  // result is known to be warp-uniform
+  const bool team_warp = __all_sync(0xffffffffu, tid < 32);
   const int N = P0.cfg.N;
   const int k = tid - 32;                       // stage of a stage thread
   const bool stage = tid >= 32 && k <= N;
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
     RES_TICK(1)
     for (;;) {
       // ---- KKT test, barrier update, Riccati factorisation (two delta_w at a time), roll-out of the Newton step ----
-      if (warp == 0) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, &S.W(0, (1 - S.J(J_CUR)) * pl.ITSZ), pl.STGp); }
+      if (team_warp) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, &S.W(0, (1 - S.J(J_CUR)) * pl.ITSZ), pl.STGp); }
       __syncthreads();
       RES_TICK(2)
       const int st = S.J(J_STATE);
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
       if (stage) { if (st == ST_FINISH) S.finish_stage(k); else if (st == ST_ACTIVE) S.template step<REF>(k); }
       __syncthreads();
       RES_TICK(3)
-      if (warp == 0) S.template ctrl_step<32>(lane);
+      if (team_warp) S.template ctrl_step<32>(lane);
       __syncthreads();
       RES_TICK(4)
       if (S.J(J_STATE) != ST_TRIAL) break;      // finished: the outputs are written
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
         if (stage) S.template trial_eval<REF>(k);
         __syncthreads();
         RES_TICK(5)
-        if (warp == 0) S.template ctrl_trial<32>(lane);
+        if (team_warp) S.template ctrl_trial<32>(lane);
         __syncthreads();
         RES_TICK(6)
         if (S.J(J_STATE) != ST_TRIAL) break;    // accepted (ST_ACTIVE) or given up (ST_DONE)

@@ -1501,8 +1501,10 @@ struct Inst {
   // fixed order; NL = 1: one lane does everything, the CPU emulation); lane 0 writes the instance state.
   template <int NL>
   __device__ bool ctrl_step(int lane) {
+    // (the state is the same in all lanes; the branches on it are taken on VOTES so that the compiler knows them warp-uniform
+    // and does not bracket every shuffle below with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE)
     const int st = J(J_STATE);
-    if (st == ST_FINISH) {  // close an instance whose stages were written by finish_stage
+    if (warp_all(st == ST_FINISH)) {  // close an instance whose stages were written by finish_stage
       double fsum = 0;
       for (int k = lane; k <= N; k += NL) fsum += W2(k, S_PART + 0);
       fsum = lanes_sum<NL>(fsum);
@@ -1515,7 +1517,7 @@ struct Inst {
       }
       return false;
     }
-    if (st != ST_ACTIVE) return false;
+    if (!warp_all(st == ST_ACTIVE)) return false;
     double ap = 1.0, ad = 1.0, gphi = 0, theta = 0, fsum = 0, logsum = 0;
     for (int k = lane; k <= N; k += NL) {
       ap = fmin(ap, W2(k, S_PART + 0)); ad = fmin(ad, W2(k, S_PART + 1));
@@ -2211,7 +2213,9 @@ __global__ void __launch_bounds__(128, REF ? MMPC_STEP_MINB - 1 : MMPC_STEP_MINB
 }
 __global__ void __launch_bounds__(128) staged_ctrl_step_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[0];  // one warp per instance
-  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5)
+  // (the loop condition is a vote: a loop that depends on threadIdx is "divergent" to the compiler, which then brackets every
+  // shuffle of the body with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE; a vote result is known to be warp-uniform)
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; __all_sync(FULL, j < n); j += (gridDim.x * blockDim.x) >> 5)
     body_ctrl_step<32>(P, j, threadIdx.x & 31);
 }
 template <bool REF>
@@ -2230,7 +2234,7 @@ __global__ void __launch_bounds__(128) staged_pose_kernel(const __grid_constant_
 }
 __global__ void __launch_bounds__(128) staged_ctrl_trial_kernel(const __grid_constant__ SParams P) {
   const int n = P.cnt[P.tsel];  // one warp per instance
-  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5)
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; __all_sync(FULL, j < n); j += (gridDim.x * blockDim.x) >> 5)   // (vote: see staged_ctrl_step_kernel)
     body_ctrl_trial<32>(P, j, threadIdx.x & 31);
 }
 #endif

@@ -524,7 +524,9 @@ struct Team {
     if (!(E0 == E0)) fin = MMPC_STATUS_NAN;
     else if (E0 <= tol) fin = MMPC_STATUS_CONVERGED;
     else if (iter >= cfg.max_iter) fin = MMPC_STATUS_MAX_ITER;
-    if (fin >= 0) { if (writer) { S.J(J_STATUS) = fin; S.J(J_STATE) = ST_FINISH; } return; }
+    // (every branch that guards shuffles is taken on a VOTE: the values are the same in all lanes, but only a vote result is
+    // warp-uniform to the compiler, which otherwise brackets each shuffle with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE)
+    if (warp_all(fin >= 0)) { if (writer) { S.J(J_STATUS) = fin; S.J(J_STATE) = ST_FINISH; } return; }
     bool mu_changed = false;
     while (kkt_error(kp, mu) <= kap_eps * mu && mu > tol / 10) {
       mu = fmax(tol / 10, fmin(kap_mu * mu, pow(mu, th_mu))); mu_changed = true;
@@ -540,14 +542,14 @@ struct Team {
       const double r_b = next_reg(r_a);
       const int fail = riccati<Q3>(half ? r_b : r_a, mu, it);
       const int fail_a = __shfl_sync(FULL, fail, 0), fail_b = __shfl_sync(FULL, fail, 16);
-      if (!fail_a) { win = 0; reg = r_a; break; }
-      if (ia + 1 > 40 || r_b > 1e20) break;      // the serial loop gives up after attempt ia (MMPC_STATUS_FACTOR)
-      if (!fail_b) { win = 1; reg = r_b; break; }
+      if (warp_all(!fail_a)) { win = 0; reg = r_a; break; }
+      if (warp_all(ia + 1 > 40 || r_b > 1e20)) break;      // the serial loop gives up after attempt ia (MMPC_STATUS_FACTOR)
+      if (warp_all(!fail_b)) { win = 1; reg = r_b; break; }
       r_a = next_reg(r_b); ia += 2;
-      if (ia > 40 || r_a > 1e20) break;
+      if (warp_all(ia > 40 || r_a > 1e20)) break;
     }
     sm = ring0;                                // roll-out: both halves do the same, one ring
-    if (win < 0) { if (writer) { S.J(J_STATUS) = MMPC_STATUS_FACTOR; S.J(J_STATE) = ST_FINISH; } S.rkp = rk0; S.rks = RS; return; }
+    if (warp_all(win < 0)) { if (writer) { S.J(J_STATUS) = MMPC_STATUS_FACTOR; S.J(J_STATE) = ST_FINISH; } S.rkp = rk0; S.rks = RS; return; }
     if (writer) { if (reg > 0) S.D(D_REGLAST) = reg; S.J(J_REGF) = reg > 0; }
     S.rkp = win ? rk1 : rk0; S.rks = win ? rk1_stride : RS;
     team_sync();
@@ -583,8 +585,12 @@ __global__ void __launch_bounds__(MMPC_TEAM_BLOCK, WARPS * 32 / MMPC_TEAM_BLOCK)
   const int c = threadIdx.x & 15;
   // a warp strides over pairs of list entries; with an odd count the last warp's second team repeats the
   // first team's instance (same computation, same stores) so that the warp stays in lock step
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; j0 < n; j0 += 2 * warps) {
+  // (the warp index is formed from blockIdx alone when a block is one warp: a loop whose start depends on threadIdx is
+  // "divergent" to the compiler, which then brackets every shuffle of the body with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE --
+  // 296 brackets, two more instructions per double shuffle)
+  const int warps = gridDim.x * (MMPC_TEAM_BLOCK / 32);
+  const int warp0 = blockIdx.x * (MMPC_TEAM_BLOCK / 32) + (MMPC_TEAM_BLOCK > 32 ? (int)(threadIdx.x >> 5) : 0);
+  for (int j0 = warp0 * 2; j0 < n; j0 += 2 * warps) {
     const int j = min(j0 + ((threadIdx.x >> 4) & 1), n - 1);
     body_solve_team<Q3>(P, j, c, ring + (threadIdx.x >> 4) * Team::SMEM_DOUBLES);
   }
