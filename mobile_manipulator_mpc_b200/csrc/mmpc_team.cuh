@@ -577,7 +577,10 @@ __device__ inline void body_solve_team(const SParams& P, int j, int c, double* s
 // 65,536 batch / one instance end to end): 16 warps (128 registers, spills) 142.7 ms / 4.76 ms, 12 warps (168) 134.3 / 4.74,
 // 10 warps 144.0 / 4.66, 8 warps (255 registers, no spills) 147.4 / 4.40: the bulk wants 12, a round whose instances all fit
 // on the GPU at 8 warps per SM is pure latency and wants the spill-free code.
-constexpr int TEAM_WARPS_BULK = 12, TEAM_WARPS_THIN = 8;
+#ifndef MMPC_TEAM_WARPS_BULK
+#define MMPC_TEAM_WARPS_BULK 12
+#endif
+constexpr int TEAM_WARPS_BULK = MMPC_TEAM_WARPS_BULK, TEAM_WARPS_THIN = 8;
 template <bool Q3, int WARPS>
 __global__ void __launch_bounds__(MMPC_TEAM_BLOCK, WARPS * 32 / MMPC_TEAM_BLOCK) staged_solve_team_kernel(const __grid_constant__ SParams P) {
   __shared__ __align__(16) double ring[(MMPC_TEAM_BLOCK / 16) * Team::SMEM_DOUBLES];  // one ring per team
