@@ -529,8 +529,10 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   // the resident kernel: forced, or AUTO's choice for small batches when the instance fits in shared memory.  Measured on a
   // B200 (config 3, reference NLP, resident / staged ms): B = 1 4.0 / 5.2, 148 14.5 / 31.8, 592 19.1 / 39.4, 1,024 32.4 / 47.7,
   // 2,048 50.4 / 51.5 -- the staged solver's floor is the launch latency of its ~270 rounds, the resident kernel's slope is
-  // one instance (two at a time) per SM.  MMPC_AUTO_RESIDENT = largest batch, in instances per SM, AUTO sends there (0: never).
-  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 10;
+  // one instance (two at a time) per SM.  Other shapes (scripts/crossover.py): N = 40 with moving obstacles (one block per SM)
+  // 1,480 171 / 181; 3 circles, 2 planes 2,960 67 / 80.  MMPC_AUTO_RESIDENT = largest batch, in instances per SM, AUTO sends
+  // there (0: never).
+  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 14;
   const bool pose = h->cfg.model == MMPC_MODEL_POSEREF;   // compiled into the pose build of the resident kernel only
   const bool fits = (pose ? mmpc_resident_pose_smem_bytes(&h->cfg) : mmpc_resident_smem_bytes(&h->cfg)) <= h->smem_optin;
   if (pose && !fits) { snprintf(g_err, sizeof g_err, "MMPC_MODEL_POSEREF runs on the resident kernel; this horizon does not fit in shared memory"); return MMPC_ERR_UNSUPPORTED; }

@@ -537,7 +537,7 @@ def test_resident_kernel_equals_staged_solver(mode, q3):
 
 def test_auto_picks_the_resident_kernel_for_small_batches():
     """MMPC_KERNEL_AUTO (the default): one launch sequence of three (resident) for a small batch, the graph for a large one."""
-    batch = scenarios.make_batch(3, 2048)
+    batch = scenarios.make_batch(3, 3000)
     S = _solver(batch, kernel="auto", mode=_abi.MODE_REFERENCE)
     small = {k: (v[:64] if isinstance(v, np.ndarray) else v) for k, v in batch.items()}
     n0 = S.launch_count(); S.solve_host(small); n1 = S.launch_count(); S.solve_host(batch); n2 = S.launch_count()
