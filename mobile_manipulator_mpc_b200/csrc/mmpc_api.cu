@@ -20,6 +20,8 @@ using namespace mmpc;
 // csrc/mmpc_resident.cu (its own translation unit: the same phase bodies compiled for a shared-memory workspace)
 extern "C" int mmpc_resident_smem_bytes(const MmpcConfig* cfg);
 extern "C" int mmpc_resident_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream);
+extern "C" int mmpc_resident_tail_node(const MmpcConfig* cfg, int B, const void* io_dev, int sm_count, const void** fn_out, int* threads_out,
+                                       int* smem_out, int* blocks_in_flight, void* params_out);
 // csrc/mmpc_resident_pose.cu (the same kernel with the end-point pose cost of MMPC_MODEL_POSEREF compiled in)
 extern "C" int mmpc_resident_pose_smem_bytes(const MmpcConfig* cfg);
 extern "C" int mmpc_resident_pose_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream);
@@ -33,7 +35,7 @@ struct MmpcHandle {
   struct { double *ws, *qp, *rk, *gd; int *gi, *lists, *cnt; SIO* io; long long LS; int* pin; cudaEvent_t ev[8]; bool ready;
            int rounds; } sg;
   // the solve as one CUDA graph (built for a batch size, rebuilt when B, the weights or the kernel selection change)
-  struct { struct { cudaGraph_t graph; cudaGraphExec_t exec; int cap, classes; } e[4]; int next, pending_classes; bool pending; } gr;
+  struct { struct { cudaGraph_t graph; cudaGraphExec_t exec; int cap, classes, tail; } e[4]; int next, pending_classes, pending_tail; bool pending; } gr;
   int hostloop;  // MMPC_KERNEL_STAGED_HOSTLOOP: the host sequences the rounds
   int resident;  // MMPC_KERNEL_RESIDENT forced
   int autosel;   // MMPC_KERNEL_AUTO: resident for small batches, staged otherwise
@@ -209,7 +211,7 @@ extern "C" int mmpc_set_kernel(MmpcHandle* h, int32_t kernel) {
 //              one cudaGraphLaunch per solve, no per-round synchronisation, any number of solver contexts per host thread.
 //   host loop  (profiling, MMPC_HOSTLOOP=1) the host sequences rounds and learns the list lengths from a 16-byte copy that
 //              trails the launches by two rounds; used when every launch is bracketed by timing events.
-__global__ void staged_set_io_kernel(SIO io, SIO* dst) { *dst = io; }
+__global__ void staged_set_io_kernel(SIO io, SIO* dst, unsigned* tail_queue) { *dst = io; *tail_queue = 0u; }   // (tail_queue: the resident tail kernel's work counter)
 // cnt[0] E list, cnt[1] / cnt[2] trial lists, cnt[3] rounds executed
 __global__ void staged_cond_kernel(cudaGraphConditionalHandle hnd, int* cnt, int which, int above, int add_rounds) {
   cnt[3] += add_rounds;
@@ -253,7 +255,7 @@ static int ensure_workspace(MmpcHandle* h) {
   CK(cudaMalloc(&h->sg.lists, (size_t)4 * LS * sizeof(int)));   // E, two trial lists, the Riccati's ordering of E
   CK(cudaMalloc(&h->sg.cnt, 4 * sizeof(int)));
   CK(cudaMalloc(&h->sg.io, sizeof(SIO)));
-  CK(cudaMalloc(&h->queue, sizeof(unsigned)));
+  CK(cudaMalloc(&h->queue, 2 * sizeof(unsigned)));   // [0] the resident kernel's work counter, [1] the resident tail kernel's
   CK(cudaMallocHost(&h->sg.pin, (8 * 4 + 4) * sizeof(int)));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->sg.ev[i], cudaEventDisableTiming | cudaEventBlockingSync));  // the host thread sleeps, it does not spin: several contexts per GPU and ranks per box share the cores
   h->sg.ready = true;
@@ -387,6 +389,16 @@ static int graph_build(MmpcHandle* h, int32_t B, int slot) {
   issue_round(h, I, P, 0, B, true, nomark);
   // size classes of the active set: B, B/2, B/4, ... and the two thin thresholds; a loop per class, entered in turn
   // (the active set only shrinks).  Class c runs while  count > lower bound of c  with launch bounds for `ub[c]`.
+  // The tail: once no more instances are active than the resident kernel holds in flight, they are handed to it (one graph
+  // node after the loops; csrc/mmpc_resident.cu, resident_tail_kernel) instead of being walked through ~300 us rounds one
+  // iteration at a time.  Same results to the bit.  (MMPC_RESIDENT_TAIL=0: A/B, the staged rounds run to the end.)
+  static const int tail_on = getenv("MMPC_RESIDENT_TAIL") ? atoi(getenv("MMPC_RESIDENT_TAIL")) : 1;
+  const void* tail_fn = nullptr; int tail_threads = 0, tail_smem = 0, tail_blocks = 0;
+  SParams Ptail;
+  if (tail_on && h->sg_fused && h->cfg.model != MMPC_MODEL_POSEREF && mmpc_resident_smem_bytes(&h->cfg) <= h->smem_optin) {
+    cudaError_t e = (cudaError_t)mmpc_resident_tail_node(&h->cfg, B, h->sg.io, h->sm_count, &tail_fn, &tail_threads, &tail_smem, &tail_blocks, &Ptail);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "resident tail kernel: %s", cudaGetErrorString(e)); return MMPC_ERR_CUDA; }
+  }
   std::vector<long long> ub;
   {
     const long long t_team = (long long)h->sm_count * TEAM_WARPS_THIN * 32 / 16;                    // largest thin-team count
@@ -395,10 +407,10 @@ static int graph_build(MmpcHandle* h, int32_t B, int slot) {
     long long v = B;
     ub.push_back(v);
     while (v > 2 * t_team) { v = (v + 1) / 2; ub.push_back(v); }
-    for (long long t : {t_team, t_parts, t_floor}) if (t > 0 && t < ub.back()) ub.push_back(t);
+    for (long long t : {t_team, t_parts, t_floor}) if (t > 0 && t < ub.back() && t > tail_blocks) ub.push_back(t);
   }
   for (size_t c = 0; c < ub.size(); ++c) {
-    const int low = c + 1 < ub.size() ? (int)ub[c + 1] : 0;   // run this class while more than `low` instances are active
+    const int low = c + 1 < ub.size() ? (int)ub[c + 1] : tail_blocks;   // run this class while more than `low` instances are active
     cudaGraphConditionalHandle hnd;
     CK(cudaGraphConditionalHandleCreate(&hnd, g, 0, 0));
     // entry condition: the trial list of the last round (parity 0 rounds write list 2) holds every active instance
@@ -419,13 +431,22 @@ static int graph_build(MmpcHandle* h, int32_t B, int slot) {
     Bd.launch((const void*)staged_cond_kernel, dim3(1), dim3(1), 0, ac);
     if (Bd.rc != MMPC_OK) return Bd.rc;
   }
+  if (tail_fn) {
+    const long long LSs = P.LS;
+    ResTail T; memset(&T, 0, sizeof T);
+    T.ws = h->sg.ws; T.qp = h->sg.qp; T.gd = h->sg.gd; T.gi = h->sg.gi; T.list = h->sg.lists + 2 * LSs; T.cnt = h->sg.cnt; T.queue = h->queue + 1;
+    T.LS = LSs; T.STG = P.STG; T.ITSZ = P.ITSZ; T.ND = P.ND;
+    void* at[] = {&Ptail, &T};
+    I.launch(tail_fn, dim3(tail_blocks), dim3(tail_threads), tail_smem, at);
+    if (I.rc != MMPC_OK) return I.rc;
+  }
   // the counters of the solve (rounds executed) for mmpc_launch_count / mmpc_phase_times
   {
     cudaGraphNode_t mn;
     CK(cudaGraphAddMemcpyNode1D(&mn, g, &I.last, 1, h->sg.pin + 32, h->sg.cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost));
   }
   CK(cudaGraphInstantiate(&E.exec, g, 0));
-  E.cap = B; E.classes = (int)ub.size();
+  E.cap = B; E.classes = (int)ub.size(); E.tail = tail_fn ? 1 : 0;
   return MMPC_OK;
 }
 
@@ -440,7 +461,7 @@ static int launch_staged_graph(MmpcHandle* h, int32_t B, cudaStream_t st) {
   }
   h->sg.pin[32 + 3] = -1;
   CK(cudaGraphLaunch(h->gr.e[slot].exec, st));
-  h->gr.pending = true; h->gr.pending_classes = h->gr.e[slot].classes;
+  h->gr.pending = true; h->gr.pending_classes = h->gr.e[slot].classes; h->gr.pending_tail = h->gr.e[slot].tail;
   return MMPC_OK;
 }
 
@@ -453,7 +474,7 @@ static void graph_account(MmpcHandle* h) {
   h->gr.pending = false;
   h->sg.rounds = 1 + rounds;
   const int ref = h->cfg.mode == MMPC_MODE_REFERENCE;   // the pose kernel: once more in round 0, once per round
-  h->launches += 2 + 8 + 2 * ref + (7LL + ref) * rounds + h->gr.pending_classes + rounds / 2;
+  h->launches += 2 + 8 + 2 * ref + (7LL + ref) * rounds + h->gr.pending_classes + rounds / 2 + h->gr.pending_tail;
 }
 
 // ---- driver 2: the host sequences rounds (profiling; MMPC_HOSTLOOP=1) ----------------------------------------------------
@@ -524,7 +545,7 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   io.circles = in->circles; io.planes = in->planes; io.n_pl_inst = in->n_pl_inst; io.flags = in->flags; io.x_guess = in->x_guess;
   io.U = out->U; io.X = out->X; io.s = out->s; io.cost = out->cost; io.kkt = out->kkt; io.iters = out->iters; io.status = out->status;
   io.B = B;
-  staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io);
+  staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io, h->queue + 1);
   CK(cudaGetLastError());
   // the resident kernel: forced, or AUTO's choice for small batches when the instance fits in shared memory.  Measured on a
   // B200 (config 3, reference NLP, resident / staged ms): B = 1 4.0 / 5.2, 148 14.5 / 31.8, 592 19.1 / 39.4, 1,024 32.4 / 47.7,

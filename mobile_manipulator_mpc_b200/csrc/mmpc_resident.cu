@@ -259,6 +259,39 @@ __device__ inline void init_pass_c(Inst& S, int k) {
   }
 }
 
+// The interior-point iterations of the instance in shared memory, until it has finished (its outputs are written by the
+// phase bodies).  in_line_search: the instance comes from the staged solver in the middle of a line search (state ST_TRIAL):
+// the first thing it needs is a trial, not a factorisation.
+template <bool REF, bool Q3>
+__device__ __forceinline__ void resident_iterate(Inst& S, const SParams& P, const ResPlan& pl, int b, bool team_warp, int lane, bool stage, int k,
+                                                 double* team_ring, bool in_line_search) {
+  for (;;) {
+    if (!in_line_search) {
+      // ---- KKT test, barrier update, Riccati factorisation (two delta_w at a time), roll-out of the Newton step ----
+      if (team_warp) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, &S.W(0, (1 - S.J(J_CUR)) * pl.ITSZ), pl.STGp); }
+      __syncthreads();
+      const int st = S.J(J_STATE);
+      // ---- slack / multiplier steps, fraction to the boundary (or: the results of an instance that has just finished) ----
+      if (stage) { if (st == ST_FINISH) S.finish_stage(k); else if (st == ST_ACTIVE) S.template step<REF>(k); }
+      __syncthreads();
+      if (team_warp) S.template ctrl_step<32>(lane);
+      __syncthreads();
+      if (S.J(J_STATE) != ST_TRIAL) break;      // finished: the outputs are written
+    }
+    in_line_search = false;
+    // ---- filter line search: candidate + evaluation of the next iteration at the candidate ----
+    for (;;) {
+      if (REF) { if (stage) S.pose_pass(k, true); __syncthreads(); }
+      if (stage) S.template trial_eval<REF>(k);
+      __syncthreads();
+      if (team_warp) S.template ctrl_trial<32>(lane);
+      __syncthreads();
+      if (S.J(J_STATE) != ST_TRIAL) break;    // accepted (ST_ACTIVE) or given up (ST_DONE)
+    }
+    if (S.J(J_STATE) != ST_ACTIVE) break;
+  }
+}
+
 template <bool REF, bool Q3>
 __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_constant__ SParams P0, unsigned* queue) {
   extern __shared__ __align__(16) double smem[];
@@ -282,13 +315,6 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
   const int B = P.io->B;
   if (tid == 0) mbar_init(&s_bar, 1);
   unsigned parity = 0;
-#ifdef MMPC_RES_PROF   // A/B build: cycles per phase of block 0, printed at the end (a clock read right behind a barrier
-                       // captures the barrier's ISSUE, so a phase's wait shows up in the next bucket: read the buckets in pairs)
-  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
-#define RES_TICK(i) { t1 = clock64(); pc[i] += t1 - t0; t0 = t1; }
-#else
-#define RES_TICK(i)
-#endif
   for (;;) {
     __syncthreads();                            // everybody is done with the previous instance (and with s_b)
     if (tid == 0) {
@@ -303,7 +329,6 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
     S.npl = P.io->n_pl_inst ? P.io->n_pl_inst[b] : P.cfg.n_pl;
     S.npl = S.npl < 0 ? 0 : (S.npl > P.cfg.n_pl ? P.cfg.n_pl : S.npl);
     const InPtr q = in_ptrs(P, pl, in, b);
-    RES_TICK(7)
     mbar_wait(&s_bar, parity); parity ^= 1;     // the bulk copies have landed (and the issuing thread's odd doubles with them)
     // ---- the starting point (:302-304), bound push, slack lift, objective scaling: Inst::init(), one thread per stage ----
     init_tables(S, pl, in, q, tid, blockDim.x);
@@ -314,44 +339,65 @@ __global__ void __launch_bounds__(96, 1) resident_solve_kernel(const __grid_cons
     __syncthreads();
     if (stage) init_pass_c(S, k);
     __syncthreads();
-    RES_TICK(0)
     if (REF) { if (stage) S.pose_pass(k, false); __syncthreads(); }
     if (stage) S.template eval<REF>(k);
     __syncthreads();
-    RES_TICK(1)
-    for (;;) {
-      // ---- KKT test, barrier update, Riccati factorisation (two delta_w at a time), roll-out of the Newton step ----
-      if (team_warp) { Team T(P, b, lane & 15, team_ring); T.template solve_spec<Q3>(lane >> 4, &S.W(0, (1 - S.J(J_CUR)) * pl.ITSZ), pl.STGp); }
-      __syncthreads();
-      RES_TICK(2)
-      const int st = S.J(J_STATE);
-      // ---- slack / multiplier steps, fraction to the boundary (or: the results of an instance that has just finished) ----
-      if (stage) { if (st == ST_FINISH) S.finish_stage(k); else if (st == ST_ACTIVE) S.template step<REF>(k); }
-      __syncthreads();
-      RES_TICK(3)
-      if (team_warp) S.template ctrl_step<32>(lane);
-      __syncthreads();
-      RES_TICK(4)
-      if (S.J(J_STATE) != ST_TRIAL) break;      // finished: the outputs are written
-      // ---- filter line search: candidate + evaluation of the next iteration at the candidate ----
-      for (;;) {
-        if (REF) { if (stage) S.pose_pass(k, true); __syncthreads(); }
-        if (stage) S.template trial_eval<REF>(k);
-        __syncthreads();
-        RES_TICK(5)
-        if (team_warp) S.template ctrl_trial<32>(lane);
-        __syncthreads();
-        RES_TICK(6)
-        if (S.J(J_STATE) != ST_TRIAL) break;    // accepted (ST_ACTIVE) or given up (ST_DONE)
-      }
-      if (S.J(J_STATE) != ST_ACTIVE) break;
-    }
+    resident_iterate<REF, Q3>(S, P, pl, b, team_warp, lane, stage, k, team_ring, false);
   }
-#ifdef MMPC_RES_PROF
-  if (blockIdx.x == 0 && tid == 0)
-    printf("resident cycles: init %lld eval0 %lld team %lld step %lld ctrl_step %lld pose+trial %lld ctrl_trial %lld other %lld\n",
-           pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
-#endif
+}
+
+// The TAIL of a staged solve (mmpc_api.cu, graph_build): when the active set has thinned out to what this kernel holds in
+// flight, a staged round costs its launch and dependency latency (~300 us for seven kernels that each serve a handful of
+// instances) while an iteration here costs ~120 us -- and a batch runs as many rounds as its slowest instance needs
+// iterations (config 3: 274 rounds for a mean of 34).  Each block pulls a still-active instance of the last trial list,
+// copies its state from the tile-major HBM workspace into shared memory and iterates it to the end.  Same phase bodies, same
+// bits as if the staged rounds had gone on.
+template <bool REF, bool Q3>
+__global__ void __launch_bounds__(96, 1) resident_tail_kernel(const __grid_constant__ SParams P0, const __grid_constant__ ResTail T) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_b;
+  const ResPlan pl = res_plan(P0.cfg);
+  const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+  const bool team_warp = __all_sync(0xffffffffu, tid < 32);   // (a vote: see resident_solve_kernel)
+  const int N = P0.cfg.N;
+  const int k = tid - 32;
+  const bool stage = tid >= 32 && k <= N;
+  SParams P = P0;
+  P.ws = smem + pl.o_ws; P.qp = smem + pl.o_qp; P.rk = smem + pl.o_rk; P.gd = smem + pl.o_gd; P.gi = (int*)(smem + pl.o_gi);
+  P.LS = 1; P.STG = pl.STGp;
+  double* team_ring = smem + pl.o_team;
+  double* ring = smem + pl.o_ring + (tid - 32);
+  const int n = T.cnt[2];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_b = (int)atomicAdd(T.queue, 1u);
+    __syncthreads();
+    const int j = s_b;
+    if (j >= n) break;
+    const int b = T.list[j];
+    const long long tile = b >> 5; const int ln = b & 31;
+    const int* gih = T.gi + ((tile * J_NFIELDS) << 5) + ln;
+    const int state = gih[J_STATE << 5];
+    if (state != ST_ACTIVE && state != ST_TRIAL) continue;   // finished in the last staged round
+    // ---- the instance's state: tile-major HBM (lane stride 32) -> shared memory (stride 1; the two iterate copies padded) ----
+    for (int f = tid; f < J_NFIELDS; f += nt) P.gi[f] = gih[f << 5];
+    const double* gdh = T.gd + ((tile * T.ND) << 5) + ln;
+    for (int f = tid; f < T.ND; f += nt) P.gd[f] = gdh[f << 5];
+    const double* wsh = T.ws + ((tile * (N + 1) * T.STG) << 5) + ln;
+    for (int i = tid; i < (N + 1) * T.STG; i += nt) {
+      const int kk = i / T.STG, f = i - kk * T.STG;
+      const int f2 = f < T.ITSZ ? f : f < 2 * T.ITSZ ? pl.ITSZ + (f - T.ITSZ) : 2 * pl.ITSZ + (f - 2 * T.ITSZ);
+      P.ws[kk * pl.STGp + f2] = wsh[(long long)i << 5];
+    }
+    for (int i = tid; i < (N + 1) * QS; i += nt) {
+      const int kk = i / QS, f = i - kk * QS;
+      P.qp[i] = T.qp[((long long)kk * T.LS + b) * QS + f];
+    }
+    __syncthreads();
+    Inst S(P, b); S.sm = ring; S.bs = pl.stage_threads;
+    S.load_npl();
+    resident_iterate<REF, Q3>(S, P, pl, b, team_warp, lane, stage, k, team_ring, state == ST_TRIAL);
+  }
 }
 
 }  // namespace mmpc_res
@@ -361,15 +407,41 @@ extern "C" int mmpc_resident_smem_bytes(const MmpcConfig* cfg) {
   return (int)(res_plan(*cfg).total * sizeof(double));
 }
 
-// Launches the resident solve of the B instances described by the device block `io_dev` (SIO of mmpc_staged.cuh; the resident
-// and the staged build share its layout).  `queue` is a zeroed device counter.  Returns a cudaError_t.
-extern "C" int mmpc_resident_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream) {
-  const MmpcConfig& c = *cfg;
+static SParams resident_params(const MmpcConfig& c, int B, const void* io_dev) {
   const ResPlan pl = res_plan(c);
   SParams P; memset(&P, 0, sizeof P);
   P.cfg = c; P.B = B; P.io = (const SIO*)io_dev;
   P.team = 1; P.fused = 1; P.parts = 0;
   P.R = staged_rows(c); P.ITSZ = pl.ITSZ; P.STG = pl.STGp; P.ND = staged_inst_doubles(c); P.LS = 1;
+  return P;
+}
+
+// The tail kernel of a staged solve as a graph node (mmpc_api.cu adds it): function, launch shape, and the kernel's first
+// parameter (SParams, written to params_out).  blocks_in_flight = what the GPU holds at once: the hand-over threshold.
+extern "C" int mmpc_resident_tail_node(const MmpcConfig* cfg, int B, const void* io_dev, int sm_count, const void** fn_out, int* threads_out,
+                                       int* smem_out, int* blocks_in_flight, void* params_out) {
+  const MmpcConfig& c = *cfg;
+  const ResPlan pl = res_plan(c);
+  const bool ref = c.mode == MMPC_MODE_REFERENCE, q3 = ref && c.terminal_rows_on_sN == 0;
+  const void* fn = ref ? (q3 ? (const void*)resident_tail_kernel<true, true> : (const void*)resident_tail_kernel<true, false>)
+                       : (const void*)resident_tail_kernel<false, false>;
+  const int smem = (int)(pl.total * sizeof(double));
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl.threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  *fn_out = fn; *threads_out = pl.threads; *smem_out = smem; *blocks_in_flight = per_sm * sm_count;
+  *(SParams*)params_out = resident_params(c, B, io_dev);
+  return 0;
+}
+
+// Launches the resident solve of the B instances described by the device block `io_dev` (SIO of mmpc_staged.cuh; the resident
+// and the staged build share its layout).  `queue` is a zeroed device counter.  Returns a cudaError_t.
+extern "C" int mmpc_resident_launch(const MmpcConfig* cfg, int B, const void* io_dev, unsigned* queue, int max_blocks, void* stream) {
+  const MmpcConfig& c = *cfg;
+  const ResPlan pl = res_plan(c);
+  SParams P = resident_params(c, B, io_dev);
   const bool ref = c.mode == MMPC_MODE_REFERENCE, q3 = ref && c.terminal_rows_on_sN == 0;
   const void* fn = ref ? (q3 ? (const void*)resident_solve_kernel<true, true> : (const void*)resident_solve_kernel<true, false>)
                        : (const void*)resident_solve_kernel<false, false>;

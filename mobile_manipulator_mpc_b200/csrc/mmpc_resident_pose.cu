@@ -7,4 +7,5 @@
 #define mmpc_res mmpc_res_pose
 #define mmpc_resident_smem_bytes mmpc_resident_pose_smem_bytes
 #define mmpc_resident_launch mmpc_resident_pose_launch
+#define mmpc_resident_tail_node mmpc_resident_pose_tail_node
 #include "mmpc_resident.cu"

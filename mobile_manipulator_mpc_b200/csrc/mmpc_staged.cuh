@@ -83,6 +83,19 @@ struct SParams {
   int team;        // 1: 16-lane column-parallel Riccati (mmpc_team.cuh), 0: one thread per instance
 };
 
+// What the resident TAIL kernel (mmpc_resident.cu) needs of the staged solver's state in HBM: once the active set of a staged
+// solve has thinned out to what the resident kernel holds in flight, the remaining instances are loaded into shared memory
+// and finished there (mmpc_api.cu, graph_build).
+struct ResTail {
+  const double *ws, *qp, *gd;   // tile-major workspace, stage-QP records, per-instance doubles (SParams::ws / qp / gd)
+  const int* gi;                // per-instance ints
+  const int* list;              // the trial list of the last round: every instance still active (and the ones that just finished)
+  const int* cnt;               // list lengths; cnt[2] is this list's
+  unsigned* queue;              // work counter (zeroed in front of every solve)
+  long long LS;
+  int STG, ITSZ, ND;            // the staged layout's stage stride, iterate size, per-instance doubles
+};
+
 // ---- iterate buffer (two copies, ping-pong): offsets inside one copy --------------------------
 constexpr int I_X = 0, I_U = 9, I_S = 14, I_LAM = 15, I_ZXL = 24, I_ZXU = 33, I_ZUL = 42, I_ZUU = 47, I_T = 52;
 // ---- after the two iterate copies (field-major, like the iterate) -----------------------------------
