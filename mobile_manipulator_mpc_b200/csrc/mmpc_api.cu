@@ -389,15 +389,20 @@ static int graph_build(MmpcHandle* h, int32_t B, int slot) {
   issue_round(h, I, P, 0, B, true, nomark);
   // size classes of the active set: B, B/2, B/4, ... and the two thin thresholds; a loop per class, entered in turn
   // (the active set only shrinks).  Class c runs while  count > lower bound of c  with launch bounds for `ub[c]`.
-  // The tail: once no more instances are active than the resident kernel holds in flight, they are handed to it (one graph
-  // node after the loops; csrc/mmpc_resident.cu, resident_tail_kernel) instead of being walked through ~300 us rounds one
+  // The tail: once the active set is down to a few times what the resident kernel holds in flight, it is handed to that
+  // kernel (one graph node after the loops; csrc/mmpc_resident.cu, resident_tail_kernel) instead of being walked through ~300 us rounds one
   // iteration at a time.  Same results to the bit.  (MMPC_RESIDENT_TAIL=0: A/B, the staged rounds run to the end.)
   static const int tail_on = getenv("MMPC_RESIDENT_TAIL") ? atoi(getenv("MMPC_RESIDENT_TAIL")) : 1;
-  const void* tail_fn = nullptr; int tail_threads = 0, tail_smem = 0, tail_blocks = 0;
+  const void* tail_fn = nullptr; int tail_threads = 0, tail_smem = 0, tail_blocks = 0, tail_hand = 0;   // tail_hand: active instances at the hand-over
   SParams Ptail;
   if (tail_on && h->sg_fused && h->cfg.model != MMPC_MODEL_POSEREF && mmpc_resident_smem_bytes(&h->cfg) <= h->smem_optin) {
     cudaError_t e = (cudaError_t)mmpc_resident_tail_node(&h->cfg, B, h->sg.io, h->sm_count, &tail_fn, &tail_threads, &tail_smem, &tail_blocks, &Ptail);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "resident tail kernel: %s", cudaGetErrorString(e)); return MMPC_ERR_CUDA; }
+    // hand over at this many times the blocks in flight.  A/B on a B200 (65,536-batch / closed-loop sub-batch of 5,461, ms):
+    // 1: 373 / 32.0, 2: 367 / 31.3, 4: 362 / 31.1, 8: 358 / 31.2, 16: 358 / 31.2 -- the queue keeps 296 blocks busy while the
+    // many instances that need only a few more iterations drain, and none of them waits for a 300 us round
+    static const int tail_mult = getenv("MMPC_TAIL_MULT") ? atoi(getenv("MMPC_TAIL_MULT")) : 8;
+    tail_hand = tail_blocks * (tail_mult > 0 ? tail_mult : 1);
   }
   std::vector<long long> ub;
   {
@@ -407,10 +412,10 @@ static int graph_build(MmpcHandle* h, int32_t B, int slot) {
     long long v = B;
     ub.push_back(v);
     while (v > 2 * t_team) { v = (v + 1) / 2; ub.push_back(v); }
-    for (long long t : {t_team, t_parts, t_floor}) if (t > 0 && t < ub.back() && t > tail_blocks) ub.push_back(t);
+    for (long long t : {t_team, t_parts, t_floor}) if (t > 0 && t < ub.back() && t > tail_hand) ub.push_back(t);
   }
   for (size_t c = 0; c < ub.size(); ++c) {
-    const int low = c + 1 < ub.size() ? (int)ub[c + 1] : tail_blocks;   // run this class while more than `low` instances are active
+    const int low = c + 1 < ub.size() ? (int)ub[c + 1] : tail_hand;   // run this class while more than `low` instances are active
     cudaGraphConditionalHandle hnd;
     CK(cudaGraphConditionalHandleCreate(&hnd, g, 0, 0));
     // entry condition: the trial list of the last round (parity 0 rounds write list 2) holds every active instance
