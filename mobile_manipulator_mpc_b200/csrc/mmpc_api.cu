@@ -403,6 +403,9 @@ static int graph_build(MmpcHandle* h, int32_t B, int slot) {
     // many instances that need only a few more iterations drain, and none of them waits for a 300 us round
     static const int tail_mult = getenv("MMPC_TAIL_MULT") ? atoi(getenv("MMPC_TAIL_MULT")) : 8;
     tail_hand = tail_blocks * (tail_mult > 0 ? tail_mult : 1);
+    // ... but never more than an eighth of the batch: the bulk belongs to the streaming kernels (B = 4,096 in three contexts:
+    // 187 k solves/s with the hand-over at 296, 177 k at 2,368)
+    if (tail_hand > B / 8) tail_hand = B / 8 > tail_blocks ? B / 8 : tail_blocks;
   }
   std::vector<long long> ub;
   {
