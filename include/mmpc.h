@@ -98,7 +98,7 @@ enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_STAGED = 3,
        MMPC_KERNEL_STAGED_HOSTLOOP = 7, /* STAGED with the host sequencing the rounds instead of the CUDA graph    */
        MMPC_KERNEL_RESIDENT = 8         /* one thread block per instance, the whole solver state of the instance in shared memory,
                                            persistent blocks on an atomic work queue (csrc/mmpc_resident.cu): the latency path.
-                                           AUTO takes it for batches of at most fourteen instances per SM when the state fits
+                                           AUTO takes it for batches of at most four instances per SM when the state fits
                                            (N = 20 with 16 circles: 112 KB, two blocks per SM); MMPC_ERR_UNSUPPORTED if it
                                            does not fit (N = 40) */ };
 

@@ -49,7 +49,7 @@ class BatchSolver:
             self.set_kernel(kernel)
 
     def set_kernel(self, kernel):
-        """'auto' ('resident' for at most fourteen instances per SM when the instance fits in shared memory, else 'staged') | 'staged' (phase kernels over active lists, one
+        """'auto' ('resident' for at most four instances per SM when the instance fits in shared memory, else 'staged') | 'staged' (phase kernels over active lists, one
         CUDA graph per solve) | 'resident' (one thread block per instance, state in shared memory) | A/B references:
         'staged_hostloop' (the host sequences the rounds), 'staged_thread', 'staged_unfused', 'staged_fat'."""
         k = {"auto": _abi.KERNEL_AUTO, "staged": _abi.KERNEL_STAGED, "staged_thread": _abi.KERNEL_STAGED_THREAD,

@@ -556,12 +556,12 @@ static int launch_staged(MmpcHandle* h, int32_t B, const MmpcBatchIn* in, const 
   staged_set_io_kernel<<<1, 1, 0, st>>>(io, h->sg.io, h->queue + 1);
   CK(cudaGetLastError());
   // the resident kernel: forced, or AUTO's choice for small batches when the instance fits in shared memory.  Measured on a
-  // B200 (config 3, reference NLP, resident / staged ms): B = 1 4.0 / 5.2, 148 14.5 / 31.8, 592 19.1 / 39.4, 1,024 32.4 / 47.7,
-  // 2,048 50.4 / 51.5 -- the staged solver's floor is the launch latency of its ~270 rounds, the resident kernel's slope is
-  // one instance (two at a time) per SM.  Other shapes (scripts/crossover.py): N = 40 with moving obstacles (one block per SM)
-  // 1,480 171 / 181; 3 circles, 2 planes 2,960 67 / 80.  MMPC_AUTO_RESIDENT = largest batch, in instances per SM, AUTO sends
-  // there (0: never).
-  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 14;
+  // B200 (reference NLP, resident / staged with its resident tail, ms; scripts/crossover.py): config 3 shapes B = 1 3.5 / -,
+  // 148 12.8 / 13.5, 592 16.6 / 23.5, 1,024 28.2 / 26.3, 2,048 43.6 / 29.9; 3 circles, 2 planes 592 17.2 / 17.5, 1,480
+  // 26.9 / 22.3; N = 40 with moving obstacles 444 59.7 / 64.5, 1,480 172 / 130.  Since the staged solve hands its tail to the
+  // resident kernel the two differ little for a few hundred instances; beyond, the bulk belongs to the streaming kernels.
+  // MMPC_AUTO_RESIDENT = largest batch, in instances per SM, AUTO sends to the resident kernel (0: never).
+  static const int auto_resident = getenv("MMPC_AUTO_RESIDENT") ? atoi(getenv("MMPC_AUTO_RESIDENT")) : 4;
   const bool pose = h->cfg.model == MMPC_MODEL_POSEREF;   // compiled into the pose build of the resident kernel only
   const bool fits = (pose ? mmpc_resident_pose_smem_bytes(&h->cfg) : mmpc_resident_smem_bytes(&h->cfg)) <= h->smem_optin;
   if (pose && !fits) { snprintf(g_err, sizeof g_err, "MMPC_MODEL_POSEREF runs on the resident kernel; this horizon does not fit in shared memory"); return MMPC_ERR_UNSUPPORTED; }

@@ -4,7 +4,7 @@ sys.path.insert(0, '/root/repo')
 import torch
 from mobile_manipulator_mpc_b200 import scenarios
 from mobile_manipulator_mpc_b200.batch_solver import BatchSolver
-for cid, B in ((5, 148), (5, 444), (5, 740), (5, 1480), (2, 1480), (2, 2960), (1, 148)):
+for cid, B in ((3, 148), (3, 296), (3, 592), (3, 1024), (3, 2048), (2, 592), (2, 1480), (2, 2960), (5, 148), (5, 444), (5, 1480)):
     b = scenarios.make_batch(cid, B)
     r = {}
     for kern in ("resident", "staged"):
