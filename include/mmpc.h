@@ -100,7 +100,7 @@ enum { MMPC_KERNEL_AUTO = 0, MMPC_KERNEL_STAGED = 3,
                                            persistent blocks on an atomic work queue (csrc/mmpc_resident.cu): the latency path.
                                            AUTO takes it for batches of at most four instances per SM when the state fits
                                            (N = 20 with 16 circles: 112 KB, two blocks per SM); MMPC_ERR_UNSUPPORTED if it
-                                           does not fit (N = 40) */ };
+                                           does not fit (N = 63) */ };
 
 typedef struct MmpcConfig {
   int32_t N;             /* horizon; demo_wholebody_qref.py:11 uses 20, class default 10 (:11)   */
